@@ -1,0 +1,86 @@
+/*
+ * cmrag.h -- C ABI of libcmrag.so, the B200 (sm_100a) implementation of
+ * CLASSMATE-RAG's hybrid retrieval hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * reference is pure Python, so the binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md); classmate_rag_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *   - Every pointer marked "device" is CUDA device memory owned by the caller
+ *     (the library never allocates or frees caller tensors).  Work is enqueued
+ *     on `stream` (a cudaStream_t) and NOT synchronised, except the *_host
+ *     entry points, which copy from/to host buffers and synchronise.
+ *   - Row ids handed back are GLOBAL: local row + row_offset of the shard.
+ *   - Ranking order everywhere: score descending, then row id ascending
+ *     (reference: stable sorted(reverse=True) over insertion order,
+ *     rag/retrieval/bm25.py:199; hnswlib ascending distance,
+ *     rag/retrieval/vector_chroma.py:204-253).
+ *   - Returned scores are float64 and bit-identical to the CPU oracle
+ *     (oracle/np_oracle.py): a fast fp32 pass over-selects candidates, an exact
+ *     float64 pass in a pinned order rescores them.  out_flags bit 0
+ *     (CMR_FLAG_UNCERTIFIED) is set when the fp32 error bound could not prove
+ *     the over-selection sufficient; callers then retry with cmr_*_exhaustive
+ *     or a larger k.
+ *   - Return value: 0 on success, negative cmr_status otherwise; the message
+ *     is available from cmr_last_error() (thread-local).
+ */
+#ifndef CMRAG_H
+#define CMRAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cmr_stream_t; /* cudaStream_t */
+
+enum cmr_status {
+  CMR_OK = 0,
+  CMR_EINVAL = -1,       /* bad argument (maps to ValueError in the Python host) */
+  CMR_ECUDA = -2,        /* CUDA runtime error (RuntimeError) */
+  CMR_EWORKSPACE = -3,   /* workspace too small */
+  CMR_EUNSUPPORTED = -4  /* shape outside the compiled kernel set */
+};
+
+#define CMR_FLAG_UNCERTIFIED 1
+#define CMR_MAX_K 120          /* largest k one pass selects (k + slack <= 128) */
+#define CMR_SLACK 8            /* over-selection slack of the fp32 pass */
+
+const char* cmr_last_error(void);
+int cmr_version(void);
+/* sm count and compute capability of the current device */
+int cmr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * A1  Dense exact top-k.  Replaces the hnswlib search behind
+ *     ChromaVectorStore.query (rag/retrieval/vector_chroma.py:204-253).
+ *
+ *   emb        device, bf16 [n_rows, dim] row-major (dim % 8 == 0, 16 B aligned)
+ *   queries    device, bf16 [n_queries, dim]
+ *   row_mask   device, uint8 [n_rows] or NULL; 0 = row filtered out (`where`)
+ *   out_scores device, float64 [n_queries, k]  exact q.c  (distance = 1 - score)
+ *   out_ids    device, int64   [n_queries, k]  global row ids, -1 padded
+ *   out_counts device, int32   [n_queries]     valid entries per query
+ *   out_flags  device, int32   [n_queries]
+ *   cert_eps   absolute bound on |fp32 score - exact score| used by the
+ *              certificate (host passes dim * 2^-24 * |q| * max row norm)
+ * ---------------------------------------------------------------------- */
+size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k);
+
+int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
+                   const uint16_t* queries, int n_queries, int k,
+                   const uint8_t* row_mask, int64_t row_offset, double cert_eps,
+                   double* out_scores, int64_t* out_ids, int32_t* out_counts, int32_t* out_flags,
+                   void* workspace, size_t workspace_bytes, cmr_stream_t stream);
+
+/* fp32 -> bf16 (round to nearest even) on device; used for queries and upserts
+ * (E5 hands the store fp32, rag/embeddings/__init__.py:85-105). */
+int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMRAG_H */
