@@ -3,114 +3,202 @@
 // Replaces the hnswlib search behind ChromaVectorStore.query
 // (reference rag/retrieval/vector_chroma.py:204-253).  Two kernels:
 //
-//  dense_scan_kernel     HBM-streaming GEMV.  Every warp owns whole rows: a row
-//                        of D bf16 is D/8 16-byte vectors, lane l loads vectors
-//                        l, l+32, ... (fully coalesced 512 B per warp request,
-//                        L1 no-allocate), multiplies with the query kept in
-//                        registers as fp32, and a butterfly reduces the warp.
-//                        The score never goes to memory: it is packed with the
-//                        row into a 64-bit key and inserted into the warp's
-//                        register-resident top-KP list only if it beats the
-//                        list's current minimum (rare after warm-up).  At the
-//                        end the CTA merges its warps' lists in shared memory
-//                        and writes ONE sorted list of KP keys.
+//  dense_scan_kernel     HBM-streaming scan, bound by HBM bandwidth.  A warp owns
+//                        tiles of 16 consecutive rows.  Lane (g = lane/4,
+//                        t4 = lane%4) issues 16-byte streaming loads of rows g and
+//                        g+8 at column block t4 of every 32-column step, so one
+//                        warp request covers 8 rows x 64 contiguous bytes (whole
+//                        32 B sectors, every byte of the matrix fetched once).
+//                        The loaded registers ARE the A fragments of
+//                        mma.sync.m16n8k16 (the k index is permuted consistently
+//                        on both operands, which a dot product does not see);
+//                        the B fragments are the queries, staged once in shared
+//                        memory.  The tensor pipe does the multiply-accumulate in
+//                        fp32, so the SM issues ~9 instructions per row instead
+//                        of ~130 for unpack+FFMA+shuffle, and one pass scores up
+//                        to 8*NQ8 queries for the same bytes.  A ring of U units
+//                        (U*1 KiB per warp) keeps loads in flight across tiles.
+//                        Scores never go to memory: each is compared with the
+//                        CTA's admission threshold and, rarely, inserted into the
+//                        CTA-shared sorted list of KP keys in shared memory.
 //  dense_finalize_kernel one CTA per query: selects the KP best keys over all
 //                        CTA lists, rescoring each candidate exactly in float64
 //                        (pinned order, bit-identical to the oracle), orders by
 //                        (exact score desc, row asc) and writes the top k plus
 //                        the over-selection certificate.
 //
-// Algorithmic bytes per query: n_rows * dim * 2 (the matrix is read once).
+// Algorithmic bytes per scan pass: n_rows * dim * 2 (the matrix is read once,
+// for up to 32 queries).
 #include "topk.cuh"
 
 namespace cmr {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_U = 8;  // ring depth in 32-column units
 constexpr int FIN_THREADS = 1024;
 
-// NV: 16-byte vectors per lane per row (dim <= NV*256); R: rows in flight per warp.
-template <int NV, int R, int KPL>
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Rare path: at least one score of this tile reached one of the warp's thresholds.
+template <int NQ8, int KP>
+__device__ __forceinline__ void scan_tile_hits(const float (&c)[NQ8][4], long long r0, long long cta_hi,
+                                               int q_base, int n_queries,
+                                               const uint8_t* __restrict__ row_mask, u64* w_lists,
+                                               float* w_thr, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int m = 0; m < NQ8; ++m) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int q = m * 8 + 2 * t4 + (r & 1);
+      const long long row = r0 + g + ((r >> 1) ? 8 : 0);
+      bool hit = (c[m][r] >= w_thr[q]) && (row < cta_hi) && (q_base + q < n_queries);
+      if (hit && row_mask != nullptr) hit = row_mask[row] != 0;
+      unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const float s = __shfl_sync(0xFFFFFFFFu, c[m][r], src);
+        const int qq = m * 8 + 2 * (src & 3) + (r & 1);
+        const long long rr = r0 + (src >> 2) + ((r >> 1) ? 8 : 0);
+        warp_list_insert<KP>(w_lists + qq * KP, w_thr + qq, make_key(s, (u32)rr), lane);
+      }
+    }
+  }
+}
+
+// NQ8: query octets per pass; KPL: list entries per lane (KP = 32*KPL);
+// COLS_FULL: dim is a multiple of 32*U columns, no column predicate needed.
+template <int NQ8, int KPL, bool COLS_FULL>
 __global__ void __launch_bounds__(SCAN_THREADS)
-dense_scan_kernel(const uint4* __restrict__ emb, long long n_rows, int dim_vec,
-                  const uint4* __restrict__ queries, const uint8_t* __restrict__ row_mask,
-                  u64* __restrict__ part, long long rows_per_cta) {
+dense_scan_kernel(const uint4* __restrict__ emb, long long n_rows, int dim_vec, int steps_padded,
+                  const uint4* __restrict__ queries, int n_queries,
+                  const uint8_t* __restrict__ row_mask, u64* __restrict__ part,
+                  long long rows_per_cta, int q_stride_vec) {
   constexpr int KP = 32 * KPL;
-  __shared__ u64 s_lists[SCAN_WARPS * KP];
-  __shared__ u64 s_out[KP];
+  constexpr int NQ = 8 * NQ8;
+  constexpr int U = SCAN_U;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* s_q = reinterpret_cast<uint4*>(smem_raw);
+  u64* s_lists = reinterpret_cast<u64*>(s_q + (size_t)NQ * q_stride_vec);  // [warp][query][KP]
+  u64* s_out = s_lists + SCAN_WARPS * NQ * KP;                             // [KP]
+  float* s_thr = reinterpret_cast<float*>(s_out + KP);                     // [warp][query]
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int qi = blockIdx.y;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q_base = blockIdx.y * NQ;
 
-  float qf[NV][8];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int v = lane + 32 * j;
-    uint4 qv = make_uint4(0, 0, 0, 0);
-    if (v < dim_vec) qv = queries[(size_t)qi * dim_vec + v];
-    qf[j][0] = bf16lo(qv.x); qf[j][1] = bf16hi(qv.x);
-    qf[j][2] = bf16lo(qv.y); qf[j][3] = bf16hi(qv.y);
-    qf[j][4] = bf16lo(qv.z); qf[j][5] = bf16hi(qv.z);
-    qf[j][6] = bf16lo(qv.w); qf[j][7] = bf16hi(qv.w);
+  // stage the queries of this pass (zero padded) and initialise the lists
+  for (int idx = threadIdx.x; idx < NQ * q_stride_vec; idx += SCAN_THREADS) {
+    const int qr = idx / q_stride_vec, v = idx - qr * q_stride_vec;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (q_base + qr < n_queries && v < dim_vec) val = queries[(size_t)(q_base + qr) * dim_vec + v];
+    s_q[idx] = val;
   }
-
-  WarpList<KPL> list;
-  list.init();
+  for (int i = threadIdx.x; i < SCAN_WARPS * NQ * KP; i += SCAN_THREADS) s_lists[i] = 0ull;
+  for (int i = threadIdx.x; i < SCAN_WARPS * NQ; i += SCAN_THREADS)
+    s_thr[i] = (q_base + (i % NQ) < n_queries) ? -INFINITY : INFINITY;
+  __syncthreads();
+  u64* w_lists = s_lists + (size_t)warp * NQ * KP;
+  float* w_thr = s_thr + warp * NQ;
 
   const long long cta_lo = (long long)blockIdx.x * rows_per_cta;
   long long cta_hi = cta_lo + rows_per_cta;
   if (cta_hi > n_rows) cta_hi = n_rows;
 
-  for (long long r0 = cta_lo + (long long)warp * R; r0 < cta_hi; r0 += (long long)SCAN_WARPS * R) {
-    uint4 d[R][NV];
-    bool valid[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      const long long row = r0 + rr;
-      valid[rr] = row < cta_hi;
-      if (valid[rr] && row_mask != nullptr) valid[rr] = row_mask[row] != 0;
-      const uint4* src = emb + (size_t)row * dim_vec;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int v = lane + 32 * j;
-        d[rr][j] = make_uint4(0, 0, 0, 0);
-        if (valid[rr] && v < dim_vec) d[rr][j] = ldg_stream(src + v);
+  long long r0 = cta_lo + (long long)warp * 16;
+  if (r0 < cta_hi) {
+    const long long last_row = cta_hi - 1;
+    auto row_ptr = [&](long long r) {
+      if (r > last_row) r = last_row;  // clamp: loads stay in bounds, result ignored
+      return emb + (size_t)r * dim_vec + t4;
+    };
+    const uint4* pa = row_ptr(r0 + g);
+    const uint4* pb = row_ptr(r0 + g + 8);
+    uint4 xa[U], xb[U];
+    auto load_unit = [&](const uint4* a, const uint4* b, int t, int slot) {
+      if (COLS_FULL || (t * 4 + t4 < dim_vec)) {
+        xa[slot] = ldg_stream(a + t * 4);
+        xb[slot] = ldg_stream(b + t * 4);
+      } else {
+        xa[slot] = make_uint4(0, 0, 0, 0);
+        xb[slot] = make_uint4(0, 0, 0, 0);
       }
-    }
+    };
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      float acc0 = 0.f, acc1 = 0.f;
+    for (int u = 0; u < U; ++u) load_unit(pa, pb, u, u);
+
+    const uint4* sq_lane = s_q + (size_t)g * q_stride_vec + t4;
+
+    while (r0 < cta_hi) {
+      const long long r0n = r0 + (long long)SCAN_WARPS * 16;
+      const bool has_next = r0n < cta_hi;
+      const uint4* pan = row_ptr(r0n + g);
+      const uint4* pbn = row_ptr(r0n + g + 8);
+      float c[NQ8][4];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const uint4 x = d[rr][j];
-        acc0 = fmaf(bf16lo(x.x), qf[j][0], acc0);
-        acc1 = fmaf(bf16hi(x.x), qf[j][1], acc1);
-        acc0 = fmaf(bf16lo(x.y), qf[j][2], acc0);
-        acc1 = fmaf(bf16hi(x.y), qf[j][3], acc1);
-        acc0 = fmaf(bf16lo(x.z), qf[j][4], acc0);
-        acc1 = fmaf(bf16hi(x.z), qf[j][5], acc1);
-        acc0 = fmaf(bf16lo(x.w), qf[j][6], acc0);
-        acc1 = fmaf(bf16hi(x.w), qf[j][7], acc1);
+      for (int m = 0; m < NQ8; ++m) c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f;
+
+      for (int t0 = 0; t0 < steps_padded; t0 += U) {
+        const bool last = (t0 + U >= steps_padded);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u;
+#pragma unroll
+          for (int m = 0; m < NQ8; ++m) {
+            const uint4 qv = sq_lane[(size_t)m * 8 * q_stride_vec + t * 4];
+            mma_bf16_16816(c[m], xa[u].x, xb[u].x, xa[u].y, xb[u].y, qv.x, qv.y);
+            mma_bf16_16816(c[m], xa[u].z, xb[u].z, xa[u].w, xb[u].w, qv.z, qv.w);
+          }
+          if (!last) load_unit(pa, pb, t + U, u);
+          else if (has_next) load_unit(pan, pbn, u, u);
+        }
       }
-      float s = acc0 + acc1;
+
+      // admission test against the warp's thresholds (fast path: 4*NQ8 compares)
+      bool pass = false;
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
-      if (valid[rr]) {  // warp-uniform
-        const u64 key = make_key(s, (u32)(r0 + rr));
-        if (key > list.kmin) list.insert(key, lane);
+      for (int m = 0; m < NQ8; ++m) {
+        const float2 th = *reinterpret_cast<const float2*>(w_thr + m * 8 + 2 * t4);
+        pass |= (c[m][0] >= th.x) | (c[m][2] >= th.x) | (c[m][1] >= th.y) | (c[m][3] >= th.y);
       }
+      if (__any_sync(0xFFFFFFFFu, pass))
+        scan_tile_hits<NQ8, KP>(c, r0, cta_hi, q_base, n_queries, row_mask, w_lists, w_thr, lane);
+
+      r0 = r0n;
+      pa = pan;
+      pb = pbn;
     }
   }
 
-  // CTA merge: warps' lists -> one sorted list of KP keys
-  list.store(s_lists + warp * KP, lane);
-  for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) s_out[i] = 0ull;
-  __syncthreads();
-  block_merge_lists<KP>(s_lists, SCAN_WARPS, s_out, threadIdx.x, SCAN_THREADS);
-  __syncthreads();
-  u64* dst = part + ((size_t)qi * gridDim.x + blockIdx.x) * KP;
-  for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) dst[i] = s_out[i];
+  // CTA merge: for every query, the warps' lists -> one sorted list of KP keys
+  for (int q = 0; q < NQ; ++q) {
+    __syncthreads();
+    if (q_base + q >= n_queries) break;  // uniform
+    for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) s_out[i] = 0ull;
+    __syncthreads();
+    for (int e = threadIdx.x; e < SCAN_WARPS * KP; e += SCAN_THREADS) {
+      const int a = e / KP;
+      const u64 kk = s_lists[((size_t)a * NQ + q) * KP + (e - a * KP)];
+      if (kk == 0ull) continue;
+      int rank = e - a * KP;
+      for (int b = 0; b < SCAN_WARPS && rank < KP; ++b) {
+        if (b == a) continue;
+        rank += count_greater(s_lists + ((size_t)b * NQ + q) * KP, KP, kk);
+      }
+      if (rank < KP) s_out[rank] = kk;
+    }
+    __syncthreads();
+    u64* dst = part + ((size_t)(q_base + q) * gridDim.x + blockIdx.x) * KP;
+    for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) dst[i] = s_out[i];
+  }
 }
 
 template <int KPL>
@@ -123,15 +211,15 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
                       int* __restrict__ out_flags) {
   constexpr int KP = 32 * KPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* s_heads = reinterpret_cast<u64*>(smem_raw);
-  u64* s_stage = s_heads + n_lists;
-  u64* s_out = s_stage + KP * KP;
+  u64* s_heads = reinterpret_cast<u64*>(smem_raw);  // [n_lists + 1]
+  u64* s_buf = s_heads + n_lists + 1;               // [KP*KP]
+  u64* s_out = s_buf + KP * KP;
   double* s_score = reinterpret_cast<double*>(s_out + KP);
-  int* s_q = reinterpret_cast<int*>(s_score + KP);
+  int* s_cnt = reinterpret_cast<int*>(s_score + KP);
 
   const int qi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  block_select_from_lists<KP>(part + (size_t)qi * n_lists * KP, n_lists, s_heads, s_stage, s_q, s_out,
+  block_select_from_lists<KP>(part + (size_t)qi * n_lists * KP, n_lists, s_heads, s_buf, s_cnt, s_out,
                               tid, FIN_THREADS);
 
   // exact rescoring, one warp per candidate
@@ -145,12 +233,10 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
   }
   __syncthreads();
 
-  // count valid (keys are sorted, zeros last)
-  int n_valid = count_greater(s_out, KP, 0ull);
+  const int n_valid = count_greater(s_out, KP, 0ull);  // keys sorted, zeros last
   const int n_out = n_valid < k ? n_valid : k;
 
   // final order: (exact score desc, row asc) by counting rank
-  double kth_exact = 0.0;
   if (tid < n_valid) {
     const double s = s_score[tid];
     const u32 r = key_row(s_out[tid]);
@@ -169,9 +255,8 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
       // fp32 score of the last selected key, hence exact score <= that + eps.
       int flag = 0;
       if (n_valid == KP) {
-        kth_exact = s;
         const double last32 = (double)key_score(s_out[KP - 1]);
-        if (!(kth_exact > last32 + cert_eps)) flag = CMR_FLAG_UNCERTIFIED;
+        if (!(s > last32 + cert_eps)) flag = CMR_FLAG_UNCERTIFIED;
       }
       out_flags[qi] = flag;
     }
@@ -197,82 +282,82 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __re
 
 // ---- host side -------------------------------------------------------------
 
+typedef void (*scan_fn_t)(const uint4*, long long, int, int, const uint4*, int, const uint8_t*, u64*,
+                          long long, int);
+
 struct DensePlan {
-  int kpl;             // keys per lane (1, 2, 4)
-  int nv;              // vectors per lane
-  int grid_x;          // CTAs along rows
+  int kpl;           // list entries per lane: KP = 32*kpl
+  int nq8;           // query octets per pass
+  int passes;        // grid.y
+  int steps_padded;  // 32-column steps, rounded up to the ring depth
+  int q_stride_vec;  // shared-memory stride of one staged query, in 16 B vectors
+  bool cols_full;
+  size_t smem;
+  int grid_x;
   long long rows_per_cta;
+  scan_fn_t fn;
 };
 
-typedef void (*scan_fn_t)(const uint4*, long long, int, const uint4*, const uint8_t*, u64*, long long);
-
-template <int KPL>
-static scan_fn_t scan_fn_for_nv(int nv) {
-  switch (nv) {
-    case 1: return dense_scan_kernel<1, 4, KPL>;
-    case 2: return dense_scan_kernel<2, 4, KPL>;
-    case 3: return dense_scan_kernel<3, 4, KPL>;
-    case 4: return dense_scan_kernel<4, 4, KPL>;
-    case 5: case 6: return dense_scan_kernel<6, 2, KPL>;
-    case 7: case 8: return dense_scan_kernel<8, 2, KPL>;
-    default: return nullptr;
-  }
+template <int NQ8, int KPL>
+static scan_fn_t pick_cols(bool full) {
+  return full ? dense_scan_kernel<NQ8, KPL, true> : dense_scan_kernel<NQ8, KPL, false>;
+}
+template <int NQ8>
+static scan_fn_t pick_kpl(int kpl, bool full) {
+  return kpl == 1 ? pick_cols<NQ8, 1>(full) : (kpl == 2 ? pick_cols<NQ8, 2>(full) : pick_cols<NQ8, 4>(full));
+}
+static scan_fn_t pick_scan(int nq8, int kpl, bool full) {
+  return nq8 == 1 ? pick_kpl<1>(kpl, full) : (nq8 == 2 ? pick_kpl<2>(kpl, full) : pick_kpl<4>(kpl, full));
 }
 
-static scan_fn_t scan_fn(int nv, int kpl) {
-  return kpl == 1 ? scan_fn_for_nv<1>(nv) : (kpl == 2 ? scan_fn_for_nv<2>(nv) : scan_fn_for_nv<4>(nv));
-}
-
-// resident CTAs per SM of the scan kernel instance (persistent grid sizing)
-static int scan_ctas_per_sm(int nv, int kpl) {
-  static int cache[9][5] = {{0}};
-  if (nv < 1 || nv > 8) return 0;
-  if (cache[nv][kpl] == 0) {
-    int n = 0;
-    scan_fn_t fn = scan_fn(nv, kpl);
-    if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, SCAN_THREADS, 0) != cudaSuccess || n <= 0) {
-      set_error("occupancy query failed for dense_scan<nv=%d,kpl=%d>", nv, kpl);
-      return 0;
-    }
-    cache[nv][kpl] = n;
-  }
-  return cache[nv][kpl];
-}
-
-static int make_plan(long long n_rows, int dim, int k, DensePlan* p) {
+static int make_plan(long long n_rows, int dim, int n_queries, int k, DensePlan* p) {
   const int kp_needed = k + CMR_SLACK;
   p->kpl = kp_needed <= 32 ? 1 : (kp_needed <= 64 ? 2 : 4);
-  const int dim_vec = dim / 8;
-  p->nv = (dim_vec + 31) / 32;
+  p->nq8 = n_queries <= 8 ? 1 : (n_queries <= 16 ? 2 : 4);
+  if (p->kpl > 1) p->nq8 = 1;  // warp-private lists: keep them within shared memory
+  p->passes = (n_queries + 8 * p->nq8 - 1) / (8 * p->nq8);
+  const int steps = (dim + 31) / 32;
+  p->steps_padded = (steps + SCAN_U - 1) / SCAN_U * SCAN_U;
+  p->cols_full = (dim == p->steps_padded * 32);
+  p->q_stride_vec = p->steps_padded * 4 + 4;  // +64 B: conflict-free LDS.128 across the 8 query rows
+  const int nq = 8 * p->nq8, kp = 32 * p->kpl;
+  p->smem = (size_t)nq * p->q_stride_vec * 16 + (size_t)SCAN_WARPS * nq * kp * 8 + (size_t)kp * 8 +
+            (size_t)SCAN_WARPS * nq * 4;
+  p->fn = pick_scan(p->nq8, p->kpl, p->cols_full);
   const int sms = sm_count();
   if (sms <= 0) return CMR_ECUDA;
-  const int per_sm = scan_ctas_per_sm(p->nv, p->kpl);
-  if (per_sm <= 0) return CMR_EUNSUPPORTED;
-  long long ctas = (long long)sms * per_sm;
-  // keep at least one full pass of work per warp group
-  const long long min_rows = (long long)SCAN_WARPS * 4;
+  if (p->smem > 200 * 1024) {
+    set_error("dense scan shared memory %zu too large", p->smem);
+    return CMR_EUNSUPPORTED;
+  }
+  // occupancy of this (kernel, shared memory) pair, cached: the plan runs per call
+  struct OccEntry { scan_fn_t fn; size_t smem; int dev; int per_sm; };
+  static OccEntry occ_cache[64];
+  static int occ_n = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int per_sm = 0;
+  for (int i = 0; i < occ_n; ++i)
+    if (occ_cache[i].fn == p->fn && occ_cache[i].smem == p->smem && occ_cache[i].dev == dev) per_sm = occ_cache[i].per_sm;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_scan)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, SCAN_THREADS, p->smem);
+    if (e != cudaSuccess || per_sm <= 0) {
+      set_error("occupancy query failed for dense_scan (nq8=%d kpl=%d smem=%zu)", p->nq8, p->kpl, p->smem);
+      return CMR_ECUDA;
+    }
+    if (occ_n < 64) occ_cache[occ_n++] = OccEntry{p->fn, p->smem, dev, per_sm};
+  }
+  long long ctas = (long long)sms * per_sm;  // persistent: exactly the resident CTAs
+  const long long min_rows = (long long)SCAN_WARPS * 16;
   long long max_ctas = (n_rows + min_rows - 1) / min_rows;
   if (max_ctas < 1) max_ctas = 1;
   if (ctas > max_ctas) ctas = max_ctas;
   p->grid_x = (int)ctas;
   long long rpc = (n_rows + ctas - 1) / ctas;
-  // round rows_per_cta up to a whole number of warp-group steps for alignment
-  p->rows_per_cta = rpc < 1 ? 1 : rpc;
-  return CMR_OK;
-}
-
-static int launch_scan(const DensePlan& p, const uint16_t* emb, long long n_rows, int dim,
-                       const uint16_t* queries, int n_queries, const uint8_t* row_mask, u64* part,
-                       cudaStream_t st) {
-  scan_fn_t fn = scan_fn(p.nv, p.kpl);
-  if (!fn) {
-    set_error("dim %d not supported (max 2048)", dim);
-    return CMR_EUNSUPPORTED;
-  }
-  dim3 grid(p.grid_x, n_queries);
-  fn<<<grid, SCAN_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(emb), n_rows, dim / 8,
-                                    reinterpret_cast<const uint4*>(queries), row_mask, part,
-                                    p.rows_per_cta);
+  rpc = (rpc + 15) / 16 * 16;  // whole 16-row tiles
+  p->rows_per_cta = rpc < 16 ? 16 : rpc;
   return CMR_OK;
 }
 
@@ -282,17 +367,19 @@ static int launch_finalize(const DensePlan& p, const u64* part, const uint16_t* 
                            double cert_eps, double* out_scores, long long* out_ids, int* out_counts,
                            int* out_flags, cudaStream_t st) {
   constexpr int KP = 32 * KPL;
-  const size_t smem = (size_t)p.grid_x * 8 + (size_t)KP * KP * 8 + KP * 8 + KP * 8 + (KP + 1) * 4 + 16;
-  static bool attr_set[5] = {false, false, false, false, false};
-  if (!attr_set[KPL]) {
-    cudaError_t e = cudaFuncSetAttribute(dense_finalize_kernel<KPL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_finalize)");
-    attr_set[KPL] = true;
-  }
+  const size_t smem = (size_t)(p.grid_x + 1) * 8 + (size_t)KP * KP * 8 + KP * 8 + KP * 8 + 16;
   if (smem > 200 * 1024) {
     set_error("finalize shared memory %zu too large", smem);
     return CMR_EUNSUPPORTED;
+  }
+  static int attr_dev_mask = 0;  // per-device one-time opt-in to large dynamic shared memory
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(dense_finalize_kernel<KPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_finalize)");
+    attr_dev_mask |= (1 << dev);
   }
   dense_finalize_kernel<KPL><<<n_queries, FIN_THREADS, smem, st>>>(
       part, p.grid_x, emb, dim, queries, row_offset, k, cert_eps, out_scores, out_ids, out_counts,
@@ -306,8 +393,11 @@ using namespace cmr;
 
 extern "C" size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
   DensePlan p;
-  if (n_rows < 0 || dim <= 0 || n_queries <= 0 || k <= 0 || k > CMR_MAX_K) return 0;
-  if (make_plan(n_rows, dim, k, &p) != CMR_OK) return 0;
+  if (n_rows < 0 || dim <= 0 || dim % 8 != 0 || dim > 2048 || n_queries <= 0 || k <= 0 || k > CMR_MAX_K) {
+    set_error("cmr_dense_workspace_bytes: bad shape");
+    return 0;
+  }
+  if (make_plan(n_rows, dim, n_queries, k, &p) != CMR_OK) return 0;
   return (size_t)n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
 }
 
@@ -318,14 +408,14 @@ extern "C" int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim, cons
                               size_t workspace_bytes, cmr_stream_t stream) {
   CMR_CHECK_ARG(n_rows >= 0 && n_rows < 0xFFFFFFFFll, "n_rows %lld out of range", (long long)n_rows);
   CMR_CHECK_ARG(dim > 0 && dim % 8 == 0 && dim <= 2048, "dim %d must be a multiple of 8, <= 2048", dim);
-  CMR_CHECK_ARG(n_queries > 0 && n_queries <= 65535, "n_queries %d out of range", n_queries);
+  CMR_CHECK_ARG(n_queries > 0 && n_queries <= 65535 * 8, "n_queries %d out of range", n_queries);
   CMR_CHECK_ARG(k > 0 && k <= CMR_MAX_K, "k %d out of range (1..%d)", k, CMR_MAX_K);
   CMR_CHECK_ARG(queries && out_scores && out_ids && out_counts && out_flags, "null output/query pointer");
   CMR_CHECK_ARG(n_rows == 0 || emb, "null embedding matrix");
   CMR_CHECK_ARG(((uintptr_t)emb % 16) == 0 && ((uintptr_t)queries % 16) == 0, "emb/queries must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   DensePlan p;
-  int rc = make_plan(n_rows, dim, k, &p);
+  int rc = make_plan(n_rows, dim, n_queries, k, &p);
   if (rc != CMR_OK) return rc;
   const size_t need = (size_t)n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
   if (workspace_bytes < need || !workspace) {
@@ -333,21 +423,15 @@ extern "C" int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim, cons
     return CMR_EWORKSPACE;
   }
   u64* part = (u64*)workspace;
-  const uint16_t* q = queries;
+  dim3 grid(p.grid_x, p.passes);
+  p.fn<<<grid, SCAN_THREADS, p.smem, st>>>(reinterpret_cast<const uint4*>(emb), n_rows, dim / 8,
+                                           p.steps_padded, reinterpret_cast<const uint4*>(queries),
+                                           n_queries, row_mask, part, p.rows_per_cta, p.q_stride_vec);
   long long* ids = (long long*)out_ids;
   switch (p.kpl) {
-    case 1:
-      rc = launch_scan(p, emb, n_rows, dim, q, n_queries, row_mask, part, st);
-      if (rc == CMR_OK) rc = launch_finalize<1>(p, part, emb, dim, q, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st);
-      break;
-    case 2:
-      rc = launch_scan(p, emb, n_rows, dim, q, n_queries, row_mask, part, st);
-      if (rc == CMR_OK) rc = launch_finalize<2>(p, part, emb, dim, q, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st);
-      break;
-    default:
-      rc = launch_scan(p, emb, n_rows, dim, q, n_queries, row_mask, part, st);
-      if (rc == CMR_OK) rc = launch_finalize<4>(p, part, emb, dim, q, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st);
-      break;
+    case 1: rc = launch_finalize<1>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
+    case 2: rc = launch_finalize<2>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
+    default: rc = launch_finalize<4>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
   }
   if (rc != CMR_OK) return rc;
   CMR_CUDA(cudaGetLastError());

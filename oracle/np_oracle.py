@@ -7,9 +7,11 @@ Numerical contracts (shared with the CUDA path, stated in DESIGN.md):
 
 * Dense score.  The corpus matrix and the query are bf16 (round-to-nearest-even
   of the fp32 E5 output).  ``exact score = dot(q, c)`` evaluated in float64 in a
-  FIXED order: 32 partial sums, partial ``l`` adds the (exact) products of
-  elements ``l, l+32, l+64, ...`` sequentially, then the 32 partials are
-  combined by the halving tree ``a[l] += a[l+off]`` for off = 16, 8, 4, 2, 1.
+  FIXED order: the row is cut into 16-byte vectors of 8 elements; 32 partial
+  sums, partial ``l`` owns vectors ``l, l+32, l+64, ...`` and adds the (exact)
+  products of their elements sequentially (vector by vector, element by
+  element); then the 32 partials are combined by the halving tree
+  ``a[l] += a[l+off]`` for off = 16, 8, 4, 2, 1.  (dim must be a multiple of 8.)
   A bf16*bf16 product is exact in float64, so the only roundings are the adds,
   and their order is pinned -> the CUDA rescoring kernel reproduces the value
   bit for bit.  ``distance = 1.0 - score`` (reference: hnswlib cosine space on
@@ -76,9 +78,10 @@ def exact_dots(q_bits: np.ndarray, c_bits: np.ndarray, chunk: int = 8192) -> np.
     if c_bits.ndim == 1:
         c_bits = c_bits[None, :]
     n, d = c_bits.shape
-    assert q_bits.shape[0] == d
-    steps = (d + _LANES - 1) // _LANES
-    dp = steps * _LANES
+    assert q_bits.shape[0] == d and d % 8 == 0
+    nvec = d // 8
+    per_lane = (nvec + _LANES - 1) // _LANES
+    dp = per_lane * _LANES * 8
     q = np.zeros(dp, dtype=np.float64)
     q[:d] = bf16_bits_to_f64(q_bits)
     out = np.empty(n, dtype=np.float64)
@@ -86,10 +89,11 @@ def exact_dots(q_bits: np.ndarray, c_bits: np.ndarray, chunk: int = 8192) -> np.
         hi = min(n, lo + chunk)
         c = np.zeros((hi - lo, dp), dtype=np.float64)
         c[:, :d] = bf16_bits_to_f64(c_bits[lo:hi])
-        prod = (c * q).reshape(hi - lo, steps, _LANES)
+        prod = (c * q).reshape(hi - lo, per_lane, _LANES, 8)
         acc = np.zeros((hi - lo, _LANES), dtype=np.float64)
-        for t in range(steps):  # sequential per lane, in element order
-            acc = acc + prod[:, t, :]
+        for j in range(per_lane):      # lane l: vectors l, l+32, ... in order
+            for e in range(8):         # elements of a vector in order
+                acc = acc + prod[:, j, :, e]
         out[lo:hi] = _tree32(acc)
     return out
 

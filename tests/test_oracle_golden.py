@@ -126,13 +126,15 @@ def test_bm25_known_answers():
 
 def test_exact_dot_order_is_the_documented_one():
     rng = np.random.default_rng(5)
-    for d in (8, 32, 40, 768, 1024):
+    for d in (8, 32, 40, 264, 768, 1024):
         a = o.f32_to_bf16_bits(rng.standard_normal(d).astype(np.float32))
         b = o.f32_to_bf16_bits(rng.standard_normal(d).astype(np.float32))
         af, bf = o.bf16_bits_to_f64(a), o.bf16_bits_to_f64(b)
         acc = [0.0] * 32
-        for i in range(d):
-            acc[i % 32] = acc[i % 32] + af[i] * bf[i]
+        for v in range(d // 8):            # vector v belongs to lane v % 32
+            for e in range(8):
+                i = 8 * v + e
+                acc[v % 32] = acc[v % 32] + af[i] * bf[i]
         for off in (16, 8, 4, 2, 1):
             for l in range(off):
                 acc[l] = acc[l] + acc[l + off]
