@@ -58,7 +58,9 @@ __device__ __forceinline__ void scan_tile_hits(const float (&c)[NQ8][4], long lo
     for (int r = 0; r < 4; ++r) {
       const int q = m * 8 + 2 * t4 + (r & 1);
       const long long row = r0 + g + ((r >> 1) ? 8 : 0);
-      bool hit = (c[m][r] >= w_thr[q]) && (row < cta_hi) && (q_base + q < n_queries);
+      // strict '>' is exact: a warp sees its rows in ascending order, so a score that
+      // only ties the list's last entry always loses the row tie-break
+      bool hit = (c[m][r] > w_thr[q]) && (row < cta_hi) && (q_base + q < n_queries);
       if (hit && row_mask != nullptr) hit = row_mask[row] != 0;
       unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
       while (bal) {
@@ -67,7 +69,12 @@ __device__ __forceinline__ void scan_tile_hits(const float (&c)[NQ8][4], long lo
         const float s = __shfl_sync(0xFFFFFFFFu, c[m][r], src);
         const int qq = m * 8 + 2 * (src & 3) + (r & 1);
         const long long rr = r0 + (src >> 2) + ((r >> 1) ? 8 : 0);
-        warp_list_insert<KP>(w_lists + qq * KP, w_thr + qq, make_key(s, (u32)rr), lane);
+        u64 new_last = 0ull;
+        if (warp_list_insert<KP, u64>(w_lists + qq * KP, make_key(s, (u32)rr), lane, new_last) &&
+            new_last != 0ull) {
+          if (lane == 0) w_thr[qq] = key_score(new_last);
+          __syncwarp();
+        }
       }
     }
   }
@@ -167,7 +174,7 @@ dense_scan_kernel(const uint4* __restrict__ emb, long long n_rows, int dim_vec, 
 #pragma unroll
       for (int m = 0; m < NQ8; ++m) {
         const float2 th = *reinterpret_cast<const float2*>(w_thr + m * 8 + 2 * t4);
-        pass |= (c[m][0] >= th.x) | (c[m][2] >= th.x) | (c[m][1] >= th.y) | (c[m][3] >= th.y);
+        pass |= (c[m][0] > th.x) | (c[m][2] > th.x) | (c[m][1] > th.y) | (c[m][3] > th.y);
       }
       if (__any_sync(0xFFFFFFFFu, pass))
         scan_tile_hits<NQ8, KP>(c, r0, cta_hi, q_base, n_queries, row_mask, w_lists, w_thr, lane);
@@ -184,17 +191,8 @@ dense_scan_kernel(const uint4* __restrict__ emb, long long n_rows, int dim_vec, 
     if (q_base + q >= n_queries) break;  // uniform
     for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) s_out[i] = 0ull;
     __syncthreads();
-    for (int e = threadIdx.x; e < SCAN_WARPS * KP; e += SCAN_THREADS) {
-      const int a = e / KP;
-      const u64 kk = s_lists[((size_t)a * NQ + q) * KP + (e - a * KP)];
-      if (kk == 0ull) continue;
-      int rank = e - a * KP;
-      for (int b = 0; b < SCAN_WARPS && rank < KP; ++b) {
-        if (b == a) continue;
-        rank += count_greater(s_lists + ((size_t)b * NQ + q) * KP, KP, kk);
-      }
-      if (rank < KP) s_out[rank] = kk;
-    }
+    block_merge_lists<KP, u64>(s_lists + (size_t)q * KP, SCAN_WARPS, (size_t)NQ * KP, s_out, threadIdx.x,
+                               SCAN_THREADS);
     __syncthreads();
     u64* dst = part + ((size_t)(q_base + q) * gridDim.x + blockIdx.x) * KP;
     for (int i = threadIdx.x; i < KP; i += SCAN_THREADS) dst[i] = s_out[i];
@@ -212,15 +210,16 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
   constexpr int KP = 32 * KPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* s_heads = reinterpret_cast<u64*>(smem_raw);  // [n_lists + 1]
-  u64* s_buf = s_heads + n_lists + 1;               // [KP*KP]
-  u64* s_out = s_buf + KP * KP;
+  constexpr int CAP = KP * KP < 4096 ? KP * KP : 4096;
+  u64* s_buf = s_heads + n_lists + 1;               // [CAP]
+  u64* s_out = s_buf + CAP;
   double* s_score = reinterpret_cast<double*>(s_out + KP);
   int* s_cnt = reinterpret_cast<int*>(s_score + KP);
 
   const int qi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  block_select_from_lists<KP>(part + (size_t)qi * n_lists * KP, n_lists, s_heads, s_buf, s_cnt, s_out,
-                              tid, FIN_THREADS);
+  block_select_from_lists<KP, CAP, u64>(part + (size_t)qi * n_lists * KP, n_lists, s_heads, s_buf, s_cnt,
+                                   s_out, tid, FIN_THREADS);
 
   // exact rescoring, one warp per candidate
   const uint16_t* q = queries + (size_t)qi * dim;
@@ -233,7 +232,7 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
   }
   __syncthreads();
 
-  const int n_valid = count_greater(s_out, KP, 0ull);  // keys sorted, zeros last
+  const int n_valid = count_valid(s_out, KP);  // keys sorted, empties last
   const int n_out = n_valid < k ? n_valid : k;
 
   // final order: (exact score desc, row asc) by counting rank
@@ -367,7 +366,8 @@ static int launch_finalize(const DensePlan& p, const u64* part, const uint16_t* 
                            double cert_eps, double* out_scores, long long* out_ids, int* out_counts,
                            int* out_flags, cudaStream_t st) {
   constexpr int KP = 32 * KPL;
-  const size_t smem = (size_t)(p.grid_x + 1) * 8 + (size_t)KP * KP * 8 + KP * 8 + KP * 8 + 16;
+  constexpr int CAP = KP * KP < 4096 ? KP * KP : 4096;
+  const size_t smem = (size_t)(p.grid_x + 1) * 8 + (size_t)CAP * 8 + KP * 8 + KP * 8 + 16;
   if (smem > 200 * 1024) {
     set_error("finalize shared memory %zu too large", smem);
     return CMR_EUNSUPPORTED;

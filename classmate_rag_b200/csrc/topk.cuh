@@ -1,118 +1,200 @@
-// topk.cuh -- CTA-shared top-k lists, block merges and the exact float64 dot
-// used by every rescoring pass.
+// topk.cuh -- warp-private top-k lists, block merges, cross-CTA selection and
+// the exact float64 dot used by the dense rescoring pass.
+//
+// Everything is generic over a key type K with a strict total order:
+//   u64   (dense)  high word = orderable fp32 score, low word = ~row; 0 = empty
+//   KeyD  (BM25)   exact float64 score + row; row 0xFFFFFFFF = empty
+// "better" means: higher score, then lower row.
 #pragma once
 #include "common.cuh"
 
 namespace cmr {
 
+struct __align__(16) KeyD {
+  double s;
+  u32 id;
+  u32 pad;
+};
+
+__device__ __forceinline__ bool key_gt(u64 a, u64 b) { return a > b; }
+__device__ __forceinline__ bool key_empty(u64 a) { return a == 0ull; }
+__device__ __forceinline__ void key_clear(u64& a) { a = 0ull; }
+
+__device__ __forceinline__ bool key_gt(const KeyD& a, const KeyD& b) {
+  return a.s > b.s || (a.s == b.s && a.id < b.id);
+}
+__device__ __forceinline__ bool key_empty(const KeyD& a) { return a.id == 0xFFFFFFFFu; }
+__device__ __forceinline__ void key_clear(KeyD& a) {
+  a.s = -INFINITY;
+  a.id = 0xFFFFFFFFu;
+  a.pad = 0;
+}
+
+__device__ __forceinline__ u64 key_shfl(u64 v, int src) { return shfl_u64(v, src); }
+__device__ __forceinline__ u64 key_shfl_up(u64 v, int d) { return shfl_up_u64(v, d); }
+__device__ __forceinline__ KeyD key_shfl(const KeyD& v, int src) {
+  KeyD r;
+  r.s = __shfl_sync(0xFFFFFFFFu, v.s, src);
+  r.id = __shfl_sync(0xFFFFFFFFu, v.id, src);
+  r.pad = 0;
+  return r;
+}
+__device__ __forceinline__ KeyD key_shfl_up(const KeyD& v, int d) {
+  KeyD r;
+  r.s = __shfl_up_sync(0xFFFFFFFFu, v.s, d);
+  r.id = __shfl_up_sync(0xFFFFFFFFu, v.id, d);
+  r.pad = 0;
+  return r;
+}
+
 // ---------------------------------------------------------------------------
-// Warp-private sorted list of KP keys in shared memory (descending, 0 = empty)
-// with the fp32 score of its last entry published as the warp's admission
-// threshold.  No lock: only the owning warp touches it.  Insertion is rare once
-// the threshold has warmed up (about KP*(1+ln(rows/KP)) inserts per warp), so
-// the streaming loops only pay one float compare per score against `thr`.
+// Warp-private sorted list of KP keys in shared memory (best first, empties
+// last).  No lock: only the owning warp touches it.  Insertion is rare once the
+// list's last score has warmed up (about KP*(1+ln(rows/KP)) inserts per warp),
+// so the streaming loops only pay one score compare against the published
+// threshold.  Returns true when the list changed; `new_last` is then its last key.
 // ---------------------------------------------------------------------------
-template <int KP>
-__device__ __forceinline__ void warp_list_insert(u64* keys, float* thr, u64 key, int lane) {
+template <int KP, typename K>
+__device__ __forceinline__ bool warp_list_insert(K* keys, const K& key, int lane, K& new_last) {
   constexpr int KPL = KP / 32;
-  u64 mine[KPL];
+  K mine[KPL];
 #pragma unroll
   for (int j = 0; j < KPL; ++j) mine[j] = keys[j * 32 + lane];
-  const u64 last = shfl_u64(mine[KPL - 1], 31);
-  if (key > last) {  // warp-uniform, authoritative (the float pre-test admits ties)
+  const K last = key_shfl(mine[KPL - 1], 31);
+  bool changed = false;
+  if (key_gt(key, last)) {  // warp-uniform and authoritative
+    changed = true;
     int pos = 0;
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) pos += __popc(__ballot_sync(0xFFFFFFFFu, mine[j] > key));
+    for (int j = 0; j < KPL; ++j) pos += __popc(__ballot_sync(0xFFFFFFFFu, key_gt(mine[j], key)));
 #pragma unroll
     for (int j = KPL - 1; j >= 0; --j) {
-      u64 up = shfl_up_u64(mine[j], 1);
+      K up = key_shfl_up(mine[j], 1);
       if (j > 0) {
-        const u64 carry = shfl_u64(mine[j - 1], 31);
+        const K carry = key_shfl(mine[j - 1], 31);
         if (lane == 0) up = carry;
       }
       const int p = j * 32 + lane;
-      u64 nv = mine[j];
+      K nv = mine[j];
       if (p == pos) nv = key;
       else if (p > pos) nv = up;
       keys[p] = nv;
-      if (j == KPL - 1 && lane == 31 && nv != 0ull) *thr = key_score(nv);
+      if (j == KPL - 1) new_last = key_shfl(nv, 31);
     }
   }
   __syncwarp();
+  return changed;
 }
 
-// number of entries of a descending-sorted list (zeros at the end) that are > k
-__device__ __forceinline__ int count_greater(const u64* list, int n, u64 k) {
+// number of entries of a best-first sorted list (empties last) that beat k
+template <typename K>
+__device__ __forceinline__ int count_better(const K* list, int n, const K& k) {
   int lo = 0, hi = n;
   while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (list[mid] > k) lo = mid + 1;
+    const int mid = (lo + hi) >> 1;
+    if (key_gt(list[mid], k)) lo = mid + 1;
     else hi = mid;
   }
   return lo;
 }
 
-// Merge n_lists descending-sorted lists of KP unique keys (shared memory) into
-// the KP best, written sorted to out[KP] (must be zero-filled by the caller).
-template <int KP>
-__device__ __forceinline__ void block_merge_lists(const u64* lists, int n_lists, u64* out,
+// number of non-empty entries of a sorted list
+template <typename K>
+__device__ __forceinline__ int count_valid(const K* list, int n) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (!key_empty(list[mid])) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Merge n_lists sorted lists of KP unique keys (shared memory, list l starts at
+// lists + l*stride) into the KP best, written sorted to out[KP] (cleared by the
+// caller beforehand).
+template <int KP, typename K>
+__device__ __forceinline__ void block_merge_lists(const K* lists, int n_lists, size_t stride, K* out,
                                                   int tid, int nthreads) {
   for (int e = tid; e < n_lists * KP; e += nthreads) {
-    const u64 k = lists[e];
-    if (k == 0ull) continue;
     const int a = e / KP;
+    const K k = lists[a * stride + (e - a * KP)];
+    if (key_empty(k)) continue;
     int rank = e - a * KP;
     for (int b = 0; b < n_lists && rank < KP; ++b) {
       if (b == a) continue;
-      rank += count_greater(lists + b * KP, KP, k);
+      rank += count_better(lists + b * stride, KP, k);
     }
     if (rank < KP) out[rank] = k;
   }
 }
 
 // Select the KP best keys out of n_lists sorted lists held in GLOBAL memory.
-//   s_heads [n_lists] scratch   s_buf [KP*KP] scratch   s_cnt [2] scratch (int)
-//   s_out   [KP] result, sorted descending, zero padded
-// T = the KP-th largest list head is a lower bound of the KP-th best key, and
-// only the (at most KP) lists whose head reaches T can hold keys >= T, so at
-// most KP*KP keys are compacted; they are then ranked by counting.  Ends with
-// __syncthreads().
-template <int KP>
-__device__ void block_select_from_lists(const u64* __restrict__ lists, int n_lists,
-                                        u64* s_heads, u64* s_buf, int* s_cnt, u64* s_out,
-                                        int tid, int nthreads) {
+//   s_heads [n_lists + 1] scratch   s_buf [CAP] scratch   s_cnt [1] scratch
+//   s_out   [KP] result, sorted best first, empties last
+// T = the KP-th best list head is a lower bound of the KP-th best key, and only
+// the (at most KP) lists whose head reaches T can hold keys >= T.  Those keys
+// (typically KP plus a few) are compacted into s_buf and ranked by counting.
+// If more than CAP keys qualify (adversarial data: the bound is KP*KP), each
+// qualifying key is instead ranked by binary searches over the qualifying lists
+// in global memory -- slower, same result.  Ends with __syncthreads().
+template <int KP, int CAP, typename K>
+__device__ void block_select_from_lists(const K* __restrict__ lists, int n_lists, K* s_heads, K* s_buf,
+                                        int* s_cnt, K* s_out, int tid, int nthreads) {
   for (int i = tid; i < n_lists; i += nthreads) s_heads[i] = lists[(size_t)i * KP];
-  for (int i = tid; i < KP; i += nthreads) s_out[i] = 0ull;
+  for (int i = tid; i < KP; i += nthreads) key_clear(s_out[i]);
   if (tid == 0) {
     s_cnt[0] = 0;
-    s_heads[n_lists] = 0ull;  // T
+    key_clear(s_heads[n_lists]);  // T: empty == "no bound"
   }
   __syncthreads();
   if (n_lists > KP) {
     for (int i = tid; i < n_lists; i += nthreads) {
-      const u64 h = s_heads[i];
-      if (h == 0ull) continue;
+      const K h = s_heads[i];
+      if (key_empty(h)) continue;
       int cnt = 0;
-      for (int j = 0; j < n_lists; ++j) cnt += (s_heads[j] > h);
+      for (int j = 0; j < n_lists; ++j) cnt += key_gt(s_heads[j], h);
       if (cnt == KP - 1) s_heads[n_lists] = h;  // unique keys: exactly one writer
     }
     __syncthreads();
   }
-  const u64 T = s_heads[n_lists];
-  // compact keys >= T (a prefix of each qualifying list); one thread per list slot
+  const K T = s_heads[n_lists];
+  const bool bounded = !key_empty(T);
   for (int e = tid; e < n_lists * KP; e += nthreads) {
     const int a = e / KP;
-    if (s_heads[a] < T || s_heads[a] == 0ull) continue;
-    const u64 k = lists[e];
-    if (k != 0ull && k >= T) s_buf[atomicAdd(&s_cnt[0], 1)] = k;
+    const K h = s_heads[a];
+    if (key_empty(h) || (bounded && key_gt(T, h))) continue;
+    const K k = lists[e];
+    if (!key_empty(k) && !(bounded && key_gt(T, k))) {
+      const int slot = atomicAdd(&s_cnt[0], 1);
+      if (slot < CAP) s_buf[slot] = k;
+    }
   }
   __syncthreads();
   const int m = s_cnt[0];
-  for (int e = tid; e < m; e += nthreads) {
-    const u64 k = s_buf[e];
-    int rank = 0;
-    for (int j = 0; j < m; ++j) rank += (s_buf[j] > k);
-    if (rank < KP) s_out[rank] = k;
+  if (m <= CAP) {
+    for (int e = tid; e < m; e += nthreads) {
+      const K k = s_buf[e];
+      int rank = 0;
+      for (int j = 0; j < m; ++j) rank += key_gt(s_buf[j], k);
+      if (rank < KP) s_out[rank] = k;
+    }
+  } else {
+    for (int e = tid; e < n_lists * KP; e += nthreads) {
+      const int a = e / KP;
+      const K h = s_heads[a];
+      if (key_empty(h) || (bounded && key_gt(T, h))) continue;
+      const K k = lists[e];
+      if (key_empty(k) || (bounded && key_gt(T, k))) continue;
+      int rank = e - a * KP;
+      for (int b2 = 0; b2 < n_lists && rank < KP; ++b2) {
+        if (b2 == a) continue;
+        const K hb = s_heads[b2];
+        if (key_empty(hb) || (bounded && key_gt(T, hb))) continue;
+        rank += count_better(lists + (size_t)b2 * KP, KP, k);
+      }
+      if (rank < KP) s_out[rank] = k;
+    }
   }
   __syncthreads();
 }

@@ -1,0 +1,196 @@
+"""Device-resident BM25 inverted index (term-major CSR + tile skip table).
+
+Build side of A7 (reference: BM25Store.upsert_many/_rebuild,
+rag/retrieval/bm25.py:140-166, which rebuilds rank_bm25.BM25Okapi from the
+token lists).  The statistics follow rank_bm25 exactly: idf uses
+``math.log`` on the host, its epsilon floor uses the average idf summed
+sequentially in vocabulary first-appearance order, avgdl = total tokens / N.
+torch is used for sorting and scans (plumbing); scoring is in libcmrag.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+BM25_K1 = 1.5
+BM25_B = 0.75
+BM25_EPS = 0.25
+DEFAULT_TILE_DOCS = 8192
+
+
+class LexIndexStruct(C.Structure):
+    """Mirror of ``cmr_lex_index`` (include/cmrag.h)."""
+    _fields_ = [
+        ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_doc", C.c_void_p),
+        ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p), ("idf", C.c_void_p),
+        ("n_docs", C.c_int64), ("n_terms", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
+        ("reserved", C.c_int32), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
+    ]
+
+
+def idf_table(df: np.ndarray, n_docs: int, vocab_order: np.ndarray, epsilon: float = BM25_EPS):
+    """rank_bm25 idf with the epsilon floor.  ``vocab_order``: term ids with
+    df > 0 in first-appearance order (the order the running sum is taken in)."""
+    idf = np.zeros(df.shape[0], dtype=np.float64)
+    idf_sum = 0.0
+    negative = []
+    for t in vocab_order.tolist():
+        n_t = int(df[t])
+        v = math.log(n_docs - n_t + 0.5) - math.log(n_t + 0.5)
+        idf[t] = v
+        idf_sum += v
+        if v < 0:
+            negative.append(t)
+    average_idf = idf_sum / max(1, len(vocab_order))
+    if negative:
+        idf[np.asarray(negative, dtype=np.int64)] = epsilon * average_idf
+    return idf, average_idf
+
+
+@dataclass
+class LexicalIndex:
+    term_ptr: torch.Tensor      # int64 [V+1]
+    tile_skip: torch.Tensor     # int32 (uint32 bits) [V, n_tiles+1]
+    post_doc: torch.Tensor      # int32 [P]
+    post_imp: torch.Tensor      # float64 [P]
+    post_tf: torch.Tensor       # int16 (uint16 bits) [P]
+    doc_len: torch.Tensor       # int32 [N]
+    idf: torch.Tensor           # float64 [V]
+    n_docs: int
+    n_terms: int
+    tile_docs: int
+    n_tiles: int
+    avgdl: float
+    k1: float = BM25_K1
+    b: float = BM25_B
+    idf_host: np.ndarray = field(default=None, repr=False)
+    df_host: np.ndarray = field(default=None, repr=False)        # corpus-wide df
+    shard_df_host: np.ndarray = field(default=None, repr=False)  # postings per term in THIS shard
+    _struct: Optional[LexIndexStruct] = field(default=None, repr=False)
+
+    @property
+    def n_postings(self) -> int:
+        return int(self.post_doc.numel())
+
+    @property
+    def device(self):
+        return self.post_doc.device
+
+    def struct(self) -> LexIndexStruct:
+        if self._struct is None:
+            self._struct = LexIndexStruct(
+                self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), self.post_doc.data_ptr(),
+                self.post_imp.data_ptr(), self.post_tf.data_ptr(), self.doc_len.data_ptr(), self.idf.data_ptr(),
+                self.n_docs, self.n_terms, self.tile_docs, self.n_tiles, 0, self.avgdl, self.k1, self.b)
+        return self._struct
+
+    def posting_bytes(self, terms: Sequence[int]) -> int:
+        """Algorithmic bytes one query streams: 12 B (int32 doc + float64 impact)
+        per posting of every query token, multiplicity counted."""
+        return 12 * int(sum(int(self.shard_df_host[t]) for t in terms if 0 <= t < self.n_terms))
+
+
+@dataclass
+class GlobalStats:
+    """Corpus-wide statistics for a doc-partitioned (sharded) index, so every
+    shard scores with the same idf / avgdl as the unsharded index."""
+    n_docs: int
+    total_tokens: int
+    df: np.ndarray            # int64 [V]
+    vocab_order: np.ndarray   # term ids with df>0, first-appearance order
+
+
+def corpus_stats(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int) -> GlobalStats:
+    """df, total length and first-appearance vocabulary order of a token corpus."""
+    n_docs = doc_ptr.numel() - 1
+    tok = tokens.long()
+    total = int(tok.numel())
+    dev = tok.device
+    if total == 0:
+        return GlobalStats(n_docs, 0, np.zeros(n_terms, dtype=np.int64), np.zeros(0, dtype=np.int64))
+    doc_len = (doc_ptr[1:] - doc_ptr[:-1]).long()
+    doc_of = torch.repeat_interleave(torch.arange(n_docs, device=dev), doc_len)
+    key = torch.unique(tok * n_docs + doc_of)
+    df = torch.bincount(key // n_docs, minlength=n_terms)
+    first_pos = torch.full((n_terms,), total, dtype=torch.int64, device=dev)
+    first_pos.scatter_reduce_(0, tok, torch.arange(total, device=dev), reduce="amin")
+    order = torch.argsort(first_pos, stable=True)
+    n_seen = int((df > 0).sum())
+    return GlobalStats(n_docs, total, df.cpu().numpy().astype(np.int64), order[:n_seen].cpu().numpy())
+
+
+def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int, *,
+                        device=None, tile_docs: int = DEFAULT_TILE_DOCS,
+                        stats: Optional[GlobalStats] = None,
+                        k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS) -> LexicalIndex:
+    """Build the CSR index of the documents ``tokens[doc_ptr[i]:doc_ptr[i+1]]``.
+
+    ``stats`` (optional) supplies corpus-wide df / N / total tokens when this
+    call builds one shard of a larger corpus."""
+    if device is None:
+        device = tokens.device
+    doc_ptr = doc_ptr.to(device).long()
+    tok = tokens.to(device).long()
+    n_docs = doc_ptr.numel() - 1
+    total = int(tok.numel())
+    if tile_docs % 512 != 0 or tile_docs <= 0:
+        raise ValueError("tile_docs must be a positive multiple of 512")
+    n_tiles = max(1, (n_docs + tile_docs - 1) // tile_docs)
+    doc_len = (doc_ptr[1:] - doc_ptr[:-1])
+    if stats is None:
+        stats = corpus_stats(doc_ptr, tok, n_terms)
+    avgdl = (stats.total_tokens / stats.n_docs) if stats.n_docs > 0 else 0.0
+    idf_host, _ = idf_table(stats.df, stats.n_docs, stats.vocab_order, epsilon)
+
+    if total > 0:
+        doc_of = torch.repeat_interleave(torch.arange(n_docs, device=device), doc_len)
+        key, _ = torch.sort(tok * max(n_docs, 1) + doc_of)
+        del doc_of
+        uniq, counts = torch.unique_consecutive(key, return_counts=True)
+        del key
+        term = uniq // max(n_docs, 1)
+        doc = uniq - term * max(n_docs, 1)
+    else:
+        uniq = torch.zeros(0, dtype=torch.int64, device=device)
+        counts = term = doc = uniq
+    term_ptr = torch.searchsorted(term, torch.arange(n_terms + 1, device=device))
+    # tile skip table: posting offset (relative to the term) where each tile starts
+    bounds = (torch.arange(n_terms, device=device)[:, None] * max(n_docs, 1)
+              + torch.clamp(torch.arange(n_tiles + 1, device=device) * tile_docs, max=max(n_docs, 1))[None, :])
+    skip = torch.searchsorted(uniq, bounds.reshape(-1)).reshape(n_terms, n_tiles + 1) - term_ptr[:-1, None]
+    del bounds
+    dl = doc_len.to(torch.float64)
+    tf64 = counts.to(torch.float64)
+    if avgdl > 0:
+        # operation for operation as rank_bm25: q_freq*(k1+1) / (q_freq + k1*(1 - b + b*doc_len/avgdl))
+        # (avgdl as a device tensor: torch turns division by a Python scalar into a
+        # multiplication by its reciprocal, which is not the same rounding)
+        avgdl_t = torch.tensor(avgdl, dtype=torch.float64, device=device)
+        imp = tf64 * (k1 + 1) / (tf64 + k1 * ((1 - b) + (b * dl[doc]) / avgdl_t))
+    else:
+        imp = torch.zeros_like(tf64)
+    tf32 = counts.clamp(max=65535).to(torch.int32)
+    tf16 = torch.where(tf32 >= 32768, tf32 - 65536, tf32).to(torch.int16)
+    return LexicalIndex(
+        term_ptr=term_ptr.contiguous(), tile_skip=skip.to(torch.int32).contiguous(),
+        post_doc=doc.to(torch.int32).contiguous(), post_imp=imp.contiguous(),
+        post_tf=tf16.contiguous(), doc_len=doc_len.to(torch.int32).contiguous(),
+        idf=torch.from_numpy(idf_host).to(device), n_docs=n_docs, n_terms=n_terms, tile_docs=tile_docs,
+        n_tiles=n_tiles, avgdl=float(avgdl), k1=k1, b=b, idf_host=idf_host, df_host=stats.df,
+        shard_df_host=(term_ptr[1:] - term_ptr[:-1]).cpu().numpy())
+
+
+def pack_queries(queries: Sequence[Sequence[int]]):
+    """[[term ids]] -> (q_terms int32, q_ptr int32 [B+1]) host tensors."""
+    ptr = np.zeros(len(queries) + 1, dtype=np.int32)
+    for i, q in enumerate(queries):
+        ptr[i + 1] = ptr[i] + len(q)
+    flat = np.fromiter((t for q in queries for t in q), dtype=np.int32, count=int(ptr[-1]))
+    if flat.size == 0:
+        flat = np.zeros(1, dtype=np.int32)  # keep a valid device pointer
+    return torch.from_numpy(flat), torch.from_numpy(ptr)

@@ -95,3 +95,46 @@ def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Op
                                 _stream())
     _lib.check(rc)
     return workspace.scores, workspace.ids, workspace.counts, workspace.flags
+
+
+class TopkBuffers:
+    """Output buffers shared by the top-k entry points."""
+
+    def __init__(self, n_queries: int, k: int, ws_bytes: int, device):
+        self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
+        self.scores = torch.empty((n_queries, k), dtype=torch.float64, device=device)
+        self.ids = torch.empty((n_queries, k), dtype=torch.int64, device=device)
+        self.counts = torch.empty((n_queries,), dtype=torch.int32, device=device)
+        self.flags = torch.empty((n_queries,), dtype=torch.int32, device=device)
+
+
+def bm25_topk(index, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int, *,
+              row_mask: Optional[torch.Tensor] = None, row_offset: int = 0,
+              buffers: Optional[TopkBuffers] = None):
+    """Exact BM25 top-k for a batch of tokenised queries (device tensors:
+    q_terms int32, q_ptr int32 [B+1]).  Returns (scores f64 [B,k], ids i64 [B,k],
+    counts, flags) on the device, enqueued on the current stream."""
+    import ctypes as C
+    for name, t in (("q_terms", q_terms), ("q_ptr", q_ptr)):
+        _require_cuda(t, name)
+        if t.dtype != torch.int32:
+            raise ValueError(f"{name} must be int32")
+    b = q_ptr.numel() - 1
+    if row_mask is not None:
+        _require_cuda(row_mask, "row_mask")
+        if row_mask.dtype != torch.uint8 or row_mask.numel() != index.n_docs:
+            raise ValueError("row_mask must be uint8 [n_docs]")
+    lib = _lib.load()
+    st = index.struct()
+    with torch.cuda.device(index.device):
+        if buffers is None:
+            nbytes = lib.cmr_bm25_workspace_bytes(C.byref(st), b, k)
+            if nbytes == 0:
+                raise ValueError(f"unsupported bm25 shape B={b} k={k}: " + _lib.last_error())
+            buffers = TopkBuffers(b, k, nbytes, index.device)
+        rc = lib.cmr_bm25_topk(C.byref(st), q_terms.data_ptr(), q_ptr.data_ptr(), b, k,
+                               _ptr(row_mask), row_offset, buffers.scores.data_ptr(), buffers.ids.data_ptr(),
+                               buffers.counts.data_ptr(), buffers.flags.data_ptr(), buffers.ws.data_ptr(),
+                               buffers.ws.numel(), _stream())
+    _lib.check(rc)
+    return buffers.scores, buffers.ids, buffers.counts, buffers.flags

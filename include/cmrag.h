@@ -80,6 +80,52 @@ int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
  * (E5 hands the store fp32, rag/embeddings/__init__.py:85-105). */
 int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * A2  BM25 (Okapi, rank_bm25 semantics) exact top-k.  Replaces
+ *     BM25Okapi.get_scores + sorted(...)[:k] inside BM25Store.search
+ *     (rag/retrieval/bm25.py:175-212).
+ *
+ * The inverted index is a term-major CSR over the shard's documents, postings
+ * of a term sorted by document, plus a skip table that gives, per term, the
+ * posting offset at which every tile of `tile_docs` documents starts.
+ * Scores are accumulated in float64 in query-token order with rank_bm25's own
+ * operation order, so they are bit-identical to the reference arithmetic and
+ * no rescoring pass (and no certificate) is needed: out_flags is always 0.
+ * All pointers are device memory.
+ * ---------------------------------------------------------------------- */
+typedef struct cmr_lex_index {
+  const int64_t* term_ptr;   /* [n_terms + 1] posting offsets                          */
+  const uint32_t* tile_skip; /* [n_terms, n_tiles + 1] offsets relative to term_ptr[t]  */
+  const int32_t* post_doc;   /* [P] local document of each posting                      */
+  const double* post_imp;    /* [P] float64 tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl))          */
+  const uint16_t* post_tf;   /* [P] term frequency (saturated at 65535); may be NULL    */
+  const int32_t* doc_len;    /* [n_docs] tokens per document; may be NULL               */
+  const double* idf;         /* [n_terms] float64 idf with the epsilon floor            */
+  int64_t n_docs;
+  int32_t n_terms;
+  int32_t tile_docs;
+  int32_t n_tiles;
+  int32_t reserved;
+  double avgdl;
+  double k1;
+  double b;
+} cmr_lex_index;
+
+size_t cmr_bm25_workspace_bytes(const cmr_lex_index* ix, int n_queries, int k);
+
+/*   q_terms    device, int32 [q_ptr[n_queries]] term ids in query-token order,
+ *              duplicates kept (rank_bm25 adds a repeated token twice), -1 = unknown
+ *   q_ptr      device, int32 [n_queries + 1]
+ *   row_mask   device, uint8 [n_docs] or NULL (candidate filter only; subset
+ *              statistics are the caller's business)
+ *   outputs as cmr_dense_topk; zero-score documents are ranked too, in
+ *   ascending id order (bm25.py:199 sorts ALL candidates, stably).            */
+int cmr_bm25_topk(const cmr_lex_index* ix, const int32_t* q_terms, const int32_t* q_ptr,
+                  int n_queries, int k, const uint8_t* row_mask,
+                  int64_t row_offset, double* out_scores, int64_t* out_ids,
+                  int32_t* out_counts, int32_t* out_flags, void* workspace,
+                  size_t workspace_bytes, cmr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

