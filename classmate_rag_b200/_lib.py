@@ -29,6 +29,11 @@ _SIGNATURES = {
     "cmr_dense_topk": (C.c_int, [_vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _i64, _f64,
                                  _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cmr_f32_to_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "cmr_gather_rows": (C.c_int, [_vp, _i64, C.c_int, _i64, _vp, C.c_int, _vp, _vp]),
+    "cmr_mmr_select": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64, _vp, _vp, _vp, _vp]),
+    "cmr_hybrid_fuse": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _f64, _f64,
+                                  C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cmr_topk_merge": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "cmr_bm25_workspace_bytes": (_sz, [_vp, C.c_int, C.c_int]),
     "cmr_bm25_topk": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -1,0 +1,318 @@
+// fuse.cu -- the small latency-bound kernels that follow the two top-k scans:
+//
+//  gather_rows_kernel   copy candidate embedding rows into a dense buffer (rows
+//                       of other shards are zero-filled, so an all-reduce SUM or
+//                       an all-gather + merge over ranks reassembles the pool)
+//  mmr_select_kernel    A4: greedy MMR re-ordering of the dense pool
+//                       (reference rag/retrieval/fusion.py:39-61,80-102); the
+//                       similarities are the pinned exact float64 dots
+//  hybrid_fuse_kernel   A3+A5: Reciprocal Rank Fusion, per-id merge and the final
+//                       stable sort of HybridRetriever.retrieve
+//                       (rag/retrieval/fusion.py:17-36,108-167)
+//  topk_merge_kernel    K7: merge the per-shard top-k lists gathered from the
+//                       ranks (score desc, id asc)
+//
+// All float64 arithmetic uses explicit round-to-nearest intrinsics so that no
+// fused multiply-add changes a rounding: results are bit-identical to Python.
+#include "topk.cuh"
+
+namespace cmr {
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ emb, long long n_rows, int dim_vec,
+                                   long long row_offset, const long long* __restrict__ ids, int n_ids,
+                                   uint4* __restrict__ out) {
+  const int i = blockIdx.x;
+  if (i >= n_ids) return;
+  const long long local = ids[i] - row_offset;
+  const bool mine = ids[i] >= 0 && local >= 0 && local < n_rows;
+  for (int v = threadIdx.x; v < dim_vec; v += blockDim.x)
+    out[(size_t)i * dim_vec + v] = mine ? emb[(size_t)local * dim_vec + v] : make_uint4(0, 0, 0, 0);
+}
+
+constexpr int MMR_THREADS = 256;
+constexpr int MMR_MAX_POOL = 64;
+
+// One CTA per query.  cand_rows [B][pool][dim] bf16, cand_sims [B][pool] (exact
+// q.c, i.e. the scores cmr_dense_topk returned), cand_ids [B][pool].
+__global__ void __launch_bounds__(MMR_THREADS)
+mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restrict__ cand_sims,
+                  const long long* __restrict__ cand_ids, const int* __restrict__ cand_counts, int pool,
+                  int dim, int k, double lambda, long long* __restrict__ out_ids,
+                  double* __restrict__ out_sims, int* __restrict__ out_counts) {
+  __shared__ double s_cc[MMR_MAX_POOL * MMR_MAX_POOL];
+  __shared__ double s_q[MMR_MAX_POOL];
+  __shared__ int s_sel[MMR_MAX_POOL];
+  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n = cand_counts[qi];
+  if (n > pool) n = pool;
+  const uint16_t* rows = cand_rows + (size_t)qi * pool * dim;
+  for (int i = tid; i < n; i += MMR_THREADS) s_q[i] = cand_sims[(size_t)qi * pool + i];
+  // pairwise similarities (symmetric: the pinned order multiplies elementwise)
+  const int n_pairs = n * (n - 1) / 2;
+  for (int p = warp; p < n_pairs; p += MMR_THREADS / 32) {
+    int i = 0, rem = p;
+    while (rem >= n - 1 - i) {  // row i holds pairs (i, i+1..n-1)
+      rem -= n - 1 - i;
+      ++i;
+    }
+    const int j = i + 1 + rem;
+    const double s = warp_exact_dot(rows + (size_t)i * dim, rows + (size_t)j * dim, dim, lane);
+    if (lane == 0) {
+      s_cc[i * MMR_MAX_POOL + j] = s;
+      s_cc[j * MMR_MAX_POOL + i] = s;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int target = k < n ? k : n;
+    int n_sel = 0;
+    unsigned long long remaining = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    if (n > 0) {
+      int first = 0;  // np.argmax: lowest index on ties
+      for (int i = 1; i < n; ++i)
+        if (s_q[i] > s_q[first]) first = i;
+      s_sel[n_sel++] = first;
+      remaining &= ~(1ull << first);
+    }
+    const double one_minus = __dsub_rn(1.0, lambda);
+    while (remaining && n_sel < target) {
+      int best = -1;
+      double best_score = -1e9;
+      for (int i = 0; i < n; ++i) {
+        if (!((remaining >> i) & 1ull)) continue;
+        double div = s_cc[i * MMR_MAX_POOL + s_sel[0]];
+        for (int j = 1; j < n_sel; ++j) {
+          const double v = s_cc[i * MMR_MAX_POOL + s_sel[j]];
+          if (v > div) div = v;
+        }
+        const double sc = __dsub_rn(__dmul_rn(lambda, s_q[i]), __dmul_rn(one_minus, div));
+        if (sc > best_score) {
+          best_score = sc;
+          best = i;
+        }
+      }
+      if (best < 0) break;
+      s_sel[n_sel++] = best;
+      remaining &= ~(1ull << best);
+    }
+    for (int i = 0; i < k; ++i) {
+      if (i < n_sel) {
+        out_ids[(size_t)qi * k + i] = cand_ids[(size_t)qi * pool + s_sel[i]];
+        out_sims[(size_t)qi * k + i] = s_q[s_sel[i]];
+      } else {
+        out_ids[(size_t)qi * k + i] = -1;
+        out_sims[(size_t)qi * k + i] = 0.0;
+      }
+    }
+    out_counts[qi] = n_sel;
+  }
+}
+
+constexpr int FUSE_THREADS = 128;
+constexpr int FUSE_MAX_ITEMS = 256;
+
+// One CTA per query.  vec list = dense results in their final (post-MMR) order.
+__global__ void __launch_bounds__(FUSE_THREADS)
+hybrid_fuse_kernel(const long long* __restrict__ vec_ids, const double* __restrict__ vec_sims,
+                   const int* __restrict__ vec_counts, int kv, const long long* __restrict__ bm_ids,
+                   const double* __restrict__ bm_scores, const int* __restrict__ bm_counts, int kb,
+                   double w_vec, double w_bm, int rrf_k, int top_k, long long* __restrict__ out_ids,
+                   double* __restrict__ out_fused, double* __restrict__ out_vdist,
+                   double* __restrict__ out_bm25, int* __restrict__ out_counts) {
+  __shared__ long long s_id[FUSE_MAX_ITEMS];
+  __shared__ double s_fused[FUSE_MAX_ITEMS];
+  __shared__ double s_vd[FUSE_MAX_ITEMS];   // vector_distance, NaN when absent
+  __shared__ double s_bm[FUSE_MAX_ITEMS];   // bm25_score, NaN when absent
+  __shared__ int s_n;
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  int nv = vec_counts ? vec_counts[qi] : 0;
+  if (nv > kv) nv = kv;
+  int nb = (bm_counts && kb > 0) ? bm_counts[qi] : 0;
+  if (nb > kb) nb = kb;
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  // vector items first, in order: fused = 0.0 + w*(1/(rrf_k+rank)) == the contribution
+  for (int i = tid; i < nv; i += FUSE_THREADS) {
+    s_id[i] = vec_ids[(size_t)qi * kv + i];
+    s_fused[i] = __dmul_rn(w_vec, __ddiv_rn(1.0, (double)(rrf_k + i + 1)));
+    s_vd[i] = __dsub_rn(1.0, vec_sims[(size_t)qi * kv + i]);
+    s_bm[i] = nan;
+  }
+  if (tid == 0) s_n = nv;
+  __syncthreads();
+  // BM25 items: join on id (sequential: insertion order of BM25-only items matters)
+  if (tid == 0) {
+    int n = nv;
+    for (int r = 0; r < nb; ++r) {
+      const long long id = bm_ids[(size_t)qi * kb + r];
+      const double contrib = __dmul_rn(w_bm, __ddiv_rn(1.0, (double)(rrf_k + r + 1)));
+      int at = -1;
+      for (int i = 0; i < n; ++i)
+        if (s_id[i] == id) {
+          at = i;
+          break;
+        }
+      if (at < 0) {
+        at = n++;
+        s_id[at] = id;
+        s_fused[at] = contrib;  // 0.0 + contrib
+        s_vd[at] = nan;
+      } else {
+        s_fused[at] = __dadd_rn(s_fused[at], contrib);
+      }
+      s_bm[at] = bm_scores[(size_t)qi * kb + r];
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const int n_out = n < top_k ? n : top_k;
+  // stable descending sort on (fused, -vector_distance); absent distance -> -0.0
+  for (int i = tid; i < n; i += FUSE_THREADS) {
+    const double f = s_fused[i];
+    const double t = (s_vd[i] != s_vd[i]) ? 0.0 : -s_vd[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double fj = s_fused[j];
+      const double tj = (s_vd[j] != s_vd[j]) ? 0.0 : -s_vd[j];
+      const bool greater = (fj > f) || (fj == f && tj > t);
+      const bool equal = (fj == f) && (tj == t);
+      rank += greater || (equal && j < i);
+    }
+    if (rank < n_out) {
+      out_ids[(size_t)qi * top_k + rank] = s_id[i];
+      out_fused[(size_t)qi * top_k + rank] = f;
+      out_vdist[(size_t)qi * top_k + rank] = s_vd[i];
+      out_bm25[(size_t)qi * top_k + rank] = s_bm[i];
+    }
+  }
+  for (int i = n_out + tid; i < top_k; i += FUSE_THREADS) {
+    out_ids[(size_t)qi * top_k + i] = -1;
+    out_fused[(size_t)qi * top_k + i] = 0.0;
+    out_vdist[(size_t)qi * top_k + i] = nan;
+    out_bm25[(size_t)qi * top_k + i] = nan;
+  }
+  if (tid == 0) out_counts[qi] = n_out;
+}
+
+constexpr int MERGE_THREADS = 256;
+
+// in_* are laid out [G][B][k]; one CTA per query.
+__global__ void __launch_bounds__(MERGE_THREADS)
+topk_merge_kernel(const double* __restrict__ in_scores, const long long* __restrict__ in_ids,
+                  const int* __restrict__ in_counts, int n_parts, int n_queries, int k,
+                  double* __restrict__ out_scores, long long* __restrict__ out_ids,
+                  int* __restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_s = reinterpret_cast<double*>(smem_raw);          // [G*k]
+  long long* s_i = reinterpret_cast<long long*>(s_s + n_parts * k);
+  __shared__ int s_total;
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const int n = n_parts * k;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  for (int e = tid; e < n; e += MERGE_THREADS) {
+    const int g = e / k, r = e - g * k;
+    const int cnt = in_counts[(size_t)g * n_queries + qi];
+    const size_t src = ((size_t)g * n_queries + qi) * k + r;
+    const bool valid = r < cnt && in_ids[src] >= 0;
+    s_s[e] = valid ? in_scores[src] : 0.0;
+    s_i[e] = valid ? in_ids[src] : -1;
+    if (valid) atomicAdd(&s_total, 1);
+  }
+  __syncthreads();
+  const int n_out = s_total < k ? s_total : k;
+  for (int e = tid; e < n; e += MERGE_THREADS) {
+    const long long id = s_i[e];
+    if (id < 0) continue;
+    const double s = s_s[e];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const long long idj = s_i[j];
+      if (idj < 0) continue;
+      const double sj = s_s[j];
+      rank += (sj > s) || (sj == s && idj < id);
+    }
+    if (rank < n_out) {
+      out_scores[(size_t)qi * k + rank] = s;
+      out_ids[(size_t)qi * k + rank] = id;
+    }
+  }
+  for (int i = n_out + tid; i < k; i += MERGE_THREADS) {
+    out_scores[(size_t)qi * k + i] = 0.0;
+    out_ids[(size_t)qi * k + i] = -1;
+  }
+  if (tid == 0) out_counts[qi] = n_out;
+}
+
+}  // namespace cmr
+
+using namespace cmr;
+
+extern "C" int cmr_gather_rows(const uint16_t* emb, int64_t n_rows, int dim, int64_t row_offset,
+                               const int64_t* ids, int n_ids, uint16_t* out_rows, cmr_stream_t stream) {
+  CMR_CHECK_ARG(dim > 0 && dim % 8 == 0, "dim must be a multiple of 8");
+  CMR_CHECK_ARG(n_ids >= 0 && (n_ids == 0 || (ids && out_rows)), "bad arguments");
+  CMR_CHECK_ARG(n_rows == 0 || emb, "null embedding matrix");
+  if (n_ids == 0) return CMR_OK;
+  gather_rows_kernel<<<n_ids, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(emb), n_rows, dim / 8, row_offset, (const long long*)ids, n_ids,
+      reinterpret_cast<uint4*>(out_rows));
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_mmr_select(const uint16_t* cand_rows, const double* cand_sims, const int64_t* cand_ids,
+                              const int32_t* cand_counts, int n_queries, int pool, int dim, int k,
+                              double lambda, int64_t* out_ids, double* out_sims, int32_t* out_counts,
+                              cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_queries > 0, "n_queries must be positive");
+  CMR_CHECK_ARG(pool > 0 && pool <= MMR_MAX_POOL, "pool %d out of range (1..%d)", pool, MMR_MAX_POOL);
+  CMR_CHECK_ARG(k > 0 && k <= pool, "k %d out of range (1..pool)", k);
+  CMR_CHECK_ARG(dim > 0 && dim % 8 == 0, "dim must be a multiple of 8");
+  CMR_CHECK_ARG(cand_rows && cand_sims && cand_ids && cand_counts && out_ids && out_sims && out_counts, "null pointer argument");
+  mmr_select_kernel<<<n_queries, MMR_THREADS, 0, (cudaStream_t)stream>>>(
+      cand_rows, cand_sims, (const long long*)cand_ids, cand_counts, pool, dim, k, lambda,
+      (long long*)out_ids, out_sims, out_counts);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_hybrid_fuse(const int64_t* vec_ids, const double* vec_sims, const int32_t* vec_counts, int kv,
+                               const int64_t* bm_ids, const double* bm_scores, const int32_t* bm_counts, int kb,
+                               int n_queries, double w_vec, double w_bm, int rrf_k, int top_k,
+                               int64_t* out_ids, double* out_fused, double* out_vdist, double* out_bm25,
+                               int32_t* out_counts, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_queries > 0, "n_queries must be positive");
+  CMR_CHECK_ARG(kv >= 0 && kb >= 0 && kv + kb <= FUSE_MAX_ITEMS, "kv + kb must be <= %d", FUSE_MAX_ITEMS);
+  CMR_CHECK_ARG(top_k > 0, "top_k must be positive");
+  CMR_CHECK_ARG(kv == 0 || (vec_ids && vec_sims && vec_counts), "null vector list");
+  CMR_CHECK_ARG(kb == 0 || (bm_ids && bm_scores && bm_counts), "null bm25 list");
+  CMR_CHECK_ARG(out_ids && out_fused && out_vdist && out_bm25 && out_counts, "null output");
+  hybrid_fuse_kernel<<<n_queries, FUSE_THREADS, 0, (cudaStream_t)stream>>>(
+      (const long long*)vec_ids, vec_sims, kv > 0 ? vec_counts : nullptr, kv, (const long long*)bm_ids, bm_scores,
+      kb > 0 ? bm_counts : nullptr, kb, w_vec, w_bm, rrf_k, top_k, (long long*)out_ids, out_fused, out_vdist,
+      out_bm25, out_counts);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_topk_merge(const double* in_scores, const int64_t* in_ids, const int32_t* in_counts,
+                              int n_parts, int n_queries, int k, double* out_scores, int64_t* out_ids,
+                              int32_t* out_counts, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_parts > 0 && n_queries > 0 && k > 0, "bad sizes");
+  CMR_CHECK_ARG((size_t)n_parts * k * 16 <= 96 * 1024, "n_parts * k too large for one merge (%d x %d)", n_parts, k);
+  CMR_CHECK_ARG(in_scores && in_ids && in_counts && out_scores && out_ids && out_counts, "null pointer argument");
+  const size_t smem = (size_t)n_parts * k * 16;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && !(attr_dev_mask & (1 << dev))) {
+    CMR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_dev_mask |= (1 << dev);
+  }
+  topk_merge_kernel<<<n_queries, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
+      in_scores, (const long long*)in_ids, in_counts, n_parts, n_queries, k, out_scores, (long long*)out_ids,
+      out_counts);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}

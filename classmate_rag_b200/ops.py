@@ -138,3 +138,86 @@ def bm25_topk(index, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int, *,
                                buffers.ws.numel(), _stream())
     _lib.check(rc)
     return buffers.scores, buffers.ids, buffers.counts, buffers.flags
+
+
+def gather_rows(emb: torch.Tensor, ids: torch.Tensor, *, row_offset: int = 0) -> torch.Tensor:
+    """Rows ``ids - row_offset`` of emb (bf16 [N, D]); ids outside this shard
+    (or -1) give zero rows.  ids: int64 [...]; returns bf16 [..., D]."""
+    _require_cuda(emb, "emb")
+    _require_cuda(ids, "ids")
+    if ids.dtype != torch.int64:
+        raise ValueError("ids must be int64")
+    n_rows, dim = emb.shape
+    out = torch.empty((*ids.shape, dim), dtype=torch.bfloat16, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.load().cmr_gather_rows(emb.data_ptr(), n_rows, dim, row_offset, ids.data_ptr(),
+                                               ids.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def mmr_select(cand_rows: torch.Tensor, cand_sims: torch.Tensor, cand_ids: torch.Tensor,
+               cand_counts: torch.Tensor, k: int, lambd: float = 0.5):
+    """Greedy MMR over each query's pool.  cand_rows bf16 [B, pool, D], cand_sims
+    f64 [B, pool], cand_ids i64 [B, pool], cand_counts i32 [B].  Returns
+    (ids i64 [B,k], sims f64 [B,k], counts i32 [B])."""
+    for name, t in (("cand_rows", cand_rows), ("cand_sims", cand_sims), ("cand_ids", cand_ids),
+                    ("cand_counts", cand_counts)):
+        _require_cuda(t, name)
+    b, pool, dim = cand_rows.shape
+    k = min(k, pool)
+    dev = cand_rows.device
+    out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    out_sims = torch.empty((b, k), dtype=torch.float64, device=dev)
+    out_counts = torch.empty((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_mmr_select(cand_rows.data_ptr(), cand_sims.data_ptr(), cand_ids.data_ptr(),
+                                              cand_counts.data_ptr(), b, pool, dim, k, float(lambd),
+                                              out_ids.data_ptr(), out_sims.data_ptr(), out_counts.data_ptr(),
+                                              _stream()))
+    return out_ids, out_sims, out_counts
+
+
+def hybrid_fuse(vec, bm, *, top_k: int, rrf_k: int = 60, w_vec: float = 1.0, w_bm: float = 1.0):
+    """RRF + merge + final order.  vec = (ids i64 [B,kv], sims f64 [B,kv], counts i32 [B]);
+    bm = (ids, scores, counts) or None for the non-hybrid path.  Returns
+    (ids [B,top_k], fused, vector_distance (NaN = None), bm25_score (NaN = None), counts)."""
+    v_ids, v_sims, v_cnt = vec
+    for name, t in (("vec ids", v_ids), ("vec sims", v_sims), ("vec counts", v_cnt)):
+        _require_cuda(t, name)
+    b, kv = v_ids.shape
+    dev = v_ids.device
+    if bm is not None:
+        b_ids, b_sc, b_cnt = bm
+        for name, t in (("bm ids", b_ids), ("bm scores", b_sc), ("bm counts", b_cnt)):
+            _require_cuda(t, name)
+        kb = b_ids.shape[1]
+        bp = (b_ids.data_ptr(), b_sc.data_ptr(), b_cnt.data_ptr())
+    else:
+        kb, bp = 0, (None, None, None)
+    out_ids = torch.empty((b, top_k), dtype=torch.int64, device=dev)
+    out_fused = torch.empty((b, top_k), dtype=torch.float64, device=dev)
+    out_vd = torch.empty((b, top_k), dtype=torch.float64, device=dev)
+    out_bm = torch.empty((b, top_k), dtype=torch.float64, device=dev)
+    out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_hybrid_fuse(v_ids.data_ptr(), v_sims.data_ptr(), v_cnt.data_ptr(), kv, *bp, kb, b,
+                                               float(w_vec), float(w_bm), int(rrf_k), int(top_k),
+                                               out_ids.data_ptr(), out_fused.data_ptr(), out_vd.data_ptr(),
+                                               out_bm.data_ptr(), out_cnt.data_ptr(), _stream()))
+    return out_ids, out_fused, out_vd, out_bm, out_cnt
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor, counts: torch.Tensor):
+    """Merge per-shard lists: scores f64 [G,B,k], ids i64 [G,B,k], counts i32 [G,B]
+    -> (scores [B,k], ids [B,k], counts [B]) ordered by (score desc, id asc)."""
+    for name, t in (("scores", scores), ("ids", ids), ("counts", counts)):
+        _require_cuda(t, name)
+    g, b, k = scores.shape
+    dev = scores.device
+    out_s = torch.empty((b, k), dtype=torch.float64, device=dev)
+    out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
+    out_c = torch.empty((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_topk_merge(scores.data_ptr(), ids.data_ptr(), counts.data_ptr(), g, b, k,
+                                              out_s.data_ptr(), out_i.data_ptr(), out_c.data_ptr(), _stream()))
+    return out_s, out_i, out_c

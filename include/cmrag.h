@@ -126,6 +126,50 @@ int cmr_bm25_topk(const cmr_lex_index* ix, const int32_t* q_terms, const int32_t
                   int32_t* out_counts, int32_t* out_flags, void* workspace,
                   size_t workspace_bytes, cmr_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * A4  MMR re-ordering of the dense pool (rag/retrieval/fusion.py:39-61,80-102).
+ *     cand_rows   device, bf16 [n_queries, pool, dim]: the pool's embeddings
+ *                 (cmr_gather_rows fills it from the matrix)
+ *     cand_sims   device, float64 [n_queries, pool]: exact q.c (cmr_dense_topk scores)
+ *     cand_ids    device, int64 [n_queries, pool];  cand_counts int32 [n_queries]
+ *     out_ids / out_sims [n_queries, k] in MMR order, out_counts [n_queries]
+ *   Similarities between candidates are the pinned exact float64 dots, the
+ *   greedy combine lambda*sim_q - (1-lambda)*max(sim_cc) is float64; first pick
+ *   = argmax (lowest index on ties), later picks by strict '>' in ascending index.
+ * ---------------------------------------------------------------------- */
+int cmr_gather_rows(const uint16_t* emb, int64_t n_rows, int dim, int64_t row_offset,
+                    const int64_t* ids, int n_ids, uint16_t* out_rows, cmr_stream_t stream);
+
+int cmr_mmr_select(const uint16_t* cand_rows, const double* cand_sims, const int64_t* cand_ids,
+                   const int32_t* cand_counts, int n_queries, int pool, int dim, int k,
+                   double lambda, int64_t* out_ids, double* out_sims, int32_t* out_counts,
+                   cmr_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * A3 + A5  Reciprocal Rank Fusion, per-id merge and final order of
+ *     HybridRetriever.retrieve (rag/retrieval/fusion.py:17-36,108-167).
+ *     vec_* : dense list in its final (post-MMR) order, sims = q.c
+ *     bm_*  : BM25 list;  kb = 0 gives the non-hybrid path (w_vec is then 1.0)
+ *     fused = sum w * (1.0 / (rrf_k + rank)), float64; vector_distance = 1 - sim;
+ *     order: (fused, -vector_distance) descending, stable over insertion order
+ *     (vector items, then BM25-only items).  out_vdist / out_bm25 are NaN where
+ *     the reference has None.
+ * ---------------------------------------------------------------------- */
+int cmr_hybrid_fuse(const int64_t* vec_ids, const double* vec_sims, const int32_t* vec_counts, int kv,
+                    const int64_t* bm_ids, const double* bm_scores, const int32_t* bm_counts, int kb,
+                    int n_queries, double w_vec, double w_bm, int rrf_k, int top_k,
+                    int64_t* out_ids, double* out_fused, double* out_vdist, double* out_bm25,
+                    int32_t* out_counts, cmr_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K7  Merge of per-shard top-k lists after the all-gather (multi-GPU; no
+ *     reference counterpart).  in_* are [n_parts, n_queries, k]; order is
+ *     (score desc, id asc), so the result does not depend on the sharding.
+ * ---------------------------------------------------------------------- */
+int cmr_topk_merge(const double* in_scores, const int64_t* in_ids, const int32_t* in_counts,
+                   int n_parts, int n_queries, int k, double* out_scores, int64_t* out_ids,
+                   int32_t* out_counts, cmr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
