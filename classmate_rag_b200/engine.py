@@ -1,0 +1,223 @@
+"""Device-level hybrid search engine: the launch sequence of the hot path.
+
+    queries (bf16) --cmr_dense_topk--> pool --cmr_gather_rows/cmr_mmr_select--> dense list
+    query terms    --cmr_bm25_topk---> lexical list
+    both           --cmr_hybrid_fuse-> (ids, fused, vector_distance, bm25_score)
+
+This is what HybridRetriever.retrieve (reference rag/retrieval/fusion.py:108-167)
+drives per question; the engine exposes it batched and asynchronous on the
+current CUDA stream, optionally replayed from a CUDA graph so that one query is
+one graph launch.  On a row-sharded corpus (one process per GPU) the per-shard
+top-k lists are exchanged with one all-gather each and merged by
+cmr_topk_merge (classmate_rag_b200.sharding).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .lexical import LexicalIndex, pack_queries
+
+
+@dataclass
+class SearchParams:
+    """Mirrors the knobs of HybridRetriever (fusion.py:64-78)."""
+    top_k: int = 8
+    k_vector: int = 8
+    k_bm25: int = 8
+    rrf_k: int = 60
+    weight_vector: float = 1.0
+    weight_bm25: float = 1.0
+    use_mmr: bool = True
+    mmr_lambda: float = 0.5
+    mmr_max_pool: int = 24
+    hybrid: bool = True
+
+    @property
+    def pool(self) -> int:
+        return max(self.k_vector, self.mmr_max_pool) if self.use_mmr else self.k_vector
+
+
+class HybridEngine:
+    """One shard (or the whole corpus) resident on one GPU."""
+
+    def __init__(self, emb: torch.Tensor, lex: Optional[LexicalIndex], *, row_offset: int = 0,
+                 max_row_norm: float = 1.0, comm=None):
+        if not emb.is_cuda or emb.dtype != torch.bfloat16:
+            raise RuntimeError("emb must be a CUDA bfloat16 matrix (no CPU path)")
+        self.emb = emb
+        self.lex = lex
+        self.row_offset = int(row_offset)
+        self.max_row_norm = float(max_row_norm)
+        self.comm = comm  # classmate_rag_b200.sharding.ShardComm or None
+        self.device = emb.device
+        self._dense_ws = {}
+        self._bm_buf = {}
+
+    # -- stage helpers -------------------------------------------------------
+    def _cert_eps(self, dim: int) -> float:
+        # |fp32 tensor-pipe score - exact| <= dim * 2^-22 * |q| * max|c| (conservative)
+        return dim * 2.0 ** -22 * 1.01 * self.max_row_norm
+
+    def dense_pool(self, q_bf16: torch.Tensor, k: int, row_mask: Optional[torch.Tensor] = None):
+        n, d = self.emb.shape
+        b = q_bf16.shape[0]
+        key = (n, d, b, k)
+        ws = self._dense_ws.get(key)
+        if ws is None:
+            ws = self._dense_ws[key] = ops.DenseWorkspace(n, d, b, k, self.device)
+        out = ops.dense_topk(self.emb, q_bf16, k, row_mask=row_mask, row_offset=self.row_offset,
+                             cert_eps=self._cert_eps(d), workspace=ws)
+        if self.comm is not None:
+            out = self.comm.merge_topk(*out)
+        return out
+
+    def lexical_topk(self, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int,
+                     row_mask: Optional[torch.Tensor] = None):
+        b = q_ptr.numel() - 1
+        key = (b, k)
+        buf = self._bm_buf.get(key)
+        if buf is None:
+            import ctypes as C
+            from . import _lib
+            st = self.lex.struct()
+            with torch.cuda.device(self.device):
+                nbytes = _lib.load().cmr_bm25_workspace_bytes(C.byref(st), b, k)
+            if nbytes == 0:
+                raise ValueError("unsupported bm25 shape: " + _lib.last_error())
+            buf = self._bm_buf[key] = ops.TopkBuffers(b, k, nbytes, self.device)
+        out = ops.bm25_topk(self.lex, q_terms, q_ptr, k, row_mask=row_mask, row_offset=self.row_offset,
+                            buffers=buf)
+        if self.comm is not None:
+            out = self.comm.merge_topk(*out)
+        return out
+
+    def pool_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        rows = ops.gather_rows(self.emb, ids, row_offset=self.row_offset)
+        if self.comm is not None:
+            rows = self.comm.sum_rows(rows)
+        return rows
+
+    # -- the hot path --------------------------------------------------------
+    def search(self, q_bf16: torch.Tensor, q_terms: Optional[torch.Tensor], q_ptr: Optional[torch.Tensor],
+               p: SearchParams, *, dense_mask: Optional[torch.Tensor] = None,
+               lex_mask: Optional[torch.Tensor] = None):
+        """Returns device tensors (ids i64 [B,top_k], fused f64, vector_distance f64
+        (NaN = None), bm25_score f64 (NaN = None), counts i32 [B]); nothing is
+        synchronised."""
+        if q_bf16.dim() == 1:
+            q_bf16 = q_bf16[None]
+        hybrid = p.hybrid and self.lex is not None and q_terms is not None
+        k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
+        pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
+        pool = min(pool, 64) if p.use_mmr else pool
+        scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
+        self.last_dense_flags = flags
+        if p.use_mmr:
+            rows = self.pool_rows(ids)
+            v_ids, v_sims, v_cnt = ops.mmr_select(rows, scores, ids, counts, min(k_vec, pool), p.mmr_lambda)
+        else:
+            v_ids, v_sims, v_cnt = ids, scores, counts
+        bm = None
+        if hybrid:
+            b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+            bm = (b_ids, b_sc, b_cnt)
+        return ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
+                               w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+
+
+class GraphedSearch:
+    """One fixed-shape hybrid search captured in a CUDA graph: host inputs are
+    copied into static device buffers, the whole kernel sequence replays as one
+    graph launch, results land in static pinned host buffers.
+
+    This is the end-to-end call with HOST buffers that bench.py's ``e2e`` times."""
+
+    def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64):
+        self.engine, self.p, self.b = engine, p, n_queries
+        dev = engine.device
+        d = engine.emb.shape[1]
+        self.hybrid = p.hybrid and engine.lex is not None
+        self.max_terms = max_terms
+        # static device inputs
+        self.q_f32 = torch.zeros((n_queries, d), dtype=torch.float32, device=dev)
+        self.q_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32, device=dev)
+        self.q_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32, device=dev)
+        # pinned host staging
+        self.h_q = torch.zeros((n_queries, d), dtype=torch.float32).pin_memory()
+        self.h_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32).pin_memory()
+        self.h_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32).pin_memory()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self._capture()
+
+    def _run(self):
+        q_bf16 = ops.f32_to_bf16(self.q_f32)
+        return self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
+                                  self.q_ptr if self.hybrid else None, self.p)
+
+    def _capture(self):
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            for _ in range(2):  # warm-up: one-time attribute / occupancy calls, allocations
+                self.out = self._run()
+            self.stream.synchronize()
+            if self.engine.comm is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self.out = self._run()
+                self.graph = g
+            ids, fused, vd, bm, cnt = self.out
+            self.h_ids = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
+            self.h_fused = torch.empty(fused.shape, dtype=fused.dtype).pin_memory()
+            self.h_vd = torch.empty(vd.shape, dtype=vd.dtype).pin_memory()
+            self.h_bm = torch.empty(bm.shape, dtype=bm.dtype).pin_memory()
+            self.h_cnt = torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory()
+
+    @property
+    def h2d_bytes(self) -> int:
+        n = self.h_q.numel() * 4
+        if self.hybrid:
+            n += self.h_terms.numel() * 4 + self.h_ptr.numel() * 4
+        return n
+
+    @property
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt))
+
+    def set_queries(self, q_f32: np.ndarray, term_lists: Optional[Sequence[Sequence[int]]]):
+        """Stage host inputs into the pinned buffers (not part of the device work)."""
+        self.h_q.copy_(torch.from_numpy(np.ascontiguousarray(q_f32, dtype=np.float32)).reshape(self.h_q.shape))
+        if self.hybrid:
+            flat, ptr = pack_queries(term_lists)
+            if int(ptr[-1]) > self.h_terms.numel():
+                raise ValueError("too many query tokens for this graph (raise max_terms)")
+            self.h_terms[: int(ptr[-1])].copy_(flat[: int(ptr[-1])])
+            self.h_ptr.copy_(ptr)
+
+    def launch(self):
+        """H2D copies + graph replay + D2H copies on the engine's stream (asynchronous)."""
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            self.q_f32.copy_(self.h_q, non_blocking=True)
+            if self.hybrid:
+                self.q_terms.copy_(self.h_terms, non_blocking=True)
+                self.q_ptr.copy_(self.h_ptr, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.out = self._run()
+            ids, fused, vd, bm, cnt = self.out
+            self.h_ids.copy_(ids, non_blocking=True)
+            self.h_fused.copy_(fused, non_blocking=True)
+            self.h_vd.copy_(vd, non_blocking=True)
+            self.h_bm.copy_(bm, non_blocking=True)
+            self.h_cnt.copy_(cnt, non_blocking=True)
+
+    def __call__(self, q_f32: np.ndarray, term_lists=None):
+        self.set_queries(q_f32, term_lists)
+        self.launch()
+        self.stream.synchronize()
+        return self.h_ids.numpy(), self.h_fused.numpy(), self.h_vd.numpy(), self.h_bm.numpy(), self.h_cnt.numpy()

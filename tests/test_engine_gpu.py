@@ -1,0 +1,108 @@
+"""GPU parity of the whole hot path (dense -> MMR -> BM25 -> RRF -> final
+order) through the engine, eager and CUDA-graph, vs the oracle pipeline."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def _oracle_hybrid(emb_bits, q_bits, lex_arrays, terms, p):
+    tp, pd, tf, dl, idf, avgdl = lex_arrays
+    hybrid = p.hybrid and terms is not None
+    k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
+    pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
+    ids, sc = o.dense_topk(q_bits, emb_bits, pool)
+    if p.use_mmr and len(ids):
+        order = o.mmr_order_bf16(q_bits, emb_bits[ids], k_vec, p.mmr_lambda)
+        ids, sc = ids[order], sc[order]
+    else:
+        ids, sc = ids[:k_vec], sc[:k_vec]
+    vec = [(int(i), 1.0 - float(s)) for i, s in zip(ids, sc)]
+    bm = []
+    if hybrid:
+        full = o.bm25_scores_csr(tp, pd, tf, dl, idf, avgdl, terms)
+        bi, bs = o.bm25_topk(full, p.k_bm25)
+        bm = [(int(i), float(s)) for i, s in zip(bi, bs)]
+    return o.hybrid_merge(vec, bm, p.top_k, p.rrf_k, p.weight_vector, p.weight_bm25, hybrid)
+
+
+def _check(out, want_lists):
+    ids, fused, vd, bm, cnt = out
+    for b, want in enumerate(want_lists):
+        n = int(cnt[b])
+        assert n == len(want)
+        for i, w in enumerate(want):
+            assert int(ids[b, i]) == w["id"]
+            assert float(fused[b, i]) == w["fused"]
+            g_vd = None if math.isnan(float(vd[b, i])) else float(vd[b, i])
+            g_bm = None if math.isnan(float(bm[b, i])) else float(bm[b, i])
+            assert g_vd == w["vector_distance"] and g_bm == w["bm25_score"]
+
+
+@pytest.fixture(scope="module")
+def small_world():
+    from classmate_rag_b200 import lexical, synth
+    from classmate_rag_b200.engine import HybridEngine
+    n, d, vocab = 30000, 256, 3000
+    emb = synth.dense_corpus(n, d, "cuda")
+    doc_ptr, tokens = synth.lexical_corpus(n, vocab, 24, "cuda")
+    lex = lexical.build_lexical_index(doc_ptr, tokens, vocab, tile_docs=2048)
+    eng = HybridEngine(emb, lex)
+    q, planted = synth.dense_queries(n, d, 6, "cuda")
+    terms = synth.lexical_queries(6, vocab)
+    terms[2][1] = -1
+    terms[3][5] = terms[3][0]
+    lex_arrays = (lex.term_ptr.cpu().numpy(), lex.post_doc.cpu().numpy(),
+                  (lex.post_tf.cpu().to(torch.int32) & 0xFFFF).numpy(), lex.doc_len.cpu().numpy(),
+                  lex.idf_host, lex.avgdl)
+    return eng, emb, lex, q, planted, terms, lex_arrays
+
+
+@pytest.mark.parametrize("hybrid,use_mmr,top_k", [(True, True, 8), (True, False, 10), (False, True, 12), (False, False, 5)])
+def test_engine_matches_oracle_pipeline(small_world, hybrid, use_mmr, top_k):
+    from classmate_rag_b200 import lexical, ops
+    from classmate_rag_b200.engine import SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    p = SearchParams(top_k=top_k, hybrid=hybrid, use_mmr=use_mmr)
+    q_bf16 = ops.f32_to_bf16(q)
+    qt, qp = lexical.pack_queries(terms)
+    out = eng.search(q_bf16, qt.cuda(), qp.cuda(), p)
+    torch.cuda.synchronize()
+    out = [t.cpu().numpy() for t in out]
+    emb_bits, q_bits = _bits(emb), _bits(q_bf16)
+    want = [_oracle_hybrid(emb_bits, q_bits[b], lex_arrays, terms[b] if hybrid else None, p) for b in range(len(terms))]
+    _check(out, want)
+    assert int(eng.last_dense_flags.sum()) == 0
+    if not use_mmr:  # the planted row is the exact top-1 of the dense list
+        for b in range(len(terms)):
+            assert int(planted[b]) in [w["id"] for w in want[b]] or hybrid
+
+
+def test_graphed_search_equals_eager_and_is_deterministic(small_world):
+    from classmate_rag_b200 import lexical, ops
+    from classmate_rag_b200.engine import GraphedSearch, SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    p = SearchParams(top_k=10)
+    gs = GraphedSearch(eng, p, n_queries=1, max_terms=16)
+    assert gs.graph is not None
+    for b in range(3):
+        got = gs(q[b:b + 1].cpu().numpy(), [terms[b]])
+        got = [g.copy() for g in got]
+        again = gs(q[b:b + 1].cpu().numpy(), [terms[b]])
+        for a, c in zip(got, again):
+            assert a.tobytes() == c.tobytes()           # run twice, bit-compare
+        qt, qp = lexical.pack_queries([terms[b]])
+        eager = eng.search(ops.f32_to_bf16(q[b:b + 1]), qt.cuda(), qp.cuda(), p)
+        torch.cuda.synchronize()
+        for a, c in zip(got, eager):
+            assert a.tobytes() == c.cpu().numpy().tobytes()
+    assert gs.h2d_bytes > 0 and gs.d2h_bytes > 0
