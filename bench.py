@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- hybrid (dense + BM25 + MMR + RRF k=60) top-10 retrieval over a
+synthetic 10M x 768 corpus on 1..8 B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # one JSON line (rank 0)
+  python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
+
+A step is one batch of `--batch` hybrid queries through the hot path.
+`value` is whole-job QPS with queries already resident in HBM; `e2e` is the same
+through the host-buffer call (pinned H2D of the queries + D2H of the results
+inside the timed region, CUDA graph replay); `latency` is the single-query
+(B=1) end-to-end latency distribution.  The corpus is fixed, so adding GPUs is
+strong scaling: rows are sharded, only per-shard top-k lists are exchanged.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "hybrid_top10_qps"
+UNIT = "queries/s"
+VOCAB = 30000
+MEAN_LEN = 64
+TOP_K = 10
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--cpu-sample-rows", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-iters", type=int, default=200)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.rows / 1e6:g}M x {a.dim} hybrid (dense bf16 exact top-k + MMR pool 24 + BM25 V={VOCAB} "
+            f"mean_len={MEAN_LEN} + RRF k=60) top-{TOP_K}, batch {a.batch} queries/step")
+
+
+# --------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample during the timed region)
+# --------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# reference arm: the CPU port of the reference path on a bounded sample
+# --------------------------------------------------------------------------
+def _cpu_sample(a, n_sample):
+    import torch
+    from classmate_rag_b200 import synth
+    from oracle.cpu_baseline import ReferencePort
+    n_sample = min(n_sample, a.rows)
+    emb = synth.dense_corpus(a.rows, a.dim, "cpu", row_lo=0, row_hi=n_sample).float().numpy()
+    doc_ptr, tokens = synth.lexical_corpus(a.rows, VOCAB, MEAN_LEN, "cpu", doc_lo=0, doc_hi=n_sample)
+    ptr, tok = doc_ptr.numpy(), tokens.numpy()
+    words = np.array([f"w{chr(97 + i % 26)}{chr(97 + (i // 26) % 26)}{chr(97 + (i // 676) % 26)}{chr(97 + i // 17576)}"
+                      for i in range(VOCAB)])
+    docs = [words[tok[ptr[i]:ptr[i + 1]]].tolist() for i in range(n_sample)]
+    port = ReferencePort(emb, docs)
+    nq = 64
+    q = torch.nn.functional.normalize(torch.from_numpy(emb[:nq]) + 0.5 * torch.randn(nq, a.dim) / a.dim ** 0.5, dim=1).numpy()
+    texts = [" ".join(words[[t for t in terms if t >= 0]]) for terms in synth.lexical_queries(nq, VOCAB)]
+    return port, q, texts, n_sample
+
+
+def cpu_baseline(a, budget_s=20.0):
+    from oracle.cpu_baseline import host_cores, time_reference_port
+    port, q, texts, n_sample = _cpu_sample(a, a.cpu_sample_rows)
+    sec, n = time_reference_port(port, q, texts, TOP_K, budget_s=budget_s)
+    qps_sample = 1.0 / sec
+    return {"value": qps_sample * n_sample / a.rows, "unit": UNIT, "cores": host_cores(), "kind": "port",
+            "sample": (f"first {n_sample} rows/docs of the workload, {n} single queries, median {sec * 1e3:.1f} ms/query "
+                       f"({qps_sample:.3f} QPS on the sample); the reference path is O(rows) per query (per-query BM25Okapi "
+                       f"rebuild + full scan), so QPS is scaled linearly by {n_sample}/{a.rows}; dense stage is an exact "
+                       f"NumPy fp32 stand-in for Chroma HNSW (chromadb not installable offline)"),
+            "qps_on_sample": qps_sample}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import host_cores
+    port, q, texts, n_sample = _cpu_sample(a, a.cpu_sample_rows)
+    times = []
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        port.retrieve(q[i % len(q)], texts[i % len(texts)], TOP_K)
+        if i >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = float(np.mean(times) * 1e3)
+    qps = (1e3 / ms) * n_sample / a.rows
+    cb = {"value": qps, "unit": UNIT, "cores": host_cores(), "kind": "port",
+          "sample": f"each step = 1 query on the first {n_sample} rows/docs; QPS scaled linearly by {n_sample}/{a.rows} (O(rows) path)"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+                      "config": {"workload": workload_name(a)}, "cpu_baseline": cb,
+                      "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    from classmate_rag_b200 import lexical, ops, sharding, synth
+    from classmate_rag_b200.engine import GraphedSearch, HybridEngine, SearchParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sm, cc_major, cc_minor = ops.device_info()
+
+    # ---- build this rank's shard -----------------------------------------
+    t_build = time.perf_counter()
+    lo, hi = sharding.shard_range(a.rows, rank, world)
+    emb = synth.dense_corpus(a.rows, a.dim, dev, row_lo=lo, row_hi=hi)
+    doc_ptr, tokens = synth.lexical_corpus(a.rows, VOCAB, MEAN_LEN, dev, doc_lo=lo, doc_hi=hi)
+    if world > 1:
+        tok_counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        tok_counts[rank] = tokens.numel()
+        dist.all_reduce(tok_counts)
+        stats = sharding.global_corpus_stats(doc_ptr, tokens, VOCAB, doc_lo=lo, n_docs_total=a.rows,
+                                             token_offset=int(tok_counts[:rank].sum()))
+    else:
+        stats = lexical.corpus_stats(doc_ptr, tokens, VOCAB)
+    lex = lexical.build_lexical_index(doc_ptr, tokens, VOCAB, stats=stats)
+    del doc_ptr, tokens
+    torch.cuda.empty_cache()
+    comm = sharding.ShardComm() if world > 1 else None
+    eng = HybridEngine(emb, lex, row_offset=lo, comm=comm)
+    p = SearchParams(top_k=TOP_K)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+
+    # ---- queries -----------------------------------------------------------
+    n_steps = a.warmup + a.steps
+    nq = a.batch * n_steps
+    q_f32, planted = synth.dense_queries(a.rows, a.dim, nq, dev)
+    terms = synth.lexical_queries(nq, VOCAB)
+    q_bf16 = ops.f32_to_bf16(q_f32)
+    dev_terms = []
+    for s in range(n_steps):
+        qt, qp = lexical.pack_queries(terms[s * a.batch:(s + 1) * a.batch])
+        dev_terms.append((qt.to(dev), qp.to(dev)))
+    posting_bytes = [sum(lex.posting_bytes(t) for t in terms[s * a.batch:(s + 1) * a.batch]) for s in range(n_steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident inputs, CUDA events, max over ranks -------------
+    clocks = ClockSampler(local)
+    stream = torch.cuda.current_stream()
+    dense_ms, lex_ms = [], []
+    for s in range(a.warmup):
+        eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(a.warmup, n_steps):
+        eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p)
+    ev1.record(stream)
+    barrier()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = total_ms / a.steps
+    value = a.batch * a.steps / (total_ms * 1e-3)
+
+    # ---- per-stage device time (same steps again, events around the two scans) ---
+    pool = p.pool
+    for s in range(a.warmup, n_steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(stream)
+        eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool)
+        e[1].record(stream)
+        e[2].record(stream)
+        eng.lexical_topk(*dev_terms[s], p.k_bm25)
+        e[3].record(stream)
+        torch.cuda.synchronize()
+        dense_ms.append(e[0].elapsed_time(e[1]))
+        lex_ms.append(e[2].elapsed_time(e[3]))
+    clock_info = clocks.stop()
+    dense_avg = float(np.mean(dense_ms))
+    lex_avg = float(np.mean(lex_ms))
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        hbm_peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s"
+    dense_bytes = (hi - lo) * a.dim * 2  # one scan pass serves the whole batch (<= 32 queries)
+    passes = (a.batch + 31) // 32
+    achieved = dense_bytes * passes / (dense_avg * 1e-3) / 1e9
+    lex_bytes = float(np.mean(posting_bytes[a.warmup:]))
+    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel (events bracket cmr_dense_topk = scan + finalize)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dense_bytes,
+                "avg_launch_ms": dense_avg, "share_of_step": dense_avg / ms_per_step,
+                "bm25": {"kernel": "bm25_tile_kernel (+finalize)", "algorithmic_bytes_per_step": lex_bytes,
+                         "avg_ms_per_step": lex_avg, "achieved": lex_bytes / (lex_avg * 1e-3) / 1e9, "unit": "GB/s",
+                         "frac": lex_bytes / (lex_avg * 1e-3) / 1e9 / hbm_peak, "share_of_step": lex_avg / ms_per_step}}
+
+    # ---- e2e: host buffers in, host results out, every step ---------------------
+    q_host = q_f32.cpu().numpy()
+    gs = GraphedSearch(eng, p, a.batch, max_terms=16)
+    for s in range(a.warmup):
+        gs(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for s in range(a.warmup, n_steps):
+        last = gs(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": a.batch * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": gs.h2d_bytes,
+           "d2h_bytes_per_step": gs.d2h_bytes, "ms_per_step": e2e_s / a.steps * 1e3,
+           "path": "GraphedSearch: pinned host queries -> H2D -> CUDA-graph replay of the kernel sequence -> D2H results"}
+    # sanity on the last batch: the planted row is the dense top-1 unless MMR/RRF reorder it out of the top-10
+    ids_last = last[0]
+    planted_last = planted[(n_steps - 1) * a.batch:].numpy()
+    hit = float(np.mean([planted_last[i] in ids_last[i] for i in range(a.batch)]))
+
+    # ---- single-query latency (B=1), end to end ----------------------------------
+    g1 = GraphedSearch(eng, p, 1, max_terms=16)
+    lat = []
+    for i in range(min(20, nq)):
+        g1(q_host[i:i + 1], [terms[i]])
+    barrier()
+    for i in range(a.latency_iters):
+        j = i % nq
+        t1 = time.perf_counter()
+        g1(q_host[j:j + 1], [terms[j]])
+        lat.append((time.perf_counter() - t1) * 1e3)
+    lat = np.array(lat)
+    latency = {"batch": 1, "iters": int(a.latency_iters), "p50_ms": float(np.percentile(lat, 50)),
+               "p95_ms": float(np.percentile(lat, 95)), "p99_ms": float(np.percentile(lat, 99)),
+               "qps_serial": float(1e3 / np.mean(lat)),
+               "hbm_frac_at_p50": (hi - lo) * a.dim * 2 / (float(np.percentile(lat, 50)) * 1e-3) / 1e9 / hbm_peak}
+
+    # kernels per step: f32->bf16 is outside the resident loop; scan, finalize, gather, mmr, bm25 tile, bm25 finalize, fuse
+    launches_per_step = 7 + (2 if world > 1 else 0)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "top_k": TOP_K,
+                      "vocab": VOCAB, "postings_this_rank": lex.n_postings, "rows_this_rank": hi - lo,
+                      "parallelism": f"row-shard x{world}", "sm_count": sm, "cc": f"{cc_major}.{cc_minor}",
+                      "l2": "inputs larger than L2 (matrix %.1f GB per rank)" % (dense_bytes / 1e9),
+                      "index_build_s": build_s},
+           "roofline": roofline, "e2e": e2e, "latency": latency, "gpu_launches": launches_per_step * a.steps,
+           "clocks": clock_info, "planted_top1_in_top10": hit}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a)
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

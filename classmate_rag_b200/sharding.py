@@ -1,0 +1,98 @@
+"""Row-sharding of the corpus over the GPUs of one box (one process per GPU).
+
+The dense matrix and the inverted index are partitioned by contiguous row
+ranges; every rank scores the same queries against its shard and only the
+per-shard top-k candidates travel: one all-gather of B x k x (score, id) per
+retriever, merged by cmr_topk_merge with the total order (score desc, id asc),
+so the result is identical for any number of shards.  The MMR pool's embedding
+rows are reassembled with one all-reduce (each row is non-zero on exactly one
+rank).  Index build needs one all-reduce of df[V] / token totals / first
+positions so that every shard scores with the corpus-wide idf and avgdl.
+The reference has no distributed code; this is new.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .lexical import GlobalStats
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 16) -> Tuple[int, int]:
+    """Contiguous, `align`-row aligned split of n rows."""
+    per = (n + world - 1) // world
+    per = (per + align - 1) // align * align
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class ShardComm:
+    """The two exchanges of the sharded hot path."""
+
+    def __init__(self, group=None, merge_fn: Optional[Callable] = None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._merge_fn = merge_fn  # injectable for the CPU (gloo) tests
+
+    def _merge(self, scores, ids, counts):
+        if self._merge_fn is not None:
+            return self._merge_fn(scores, ids, counts)
+        from . import ops
+        return ops.topk_merge(scores, ids, counts)
+
+    def merge_topk(self, scores: torch.Tensor, ids: torch.Tensor, counts: torch.Tensor, flags: torch.Tensor):
+        """All-gather the per-shard lists (one collective) and merge them."""
+        b, k = scores.shape
+        # one packed float64 message per rank: [scores | ids (bit-cast) | count | flag]
+        msg = torch.empty((b, 2 * k + 2), dtype=torch.float64, device=scores.device)
+        msg[:, :k] = scores
+        msg[:, k:2 * k] = ids.view(torch.float64)
+        msg[:, 2 * k] = counts.to(torch.float64)
+        msg[:, 2 * k + 1] = flags.to(torch.float64)
+        flat = torch.empty((self.world * b, 2 * k + 2), dtype=torch.float64, device=scores.device)
+        dist.all_gather_into_tensor(flat, msg, group=self.group)
+        out = flat.view(self.world, b, 2 * k + 2)
+        g_scores = out[:, :, :k].contiguous()
+        g_ids = out[:, :, k:2 * k].contiguous().view(torch.int64)
+        g_counts = out[:, :, 2 * k].to(torch.int32).contiguous()
+        m_scores, m_ids, m_counts = self._merge(g_scores, g_ids, g_counts)
+        m_flags = out[:, :, 2 * k + 1].amax(dim=0).to(torch.int32)
+        return m_scores, m_ids, m_counts, m_flags
+
+    def sum_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """Reassemble gathered bf16 rows: exactly one rank holds each row, the
+        others hold zeros, so an integer SUM is exact."""
+        buf = rows.contiguous().view(torch.int32)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        return buf.view(torch.bfloat16).view(rows.shape)
+
+
+def global_corpus_stats(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int, *, doc_lo: int,
+                        n_docs_total: int, token_offset: int, group=None) -> GlobalStats:
+    """Corpus-wide (N, total tokens, df, first-appearance order) from shard-local
+    token arrays: three all-reduces.  `token_offset` = number of tokens in all
+    earlier shards (so first positions are comparable across shards)."""
+    dev = tokens.device
+    tok = tokens.long()
+    n_local = doc_ptr.numel() - 1
+    total_local = int(tok.numel())
+    big = torch.iinfo(torch.int64).max
+    first_pos = torch.full((n_terms,), big, dtype=torch.int64, device=dev)
+    df = torch.zeros(n_terms, dtype=torch.int64, device=dev)
+    if total_local:
+        doc_len = (doc_ptr[1:] - doc_ptr[:-1]).long()
+        doc_of = torch.repeat_interleave(torch.arange(n_local, device=dev), doc_len)
+        key = torch.unique(tok * max(n_local, 1) + doc_of)
+        df = torch.bincount(key // max(n_local, 1), minlength=n_terms)
+        first_pos.scatter_reduce_(0, tok, torch.arange(total_local, device=dev) + token_offset, reduce="amin")
+    total = torch.tensor([total_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(df, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(first_pos, op=dist.ReduceOp.MIN, group=group)
+    order = torch.argsort(first_pos, stable=True)
+    n_seen = int((df > 0).sum())
+    return GlobalStats(n_docs_total, int(total.item()), df.cpu().numpy().astype(np.int64), order[:n_seen].cpu().numpy())
