@@ -30,6 +30,7 @@
 
 namespace cmr {
 
+typedef void (*tile_fn_t)(cmr_lex_index, const int*, const int*, const uint8_t*, KeyD*);
 constexpr int BM_THREADS = 512;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BMF_THREADS = 1024;
@@ -45,7 +46,18 @@ __device__ __forceinline__ double ldg_stream_f64(const double* p) {
   return r;
 }
 
-template <int KPL>
+constexpr int BM_MAXQ = 64;  // query tokens staged per chunk
+constexpr int BM_U = 8;      // postings in flight per thread
+
+__device__ __forceinline__ u32 ldg_stream_u32(const u32* p) {
+  u32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// PACKED: 4-byte postings (code << 16 | tile-local doc) + float64 factor table;
+// otherwise int32 doc + float64 factor per posting.
+template <int KPL, bool PACKED>
 __global__ void __launch_bounds__(BM_THREADS)
 bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr,
                  const uint8_t* __restrict__ row_mask, KeyD* __restrict__ part) {
@@ -55,6 +67,12 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   KeyD* s_lists = reinterpret_cast<KeyD*>(acc + ix.tile_docs);   // [warps][KP]
   KeyD* s_out = s_lists + BM_WARPS * KP;                         // [KP]
   double* s_thr = reinterpret_cast<double*>(s_out + KP);         // [warps]
+  double* s_w = s_thr + BM_WARPS;                                // [MAXQ] idf of each staged token
+  long long* s_base = reinterpret_cast<long long*>(s_w + BM_MAXQ);   // [MAXQ] term_ptr
+  const uint32_t** s_skip = reinterpret_cast<const uint32_t**>(s_base + BM_MAXQ);  // [MAXQ] skip row
+  long long* s_lo = reinterpret_cast<long long*>(s_skip + BM_MAXQ);  // [2][MAXQ] slice bounds
+  long long* s_hi = s_lo + 2 * BM_MAXQ;
+  double* s_seed_buf = reinterpret_cast<double*>(s_hi + 2 * BM_MAXQ);  // [128] group maxima (seeding)
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -63,58 +81,192 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   const int qlo = q_ptr[b], qhi = q_ptr[b + 1];
   KeyD* w_list = s_lists + warp * KP;
   volatile double* w_thr = s_thr + warp;
+  const int first_tile = blockIdx.y;
 
-  for (int tile = blockIdx.y; tile < ix.n_tiles; tile += gridDim.y) {
+  // Query tokens are processed in chunks of BM_MAXQ (one chunk for any normal query).
+  // With more than one chunk the accumulators must persist across chunks, so the tile
+  // loop is the outer loop and chunks the inner one.
+  for (int tile = first_tile; tile < ix.n_tiles; tile += gridDim.y) {
     const long long tile_lo = (long long)tile * ix.tile_docs;
     const long long rem = ix.n_docs - tile_lo;
     const int n_here = rem < ix.tile_docs ? (int)rem : ix.tile_docs;
     for (int i = tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;
+
+    for (int c0 = qlo; c0 < qhi; c0 += BM_MAXQ) {
+      const int m = (qhi - c0) < BM_MAXQ ? (qhi - c0) : BM_MAXQ;
+      __syncthreads();  // previous users of the staging arrays are done; acc zeroed
+      if (tid < m) {
+        const int t = q_terms[c0 + tid];
+        long long lo = 0, hi = 0;
+        double w = 0.0;
+        if (t >= 0 && t < ix.n_terms) {  // unknown token: empty slice
+          const long long base = ix.term_ptr[t];
+          const uint32_t* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
+          lo = base + sk[0];
+          hi = base + sk[1];
+          w = ix.idf[t];
+        }
+        s_w[tid] = w;
+        s_lo[tid] = lo;
+        s_hi[tid] = hi;
+      }
+      __syncthreads();
+
+      // token passes, in query order; loads of pass j+1 are issued before pass j is applied
+      u32 pk[2][BM_U];      // packed postings / tile-local docs
+      double pv[2][BM_U];   // wide format: factors
+      auto issue = [&](int j, int buf) {
+        const long long lo = s_lo[j];
+        const int n = (int)(s_hi[j] - lo);  // <= tile_docs
+        const u32* pp = ix.post_pack + lo;
+        const int* pd = ix.post_doc + lo;
+        const double* pi = ix.post_imp + lo;
+#pragma unroll
+        for (int u = 0; u < BM_U; ++u) {
+          const int i = tid + u * BM_THREADS;
+          if (i < n) {
+            if (PACKED) {
+              pk[buf][u] = ldg_stream_u32(pp + i);
+            } else {
+              pk[buf][u] = (u32)(ldg_stream_i32(pd + i) - (int)tile_lo);
+              pv[buf][u] = ldg_stream_f64(pi + i);
+            }
+          }
+        }
+      };
+      auto apply = [&](int j, int buf) {
+        const long long lo = s_lo[j];
+        const int n = (int)(s_hi[j] - lo);
+        const double w = s_w[j];
+#pragma unroll
+        for (int u = 0; u < BM_U; ++u) {
+          const int i = tid + u * BM_THREADS;
+          if (i < n) {
+            const u32 loc = PACKED ? (pk[buf][u] & 0xFFFFu) : pk[buf][u];
+            const double imp = PACKED ? __ldg(ix.imp_table + (pk[buf][u] >> 16)) : pv[buf][u];
+            acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));  // no fma: rank_bm25 rounds the product
+          }
+        }
+        // long slices (tile_docs > BM_U * BM_THREADS): the rest, BM_U at a time
+        const u32* pp = ix.post_pack + lo;
+        const int* pd = ix.post_doc + lo;
+        const double* pi = ix.post_imp + lo;
+        for (int i0 = BM_U * BM_THREADS; i0 < n; i0 += BM_U * BM_THREADS) {
+          u32 k2[BM_U];
+          double v2[BM_U];
+#pragma unroll
+          for (int u = 0; u < BM_U; ++u) {
+            const int i = i0 + tid + u * BM_THREADS;
+            if (i < n) {
+              if (PACKED) {
+                k2[u] = ldg_stream_u32(pp + i);
+              } else {
+                k2[u] = (u32)(ldg_stream_i32(pd + i) - (int)tile_lo);
+                v2[u] = ldg_stream_f64(pi + i);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < BM_U; ++u) {
+            const int i = i0 + tid + u * BM_THREADS;
+            if (i < n) {
+              const u32 loc = PACKED ? (k2[u] & 0xFFFFu) : k2[u];
+              const double imp = PACKED ? __ldg(ix.imp_table + (k2[u] >> 16)) : v2[u];
+              acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));
+            }
+          }
+        }
+      };
+      if (m > 0) issue(0, 0);
+      for (int j = 0; j < m; ++j) {
+        if (j + 1 < m) {
+          if ((j & 1) == 0) issue(j + 1, 1);
+          else issue(j + 1, 0);
+        }
+        if ((j & 1) == 0) apply(j, 0);
+        else apply(j, 1);
+        __syncthreads();  // a document may appear in the next token's list too
+      }
+    }
     __syncthreads();
 
-    for (int j = qlo; j < qhi; ++j) {
-      const int t = q_terms[j];
-      if (t < 0 || t >= ix.n_terms) continue;  // unknown token contributes nothing (uniform)
-      const double w = ix.idf[t];
-      const long long base = ix.term_ptr[t];
-      const uint32_t* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
-      const long long lo = base + sk[0], hi = base + sk[1];
-      for (long long p = lo + tid; p < hi; p += BM_THREADS) {
-        const int d = ldg_stream_i32(ix.post_doc + p) - (int)tile_lo;
-        const double imp = ldg_stream_f64(ix.post_imp + p);
-        acc[d] = __dadd_rn(acc[d], __dmul_rn(w, imp));  // no fma: rank_bm25 rounds the product
+    // Threshold seeding (first tile of this CTA only).  Split the tile into 128
+    // groups of documents and take each group's best score: the KP-th largest of
+    // those 128 maxima is reached by at least KP documents, so nothing below it can
+    // be in this CTA's top KP.  Every warp starts from the largest double below
+    // that value (ties are admitted until its own list is full) instead of -inf,
+    // which removes almost all of the list-filling inserts.
+    if (tile == first_tile) {
+      double m = -INFINITY;
+      for (int i = tid; i < n_here; i += BM_THREADS) {
+        bool ok = true;
+        if (row_mask != nullptr) ok = row_mask[tile_lo + i] != 0;
+        if (ok) m = fmax(m, acc[i]);
+      }
+      m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+      m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+      if ((tid & 3) == 0) s_seed_buf[tid >> 2] = m;
+      __syncthreads();
+      if (tid < 128) {
+        const double mine = s_seed_buf[tid];
+        int cnt = 0;
+        for (int j = 0; j < 128; ++j) {
+          const double o = s_seed_buf[j];
+          cnt += (o > mine) || (o == mine && j < tid);
+        }
+        if (cnt == KP - 1 && mine > -INFINITY) {
+          // largest double strictly below `mine` (mine is finite)
+          const long long bits = __double_as_longlong(mine);
+          double below;
+          if (mine > 0.0) below = __longlong_as_double(bits - 1);
+          else if (mine < 0.0) below = __longlong_as_double(bits + 1);
+          else below = -4.9406564584124654e-324;  // -denorm_min (mine is +-0.0)
+          for (int w = 0; w < BM_WARPS; ++w) s_thr[w] = below;
+        }
       }
       __syncthreads();
     }
 
-    // per-warp selection over the tile's accumulators, ascending document order
-    const int per_warp = ix.tile_docs / BM_WARPS;
-    const int w_lo = warp * per_warp;
-    int w_hi = w_lo + per_warp;
-    if (w_hi > n_here) w_hi = n_here;
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-      const int i = i0 + lane;
-      double s = -INFINITY;
-      bool ok = i < w_hi;
-      if (ok) {
-        s = acc[i];
-        if (row_mask != nullptr) ok = row_mask[tile_lo + i] != 0;
-      }
-      // strict '>' is exact: documents arrive in ascending order, a tie with the
-      // list's last entry loses the id tie-break
-      unsigned bal = __ballot_sync(0xFFFFFFFFu, ok && (s > *w_thr));
-      while (bal) {
-        const int src = __ffs(bal) - 1;
-        bal &= bal - 1;
-        KeyD key;
-        key.s = __shfl_sync(0xFFFFFFFFu, s, src);
-        key.id = (u32)(tile_lo + i0 + src);
-        key.pad = 0;
-        if (key.s > *w_thr) {
-          KeyD new_last;
-          key_clear(new_last);
-          if (warp_list_insert<KP, KeyD>(w_list, key, lane, new_last) && !key_empty(new_last)) {
-            if (lane == 0) *w_thr = new_last.s;
-            __syncwarp();
+    // per-warp selection over the tile's accumulators.  A warp owns a slice and
+    // visits it 128 documents at a time: lane l looks at documents l, l+32, l+64,
+    // l+96 of the chunk, so hits are inserted in ascending document order and the
+    // strict '>' admission test is exact (a tie with the list's last entry always
+    // loses the id tie-break).  Fast path: 4 LDS.64 + 4 compares per 128 documents.
+    {
+      const int per_warp = ix.tile_docs / BM_WARPS;  // multiple of 32
+      const int w_lo = warp * per_warp;
+      const int w_hi = w_lo + per_warp;
+      for (int c = w_lo; c < w_hi; c += 128) {
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = c + e * 32 + lane;
+          v[e] = (i < w_hi) ? acc[i] : -INFINITY;
+        }
+        const double thr = *w_thr;
+        const bool any_hit = (v[0] > thr) | (v[1] > thr) | (v[2] > thr) | (v[3] > thr);
+        if (!__any_sync(0xFFFFFFFFu, any_hit)) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = c + e * 32 + lane;
+          bool ok = (i < w_hi) && (i < n_here) && (v[e] > *w_thr);
+          if (ok && row_mask != nullptr) ok = row_mask[tile_lo + i] != 0;
+          unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+          while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            KeyD key;
+            key.s = __shfl_sync(0xFFFFFFFFu, v[e], src);
+            key.id = (u32)(tile_lo + c + e * 32 + src);
+            key.pad = 0;
+            if (key.s > *w_thr) {
+              KeyD new_last;
+              key_clear(new_last);
+              if (warp_list_insert<KP, KeyD>(w_list, key, lane, new_last) && !key_empty(new_last)) {
+                if (lane == 0) *w_thr = new_last.s;
+                __syncwarp();
+              }
+            }
           }
         }
       }
@@ -163,6 +315,8 @@ bm25_finalize_kernel(const KeyD* __restrict__ part, int n_lists, long long row_o
 }
 
 struct Bm25Plan {
+  bool packed;
+  tile_fn_t fn;
   int kpl;
   int grid_y;  // tile groups (lists per query)
   size_t smem_tile, smem_fin;
@@ -171,26 +325,32 @@ struct Bm25Plan {
 static int check_index(const cmr_lex_index* ix) {
   CMR_CHECK_ARG(ix != nullptr, "null index");
   CMR_CHECK_ARG(ix->n_docs >= 0 && ix->n_docs < 0xFFFFFFFFll, "n_docs out of range");
-  CMR_CHECK_ARG(ix->tile_docs >= 512 && ix->tile_docs % 512 == 0, "tile_docs must be a positive multiple of 512");
+  CMR_CHECK_ARG(ix->tile_docs >= 512 && ix->tile_docs % 512 == 0 && ix->tile_docs <= 65536,
+                "tile_docs must be a multiple of 512 in [512, 65536]");
+  CMR_CHECK_ARG(ix->n_terms == 0 || (ix->post_pack && ix->imp_table) || (ix->post_doc && ix->post_imp) || ix->term_ptr,
+                "index needs packed or wide postings");
   CMR_CHECK_ARG(ix->n_tiles >= 1 && (long long)ix->n_tiles * ix->tile_docs >= ix->n_docs, "n_tiles inconsistent with n_docs/tile_docs");
   CMR_CHECK_ARG(ix->n_terms >= 0, "n_terms negative");
   CMR_CHECK_ARG(ix->n_terms == 0 || (ix->term_ptr && ix->tile_skip && ix->idf), "null index arrays");
   return CMR_OK;
 }
 
-typedef void (*tile_fn_t)(cmr_lex_index, const int*, const int*, const uint8_t*, KeyD*);
-
 static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p) {
   p->kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
   const int kp = 32 * p->kpl;
-  p->smem_tile = (size_t)ix.tile_docs * 8 + (size_t)BM_WARPS * kp * 16 + (size_t)kp * 16 + BM_WARPS * 8 + 16;
+  p->smem_tile = (size_t)ix.tile_docs * 8 + (size_t)BM_WARPS * kp * 16 + (size_t)kp * 16 + BM_WARPS * 8 +
+                 (size_t)BM_MAXQ * (8 + 8 + 8 + 4 * 8) + 128 * 8 + 16;
+  p->packed = ix.post_pack != nullptr && ix.imp_table != nullptr;
   if (p->smem_tile > 220 * 1024) {
     set_error("bm25 tile shared memory %zu too large: lower tile_docs", p->smem_tile);
     return CMR_EUNSUPPORTED;
   }
   const int sms = sm_count();
   if (sms <= 0) return CMR_ECUDA;
-  tile_fn_t fn = p->kpl == 1 ? bm25_tile_kernel<1> : (p->kpl == 2 ? bm25_tile_kernel<2> : bm25_tile_kernel<4>);
+  tile_fn_t fn;
+  if (p->packed) fn = p->kpl == 1 ? bm25_tile_kernel<1, true> : (p->kpl == 2 ? bm25_tile_kernel<2, true> : bm25_tile_kernel<4, true>);
+  else fn = p->kpl == 1 ? bm25_tile_kernel<1, false> : (p->kpl == 2 ? bm25_tile_kernel<2, false> : bm25_tile_kernel<4, false>);
+  p->fn = fn;
   struct Occ { tile_fn_t fn; size_t smem; int dev; int per_sm; };
   static Occ cache[32];
   static int n_cache = 0;
@@ -210,7 +370,7 @@ static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p)
     if (n_cache < 32) cache[n_cache++] = Occ{fn, p->smem_tile, dev, per_sm};
   }
   const long long resident = (long long)sms * per_sm;
-  long long gy = (resident + n_queries - 1) / n_queries;
+  long long gy = resident / n_queries;  // one wave: every CTA resident
   if (gy < 1) gy = 1;
   if (gy > ix.n_tiles) gy = ix.n_tiles;
   if (gy > 65535) gy = 65535;
@@ -238,7 +398,7 @@ static int launch_bm25(const cmr_lex_index& ix, const Bm25Plan& p, const int* q_
     attr_dev_mask |= (1 << dev);
   }
   dim3 grid(n_queries, p.grid_y);
-  bm25_tile_kernel<KPL><<<grid, BM_THREADS, p.smem_tile, st>>>(ix, q_terms, q_ptr, row_mask, part);
+  p.fn<<<grid, BM_THREADS, p.smem_tile, st>>>(ix, q_terms, q_ptr, row_mask, part);
   bm25_finalize_kernel<KPL><<<n_queries, BMF_THREADS, p.smem_fin, st>>>(part, p.grid_y, row_offset, k, out_scores,
                                                                        out_ids, out_counts, out_flags);
   return CMR_OK;

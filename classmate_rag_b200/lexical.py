@@ -26,10 +26,11 @@ DEFAULT_TILE_DOCS = 8192
 class LexIndexStruct(C.Structure):
     """Mirror of ``cmr_lex_index`` (include/cmrag.h)."""
     _fields_ = [
-        ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_doc", C.c_void_p),
-        ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p), ("idf", C.c_void_p),
+        ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_pack", C.c_void_p), ("imp_table", C.c_void_p),
+        ("post_doc", C.c_void_p), ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p),
+        ("idf", C.c_void_p),
         ("n_docs", C.c_int64), ("n_terms", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
-        ("reserved", C.c_int32), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
+        ("n_codes", C.c_int32), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
     ]
 
 
@@ -57,7 +58,7 @@ class LexicalIndex:
     term_ptr: torch.Tensor      # int64 [V+1]
     tile_skip: torch.Tensor     # int32 (uint32 bits) [V, n_tiles+1]
     post_doc: torch.Tensor      # int32 [P]
-    post_imp: torch.Tensor      # float64 [P]
+    post_imp: Optional[torch.Tensor]   # float64 [P] (wide format only)
     post_tf: torch.Tensor       # int16 (uint16 bits) [P]
     doc_len: torch.Tensor       # int32 [N]
     idf: torch.Tensor           # float64 [V]
@@ -68,6 +69,10 @@ class LexicalIndex:
     avgdl: float
     k1: float = BM25_K1
     b: float = BM25_B
+    post_pack: Optional[torch.Tensor] = None   # int32 (uint32 bits) [P]: code << 16 | tile-local doc
+    imp_table: Optional[torch.Tensor] = None   # float64 [n_codes]: factor of each distinct (tf, doc_len) pair
+    pair_tf: Optional[torch.Tensor] = None     # int32 [n_codes]
+    pair_dl: Optional[torch.Tensor] = None     # int32 [n_codes]
     idf_host: np.ndarray = field(default=None, repr=False)
     df_host: np.ndarray = field(default=None, repr=False)        # corpus-wide df
     shard_df_host: np.ndarray = field(default=None, repr=False)  # postings per term in THIS shard
@@ -83,16 +88,19 @@ class LexicalIndex:
 
     def struct(self) -> LexIndexStruct:
         if self._struct is None:
+            opt = lambda t: None if t is None else t.data_ptr()
             self._struct = LexIndexStruct(
-                self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), self.post_doc.data_ptr(),
-                self.post_imp.data_ptr(), self.post_tf.data_ptr(), self.doc_len.data_ptr(), self.idf.data_ptr(),
-                self.n_docs, self.n_terms, self.tile_docs, self.n_tiles, 0, self.avgdl, self.k1, self.b)
+                self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), opt(self.post_pack), opt(self.imp_table),
+                self.post_doc.data_ptr(), opt(self.post_imp), self.post_tf.data_ptr(), self.doc_len.data_ptr(),
+                self.idf.data_ptr(), self.n_docs, self.n_terms, self.tile_docs, self.n_tiles,
+                0 if self.imp_table is None else int(self.imp_table.numel()), self.avgdl, self.k1, self.b)
         return self._struct
 
     def posting_bytes(self, terms: Sequence[int]) -> int:
-        """Algorithmic bytes one query streams: 12 B (int32 doc + float64 impact)
-        per posting of every query token, multiplicity counted."""
-        return 12 * int(sum(int(self.shard_df_host[t]) for t in terms if 0 <= t < self.n_terms))
+        """Algorithmic bytes one query streams: 4 B per packed posting (12 B wide:
+        int32 doc + float64 factor) of every query token, multiplicity counted."""
+        per = 4 if self.post_pack is not None else 12
+        return per * int(sum(int(self.shard_df_host[t]) for t in terms if 0 <= t < self.n_terms))
 
 
 @dataclass
@@ -124,9 +132,18 @@ def corpus_stats(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int) -> G
     return GlobalStats(n_docs, total, df.cpu().numpy().astype(np.int64), order[:n_seen].cpu().numpy())
 
 
+def bm25_factor(tf: torch.Tensor, dl: torch.Tensor, avgdl: float, k1: float, b: float) -> torch.Tensor:
+    """float64 tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl)), operation for operation as
+    rank_bm25 evaluates it.  (avgdl goes in as a device tensor: torch turns a division
+    by a Python scalar into a multiplication by its reciprocal -- a different rounding.)"""
+    tf64, dl64 = tf.to(torch.float64), dl.to(torch.float64)
+    avgdl_t = torch.tensor(avgdl, dtype=torch.float64, device=tf.device)
+    return tf64 * (k1 + 1) / (tf64 + k1 * ((1 - b) + (b * dl64) / avgdl_t))
+
+
 def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int, *,
                         device=None, tile_docs: int = DEFAULT_TILE_DOCS,
-                        stats: Optional[GlobalStats] = None,
+                        stats: Optional[GlobalStats] = None, fmt: str = "auto",
                         k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS) -> LexicalIndex:
     """Build the CSR index of the documents ``tokens[doc_ptr[i]:doc_ptr[i+1]]``.
 
@@ -164,21 +181,40 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
               + torch.clamp(torch.arange(n_tiles + 1, device=device) * tile_docs, max=max(n_docs, 1))[None, :])
     skip = torch.searchsorted(uniq, bounds.reshape(-1)).reshape(n_terms, n_tiles + 1) - term_ptr[:-1, None]
     del bounds
-    dl = doc_len.to(torch.float64)
-    tf64 = counts.to(torch.float64)
-    if avgdl > 0:
-        # operation for operation as rank_bm25: q_freq*(k1+1) / (q_freq + k1*(1 - b + b*doc_len/avgdl))
-        # (avgdl as a device tensor: torch turns division by a Python scalar into a
-        # multiplication by its reciprocal, which is not the same rounding)
-        avgdl_t = torch.tensor(avgdl, dtype=torch.float64, device=device)
-        imp = tf64 * (k1 + 1) / (tf64 + k1 * ((1 - b) + (b * dl[doc]) / avgdl_t))
-    else:
-        imp = torch.zeros_like(tf64)
+    if tile_docs > 65536:
+        raise ValueError("tile_docs must be <= 65536")
+    if fmt not in ("auto", "packed", "wide"):
+        raise ValueError("fmt must be auto, packed or wide")
+    # distinct (tf, doc_len) pairs -> 16-bit codes into an exact float64 factor table
+    post_pack = imp_table = pair_tf = pair_dl = imp = None
+    dl_post = doc_len[doc] if total > 0 else doc_len[:0]
+    if fmt != "wide" and total > 0 and int(doc_len.max()) < (1 << 31) // 65536:
+        pair_key = counts.clamp(max=65535) * (int(doc_len.max()) + 1) + dl_post
+        pairs, code = torch.unique(pair_key, return_inverse=True)
+        if pairs.numel() <= 65536 and int(counts.max()) <= 65535:
+            pair_tf = (pairs // (int(doc_len.max()) + 1)).to(torch.int32)
+            pair_dl = (pairs % (int(doc_len.max()) + 1)).to(torch.int32)
+            imp_table = (bm25_factor(pair_tf, pair_dl, avgdl, k1, b) if avgdl > 0
+                         else torch.zeros(pairs.numel(), dtype=torch.float64, device=device))
+            local = doc - (doc // tile_docs) * tile_docs
+            pk = (code << 16) | local                      # < 2^32, held in int64 here
+            post_pack = torch.where(pk >= (1 << 31), pk - (1 << 32), pk).to(torch.int32).contiguous()
+            del pk, local
+        del pair_key, code
+    elif fmt != "wide" and total == 0:
+        post_pack = torch.zeros(1, dtype=torch.int32, device=device)
+        imp_table = torch.zeros(1, dtype=torch.float64, device=device)
+    if post_pack is None:
+        if fmt == "packed":
+            raise ValueError("corpus has more than 65536 distinct (tf, doc_len) pairs: packed postings impossible")
+        imp = (bm25_factor(counts, dl_post, avgdl, k1, b) if avgdl > 0
+               else torch.zeros(counts.numel(), dtype=torch.float64, device=device))
     tf32 = counts.clamp(max=65535).to(torch.int32)
     tf16 = torch.where(tf32 >= 32768, tf32 - 65536, tf32).to(torch.int16)
     return LexicalIndex(
         term_ptr=term_ptr.contiguous(), tile_skip=skip.to(torch.int32).contiguous(),
-        post_doc=doc.to(torch.int32).contiguous(), post_imp=imp.contiguous(),
+        post_doc=doc.to(torch.int32).contiguous(), post_imp=None if imp is None else imp.contiguous(),
+        post_pack=post_pack, imp_table=imp_table, pair_tf=pair_tf, pair_dl=pair_dl,
         post_tf=tf16.contiguous(), doc_len=doc_len.to(torch.int32).contiguous(),
         idf=torch.from_numpy(idf_host).to(device), n_docs=n_docs, n_terms=n_terms, tile_docs=tile_docs,
         n_tiles=n_tiles, avgdl=float(avgdl), k1=k1, b=b, idf_host=idf_host, df_host=stats.df,

@@ -89,23 +89,29 @@ int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t str
  * of a term sorted by document, plus a skip table that gives, per term, the
  * posting offset at which every tile of `tile_docs` documents starts.
  * Scores are accumulated in float64 in query-token order with rank_bm25's own
- * operation order, so they are bit-identical to the reference arithmetic and
+ * operation order (the per-posting factor is an exact float64, stored either per
+ * posting or once per distinct (tf, doc_len) pair), so they are bit-identical to the reference arithmetic and
  * no rescoring pass (and no certificate) is needed: out_flags is always 0.
  * All pointers are device memory.
  * ---------------------------------------------------------------------- */
 typedef struct cmr_lex_index {
   const int64_t* term_ptr;   /* [n_terms + 1] posting offsets                          */
   const uint32_t* tile_skip; /* [n_terms, n_tiles + 1] offsets relative to term_ptr[t]  */
-  const int32_t* post_doc;   /* [P] local document of each posting                      */
-  const double* post_imp;    /* [P] float64 tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl))          */
+  /* packed postings (preferred, 4 B each): (code << 16) | (doc - tile_lo); code indexes
+   * imp_table, the float64 BM25 factor of that posting's (tf, doc_len) pair.            */
+  const uint32_t* post_pack; /* [P] or NULL                                             */
+  const double* imp_table;   /* [n_codes] or NULL                                       */
+  /* wide postings (fallback when the corpus has > 65536 distinct (tf, doc_len) pairs)   */
+  const int32_t* post_doc;   /* [P] local document of each posting; may be NULL if packed */
+  const double* post_imp;    /* [P] float64 tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl)); may be NULL if packed */
   const uint16_t* post_tf;   /* [P] term frequency (saturated at 65535); may be NULL    */
   const int32_t* doc_len;    /* [n_docs] tokens per document; may be NULL               */
   const double* idf;         /* [n_terms] float64 idf with the epsilon floor            */
   int64_t n_docs;
   int32_t n_terms;
-  int32_t tile_docs;
+  int32_t tile_docs;         /* multiple of 512, <= 65536                               */
   int32_t n_tiles;
-  int32_t reserved;
+  int32_t n_codes;
   double avgdl;
   double k1;
   double b;

@@ -9,9 +9,10 @@ from tests.synth_small import zipf_corpus, zipf_queries
 pytestmark = pytest.mark.gpu
 
 
-def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0):
+def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0, fmt="auto"):
     from classmate_rag_b200 import lexical, ops
-    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs)
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs, fmt=fmt)
+    assert (ix.post_pack is None) == (fmt == "wide")
     qt, qp = lexical.pack_queries(queries)
     m = None if mask is None else torch.from_numpy(mask).cuda()
     sc, ids, cnt, fl = ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=m, row_offset=row_offset)
@@ -76,3 +77,13 @@ def test_bm25_mask_and_offset():
 def test_bm25_fewer_docs_than_k():
     docs, doc_ptr, tokens, v = zipf_corpus(seed=10, n_docs=5, vocab=10, mean_len=4, empty_every=0)
     _run(docs, doc_ptr, tokens, v, [[0, 1], [3]], 8, 512)
+
+
+def test_bm25_wide_format_and_long_queries():
+    """The fallback posting format and queries longer than one staging chunk (64 tokens)."""
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=11, n_docs=9000, vocab=200, mean_len=15)
+    rng = np.random.default_rng(4)
+    long_q = rng.integers(0, 200, 150).tolist()
+    queries = zipf_queries(3, 5, 200) + [long_q]
+    _run(docs, doc_ptr, tokens, v, queries, 10, 1024, fmt="wide")
+    _run(docs, doc_ptr, tokens, v, queries, 10, 1024, fmt="packed")

@@ -26,7 +26,11 @@ def test_index_statistics_match_bm25okapi():
     tf = (ix.post_tf.to(torch.int32) & 0xFFFF).numpy().astype(np.int64)
     dl = ix.doc_len.numpy()[ix.post_doc.numpy()]
     want_imp = tf * (1.5 + 1) / (tf + 1.5 * (1 - 0.75 + 0.75 * dl / bm.avgdl))
-    assert np.array_equal(ix.post_imp.numpy(), want_imp)
+    code = (ix.post_pack.numpy().view(np.uint32) >> 16).astype(np.int64)
+    assert np.array_equal(ix.imp_table.numpy()[code], want_imp)              # packed: table lookup
+    assert np.array_equal(ix.post_pack.numpy().view(np.uint32) & 0xFFFF, ix.post_doc.numpy() % 512)
+    wide = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512, fmt="wide")
+    assert wide.post_pack is None and np.array_equal(wide.post_imp.numpy(), want_imp)
     # skip table: tile slices partition each posting list by document range
     sk = ix.tile_skip.numpy()
     assert sk.shape == (v, ix.n_tiles + 1)
