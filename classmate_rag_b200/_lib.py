@@ -16,6 +16,7 @@ CMR_OK, CMR_EINVAL, CMR_ECUDA, CMR_EWORKSPACE, CMR_EUNSUPPORTED = 0, -1, -2, -3,
 CMR_FLAG_UNCERTIFIED = 1
 CMR_MAX_K = 120
 CMR_SLACK = 8
+CMR_DENSE_AUTO, CMR_DENSE_SCAN, CMR_DENSE_MMA = 0, 1, 2
 
 _lib = None
 
@@ -28,6 +29,8 @@ _SIGNATURES = {
     "cmr_dense_workspace_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int]),
     "cmr_dense_topk": (C.c_int, [_vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _i64, _f64,
                                  _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cmr_dense_topk_ex": (C.c_int, [_vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _i64, _f64,
+                                    _vp, _vp, _vp, _vp, _vp, _sz, _vp, C.c_int]),
     "cmr_f32_to_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "cmr_gather_rows": (C.c_int, [_vp, _i64, C.c_int, _i64, _vp, C.c_int, _vp, _vp]),
     "cmr_mmr_select": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _f64, _vp, _vp, _vp, _vp]),

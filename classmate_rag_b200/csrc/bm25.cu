@@ -360,7 +360,8 @@ static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p)
   for (int i = 0; i < n_cache; ++i)
     if (cache[i].fn == fn && cache[i].smem == p->smem_tile && cache[i].dev == dev) per_sm = cache[i].per_sm;
   if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_tile);
+    // largest size any plan can ask for (per-kernel attribute: never lower it for a later shape)
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(bm25_tile)");
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BM_THREADS, p->smem_tile);
     if (e != cudaSuccess || per_sm <= 0) {

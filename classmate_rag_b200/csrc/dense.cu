@@ -29,14 +29,13 @@
 //
 // Algorithmic bytes per scan pass: n_rows * dim * 2 (the matrix is read once,
 // for up to 32 queries).
-#include "topk.cuh"
+#include "dense_common.cuh"
 
 namespace cmr {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_U = 8;  // ring depth in 32-column units
-constexpr int FIN_THREADS = 1024;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
   asm volatile(
@@ -217,57 +216,12 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
   int* s_cnt = reinterpret_cast<int*>(s_score + KP);
 
   const int qi = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   block_select_from_lists<KP, CAP, u64>(part + (size_t)qi * n_lists * KP, n_lists, s_heads, s_buf, s_cnt,
                                    s_out, tid, FIN_THREADS);
 
-  // exact rescoring, one warp per candidate
-  const uint16_t* q = queries + (size_t)qi * dim;
-  for (int c = warp; c < KP; c += FIN_THREADS / 32) {
-    const u64 key = s_out[c];
-    if (key == 0ull) continue;  // warp-uniform
-    const uint16_t* row = emb + (size_t)key_row(key) * dim;
-    const double s = warp_exact_dot(q, row, dim, lane);
-    if (lane == 0) s_score[c] = s;
-  }
-  __syncthreads();
-
-  const int n_valid = count_valid(s_out, KP);  // keys sorted, empties last
-  const int n_out = n_valid < k ? n_valid : k;
-
-  // final order: (exact score desc, row asc) by counting rank
-  if (tid < n_valid) {
-    const double s = s_score[tid];
-    const u32 r = key_row(s_out[tid]);
-    int rank = 0;
-    for (int j = 0; j < n_valid; ++j) {
-      const double sj = s_score[j];
-      const u32 rj = key_row(s_out[j]);
-      rank += (sj > s) || (sj == s && rj < r);
-    }
-    if (rank < n_out) {
-      out_scores[(size_t)qi * k + rank] = s;
-      out_ids[(size_t)qi * k + rank] = (long long)r + row_offset;
-    }
-    if (rank == n_out - 1) {
-      // certificate: every row outside the candidate set has fp32 score <= the
-      // fp32 score of the last selected key, hence exact score <= that + eps.
-      int flag = 0;
-      if (n_valid == KP) {
-        const double last32 = (double)key_score(s_out[KP - 1]);
-        if (!(s > last32 + cert_eps)) flag = CMR_FLAG_UNCERTIFIED;
-      }
-      out_flags[qi] = flag;
-    }
-  }
-  for (int i = n_out + tid; i < k; i += FIN_THREADS) {
-    out_scores[(size_t)qi * k + i] = 0.0;
-    out_ids[(size_t)qi * k + i] = -1;
-  }
-  if (tid == 0) {
-    out_counts[qi] = n_out;
-    if (n_out == 0) out_flags[qi] = 0;
-  }
+  dense_finalize_tail<KP>(s_out, s_score, emb, dim, queries + (size_t)qi * dim, row_offset, k, cert_eps, 0, qi,
+                          out_scores, out_ids, out_counts, out_flags);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
@@ -339,7 +293,9 @@ static int make_plan(long long n_rows, int dim, int n_queries, int k, DensePlan*
   for (int i = 0; i < occ_n; ++i)
     if (occ_cache[i].fn == p->fn && occ_cache[i].smem == p->smem && occ_cache[i].dev == dev) per_sm = occ_cache[i].per_sm;
   if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    // opt in to the largest size any plan can ask for (the attribute is per kernel, not per
+    // launch: setting it to this plan's size would lower it for an earlier, larger shape)
+    cudaError_t e = cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_scan)");
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, SCAN_THREADS, p->smem);
     if (e != cudaSuccess || per_sm <= 0) {
@@ -391,21 +347,57 @@ static int launch_finalize(const DensePlan& p, const u64* part, const uint16_t* 
 
 using namespace cmr;
 
-extern "C" size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
+static size_t scan_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
   DensePlan p;
-  if (n_rows < 0 || dim <= 0 || dim % 8 != 0 || dim > 2048 || n_queries <= 0 || k <= 0 || k > CMR_MAX_K) {
-    set_error("cmr_dense_workspace_bytes: bad shape");
-    return 0;
-  }
   if (make_plan(n_rows, dim, n_queries, k, &p) != CMR_OK) return 0;
   return (size_t)n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
 }
 
-extern "C" int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim, const uint16_t* queries,
-                              int n_queries, int k, const uint8_t* row_mask, int64_t row_offset,
-                              double cert_eps, double* out_scores, int64_t* out_ids,
-                              int32_t* out_counts, int32_t* out_flags, void* workspace,
-                              size_t workspace_bytes, cmr_stream_t stream) {
+extern "C" size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
+  if (n_rows < 0 || dim <= 0 || dim % 8 != 0 || dim > 2048 || n_queries <= 0 || k <= 0 || k > CMR_MAX_K) {
+    set_error("cmr_dense_workspace_bytes: bad shape");
+    return 0;
+  }
+  // large enough for either path (the choice can depend on row_mask, known only at call time)
+  size_t need = scan_workspace_bytes(n_rows, dim, n_queries, k);
+  if (need == 0) return 0;
+  if (dense_mma_eligible(n_rows, dim, n_queries, k, false)) {
+    const size_t m = dense_mma_workspace_bytes(n_rows, dim, n_queries, k);
+    if (m > need) need = m;
+  }
+  return need;
+}
+
+static int dense_scan_topk(const DenseArgs& a) {
+  cudaStream_t st = a.stream;
+  DensePlan p;
+  int rc = make_plan(a.n_rows, a.dim, a.n_queries, a.k, &p);
+  if (rc != CMR_OK) return rc;
+  const size_t need = (size_t)a.n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
+  if (a.workspace_bytes < need || !a.workspace) {
+    set_error("workspace too small: %zu < %zu", a.workspace_bytes, need);
+    return CMR_EWORKSPACE;
+  }
+  u64* part = (u64*)a.workspace;
+  dim3 grid(p.grid_x, p.passes);
+  p.fn<<<grid, SCAN_THREADS, p.smem, st>>>(reinterpret_cast<const uint4*>(a.emb), a.n_rows, a.dim / 8,
+                                           p.steps_padded, reinterpret_cast<const uint4*>(a.queries),
+                                           a.n_queries, a.row_mask, part, p.rows_per_cta, p.q_stride_vec);
+  switch (p.kpl) {
+    case 1: rc = launch_finalize<1>(p, part, a.emb, a.dim, a.queries, a.n_queries, a.row_offset, a.k, a.cert_eps, a.out_scores, a.out_ids, a.out_counts, a.out_flags, st); break;
+    case 2: rc = launch_finalize<2>(p, part, a.emb, a.dim, a.queries, a.n_queries, a.row_offset, a.k, a.cert_eps, a.out_scores, a.out_ids, a.out_counts, a.out_flags, st); break;
+    default: rc = launch_finalize<4>(p, part, a.emb, a.dim, a.queries, a.n_queries, a.row_offset, a.k, a.cert_eps, a.out_scores, a.out_ids, a.out_counts, a.out_flags, st); break;
+  }
+  if (rc != CMR_OK) return rc;
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim, const uint16_t* queries,
+                                 int n_queries, int k, const uint8_t* row_mask, int64_t row_offset,
+                                 double cert_eps, double* out_scores, int64_t* out_ids,
+                                 int32_t* out_counts, int32_t* out_flags, void* workspace,
+                                 size_t workspace_bytes, cmr_stream_t stream, int algo) {
   CMR_CHECK_ARG(n_rows >= 0 && n_rows < 0xFFFFFFFFll, "n_rows %lld out of range", (long long)n_rows);
   CMR_CHECK_ARG(dim > 0 && dim % 8 == 0 && dim <= 2048, "dim %d must be a multiple of 8, <= 2048", dim);
   CMR_CHECK_ARG(n_queries > 0 && n_queries <= 65535 * 8, "n_queries %d out of range", n_queries);
@@ -413,29 +405,30 @@ extern "C" int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim, cons
   CMR_CHECK_ARG(queries && out_scores && out_ids && out_counts && out_flags, "null output/query pointer");
   CMR_CHECK_ARG(n_rows == 0 || emb, "null embedding matrix");
   CMR_CHECK_ARG(((uintptr_t)emb % 16) == 0 && ((uintptr_t)queries % 16) == 0, "emb/queries must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  DensePlan p;
-  int rc = make_plan(n_rows, dim, n_queries, k, &p);
-  if (rc != CMR_OK) return rc;
-  const size_t need = (size_t)n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
-  if (workspace_bytes < need || !workspace) {
-    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
-    return CMR_EWORKSPACE;
+  CMR_CHECK_ARG(algo == CMR_DENSE_AUTO || algo == CMR_DENSE_SCAN || algo == CMR_DENSE_MMA, "unknown algo %d", algo);
+  DenseArgs a{emb, (long long)n_rows, dim, queries, n_queries, k, row_mask, (long long)row_offset, cert_eps,
+              out_scores, (long long*)out_ids, out_counts, out_flags, workspace, workspace_bytes,
+              (cudaStream_t)stream};
+  const bool can_mma = dense_mma_eligible(n_rows, dim, n_queries, k, row_mask != nullptr);
+  if (algo == CMR_DENSE_MMA && !can_mma) {
+    set_error("tcgen05 path does not cover this shape (n_rows=%lld dim=%d B=%d k=%d mask=%d)",
+              (long long)n_rows, dim, n_queries, k, row_mask != nullptr);
+    return CMR_EUNSUPPORTED;
   }
-  u64* part = (u64*)workspace;
-  dim3 grid(p.grid_x, p.passes);
-  p.fn<<<grid, SCAN_THREADS, p.smem, st>>>(reinterpret_cast<const uint4*>(emb), n_rows, dim / 8,
-                                           p.steps_padded, reinterpret_cast<const uint4*>(queries),
-                                           n_queries, row_mask, part, p.rows_per_cta, p.q_stride_vec);
-  long long* ids = (long long*)out_ids;
-  switch (p.kpl) {
-    case 1: rc = launch_finalize<1>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
-    case 2: rc = launch_finalize<2>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
-    default: rc = launch_finalize<4>(p, part, emb, dim, queries, n_queries, row_offset, k, cert_eps, out_scores, ids, out_counts, out_flags, st); break;
-  }
-  if (rc != CMR_OK) return rc;
-  CMR_CUDA(cudaGetLastError());
-  return CMR_OK;
+  // auto: a single scan pass serves up to 8 queries at the HBM rate; above that the
+  // tensor-core GEMM reads the matrix once for up to 128 queries.
+  const bool use_mma = algo == CMR_DENSE_MMA || (algo == CMR_DENSE_AUTO && can_mma && n_queries > 8);
+  return use_mma ? dense_mma_topk(a) : dense_scan_topk(a);
+}
+
+extern "C" int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim, const uint16_t* queries,
+                              int n_queries, int k, const uint8_t* row_mask, int64_t row_offset,
+                              double cert_eps, double* out_scores, int64_t* out_ids,
+                              int32_t* out_counts, int32_t* out_flags, void* workspace,
+                              size_t workspace_bytes, cmr_stream_t stream) {
+  return cmr_dense_topk_ex(emb, n_rows, dim, queries, n_queries, k, row_mask, row_offset, cert_eps,
+                           out_scores, out_ids, out_counts, out_flags, workspace, workspace_bytes, stream,
+                           CMR_DENSE_AUTO);
 }
 
 extern "C" int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t stream) {

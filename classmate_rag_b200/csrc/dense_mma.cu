@@ -1,0 +1,517 @@
+// dense_mma.cu -- A1 batched: exact dense top-k as a tcgen05/TMA GEMM with a top-k epilogue.
+//
+// Replaces the hnswlib search behind ChromaVectorStore.query (reference
+// rag/retrieval/vector_chroma.py:204-253) for batches of queries.  scores = Q . C^T is
+// computed on the 5th-generation tensor cores and never written to memory:
+//
+//   warp 0   TMA producer: per 64-column K chunk one box of queries ([<=128, 64] bf16) and one
+//            box of rows ([256, 64] bf16) land in a 4-stage ring of 128-byte-swizzled shared
+//            memory tiles (cp.async.bulk.tensor + mbarrier complete_tx).
+//   warp 1   one thread issues tcgen05.mma.cta_group::1.kind::f16, M = 128 (queries),
+//            N = 256 (rows), K = 16, both operands K-major from shared memory, fp32
+//            accumulators in TMEM (two buffers of 256 columns, so the tensor pipe works on
+//            tile i+1 while tile i is read back); tcgen05.commit frees ring slots and
+//            publishes accumulators.
+//   warps 2-5 epilogue: tcgen05.ld.32x32b gives every thread ONE query (TMEM lane) and 32
+//            rows per load.  A thread reduces the 32 scores with max and compares once with
+//            its query's admission bound; only the rare survivors are appended to the
+//            query's candidate buffer (one global atomic each).
+//
+// The admission bound makes the single pass exact without keeping sorted lists on chip:
+// the same kernel first runs in SAMPLE mode over every 16th row tile and writes the maximum
+// score of each sampled group of rows; the KP-th largest of those maxima is attained by at
+// least KP different rows, hence it is a lower bound of the KP-th best score of the query,
+// and every row of the true top-KP passes `score >= bound` in MAIN mode.  About 16*KP rows
+// per query pass; dense_finalize_cand_kernel picks the KP best fp32 keys and hands them to
+// the shared exact float64 rescoring tail (dense_common.cuh), so ids, order and scores are
+// bit-identical to the scan path and to the oracle.
+//
+// Work distribution: persistent CTAs (one per SM), CTA c owns row tiles c, c+grid, ...; for
+// more than 128 queries the query blocks are the inner loop, so a row tile is fetched from
+// HBM once and re-read from L2.  Algorithmic bytes per launch: n_rows * dim * 2 (+1/16 for
+// the sample pass); flops 2 * n_queries * n_rows * dim.
+#include <cuda.h>
+
+#include "dense_common.cuh"
+
+namespace cmr {
+
+constexpr int MM_Q = 128;     // queries per MMA tile (UMMA M, TMEM lanes)
+constexpr int MM_R = 256;     // rows per MMA tile (UMMA N, TMEM columns)
+constexpr int MM_K = 64;      // bf16 per K chunk: one 128-byte swizzle span
+constexpr int MM_STAGES = 4;
+constexpr int MM_A_BYTES = MM_Q * MM_K * 2;  // 16 KiB
+constexpr int MM_B_BYTES = MM_R * MM_K * 2;  // 32 KiB
+constexpr int MM_STAGE_BYTES = MM_A_BYTES + MM_B_BYTES;
+constexpr int MM_THREADS = 192;
+constexpr int MM_SMEM_BYTES = MM_STAGES * MM_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int MM_SAMPLE = 0, MM_MAIN = 1;
+constexpr int MM_CAP_PER_KP = 64;    // candidate slots per query = 64 * KP
+constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile
+constexpr int MM_MAX_GROUPS = 49152; // threshold kernel keeps the group maxima in shared memory
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
+constexpr u32 MM_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(MM_R >> 3) << 17) | ((u32)(MM_Q >> 4) << 24);
+
+constexpr unsigned long long TMA_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr unsigned long long TMA_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr unsigned long long TMA_EVICT_LAST = 0x14F0000000000000ull;
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap* map, u32 bar, int c0, int c1,
+                                            unsigned long long hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(u32 d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                            u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor of a K-major tile with 128-byte swizzle: rows of 64 bf16
+// (128 B), groups of 8 rows 1024 B apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ unsigned long long umma_desc_sw128(u32 smem_addr) {
+  const u32 lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);              // start address, LBO = 1 (unused)
+  const u32 hi = (1024u >> 4) | (1u << 14) | (2u << 29);                  // SBO, version, SWIZZLE_128B
+  return ((unsigned long long)hi << 32) | lo;
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread, complete on return
+__device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
+  u32 r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// MODE == MM_SAMPLE: work item w is row tile w * tile_stride (always a full tile); the
+//   epilogue writes group maxima: gmax[(w * gpt + g) * gstride + query], gpt = 8 (groups of
+//   32 rows) or 1 (the whole tile).
+// MODE == MM_MAIN:   work item w is row tile w; scores >= thr[query] are appended to
+//   cand[query * cap + atomicAdd(cnt[query])] as (orderable fp32 score, ~row) keys.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_rows,
+                 int n_queries, long long n_rows, int n_chunks, int n_mb, int n_work, int tile_stride,
+                 u32 tx_bytes, int rows_evict_first, const float* __restrict__ thr,
+                 float* __restrict__ gmax, int gstride, int gpt, u64* __restrict__ cand,
+                 int* __restrict__ cnt, int cap) {
+  extern __shared__ unsigned char smem_raw[];
+  const u32 raw = smem_u32(smem_raw);
+  const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const u32 bars = base + MM_STAGES * MM_STAGE_BYTES;
+  // barrier slots: full[s] at +8s, empty[s] at +32+8s, tmem_full[b] at +64+8b, tmem_empty[b] at +80+8b
+  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(smem_raw + (bars - raw) + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+    for (int s = 0; s < MM_STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 32 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + 64 + 8 * b, 1);
+      mbar_init(bars + 80 + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the allocating warp also frees
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 96), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const unsigned long long hint_rows = rows_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+      u32 it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int row0 = w * tile_stride * MM_R;
+        for (int mb = 0; mb < n_mb; ++mb) {
+          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+            mbar_wait(bars + 32 + 8 * s, ph ^ 1u);
+            const u32 full = bars + 8 * s;
+            mbar_expect_tx(full, tx_bytes);
+            const u32 sa = base + s * MM_STAGE_BYTES;
+            tma_load_2d(sa, &tm_q, full, kc * MM_K, mb * MM_Q, TMA_EVICT_LAST);
+            tma_load_2d(sa + MM_A_BYTES, &tm_rows, full, kc * MM_K, row0, hint_rows);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      u32 it = 0, ai = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        for (int mb = 0; mb < n_mb; ++mb, ++ai) {
+          const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
+          mbar_wait(bars + 80 + 8 * ab, aph ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const u32 d_tmem = tmem_base + ab * MM_R;
+          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+            mbar_wait(bars + 8 * s, ph);  // TMA bytes have landed
+            tc_fence_after();
+            const u32 sa = base + s * MM_STAGE_BYTES;
+            const unsigned long long da = umma_desc_sw128(sa);
+            const unsigned long long db = umma_desc_sw128(sa + MM_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < MM_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
+              tc_mma_bf16(d_tmem, da + 2ull * k, db + 2ull * k, MM_IDESC, (kc | k) != 0);
+            tc_commit(bars + 32 + 8 * s);  // frees the ring slot when these MMAs retire
+          }
+          tc_commit(bars + 64 + 8 * ab);   // accumulator complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 =====
+    const int lg = warp & 3;
+    const int lane_row = lg * 32 + lane;
+    u32 ai = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const long long row0 = (long long)w * tile_stride * MM_R;
+      for (int mb = 0; mb < n_mb; ++mb, ++ai) {
+        const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
+        const int qi = mb * MM_Q + lane_row;
+        const bool q_ok = qi < n_queries;
+        float bound = INFINITY;
+        if (MODE == MM_MAIN && q_ok) bound = thr[qi];
+        mbar_wait(bars + 64 + 8 * ab, aph);
+        tc_fence_after();
+        const u32 taddr = tmem_base + ((u32)(lg * 32) << 16) + ab * MM_R;
+        float tile_max = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < MM_R / 32; ++c) {
+          __syncwarp();
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          float m = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+          if (MODE == MM_SAMPLE) {
+            if (gpt == 8) {
+              if (q_ok) gmax[((size_t)w * 8 + c) * gstride + qi] = m;
+            } else {
+              tile_max = fmaxf(tile_max, m);
+            }
+          } else if (q_ok && m >= bound) {
+            // rare: about 16*KP rows per query over the whole scan
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] >= bound) {
+                const long long row = row0 + c * 32 + j;
+                if (row < n_rows) {
+                  const int slot = atomicAdd(&cnt[qi], 1);
+                  if (slot < cap) cand[(size_t)qi * cap + slot] = make_key(v[j], (u32)row);
+                }
+              }
+            }
+          }
+        }
+        if (MODE == MM_SAMPLE && gpt != 8 && q_ok) gmax[(size_t)w * gstride + qi] = tile_max;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 80 + 8 * ab);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// One CTA per query: bound = the kp-th largest of the G sampled group maxima (bit-wise
+// bisection on the orderable integer image of the floats), -inf when there are fewer than
+// kp groups.  Also clears the query's candidate counter for the MAIN pass.
+__global__ void __launch_bounds__(256)
+dense_thresh_kernel(const float* __restrict__ gmax, int n_groups, int gstride, int kp,
+                    float* __restrict__ thr, int* __restrict__ cnt) {
+  extern __shared__ u32 s_vals[];
+  __shared__ int s_count;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) cnt[q] = 0;
+  if (n_groups < kp) {
+    if (tid == 0) thr[q] = -INFINITY;
+    return;
+  }
+  for (int g = tid; g < n_groups; g += 256) s_vals[g] = f32_orderable(gmax[(size_t)g * gstride + q]);
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  u32 prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const u32 c = prefix | (1u << bit);
+    int local = 0;
+    for (int g = tid; g < n_groups; g += 256) local += s_vals[g] >= c;
+    local = __reduce_add_sync(0xFFFFFFFFu, local);
+    if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
+    __syncthreads();
+    if (s_count >= kp) prefix = c;
+    __syncthreads();
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+  }
+  if (tid == 0) thr[q] = orderable_f32(prefix);
+}
+
+// One CTA per query: the KP best of the query's candidates (unique keys, ranked by counting),
+// then the shared exact rescoring tail.  More candidates than slots -> CMR_FLAG_UNCERTIFIED.
+template <int KPL>
+__global__ void __launch_bounds__(FIN_THREADS)
+dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__ cnt, int cap,
+                           const uint16_t* __restrict__ emb, int dim, const uint16_t* __restrict__ queries,
+                           long long row_offset, int k, double cert_eps, double* __restrict__ out_scores,
+                           long long* __restrict__ out_ids, int* __restrict__ out_counts,
+                           int* __restrict__ out_flags) {
+  constexpr int KP = 32 * KPL;
+  extern __shared__ __align__(16) unsigned char smem_fin[];
+  u64* s_keys = reinterpret_cast<u64*>(smem_fin);  // [cap]
+  u64* s_out = s_keys + cap;                       // [KP]
+  double* s_score = reinterpret_cast<double*>(s_out + KP);
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const int total = cnt[qi];
+  const int m = total < cap ? total : cap;
+  for (int i = tid; i < m; i += FIN_THREADS) s_keys[i] = cand[(size_t)qi * cap + i];
+  for (int i = tid; i < KP; i += FIN_THREADS) s_out[i] = 0ull;
+  __syncthreads();
+  for (int e = tid; e < m; e += FIN_THREADS) {
+    const u64 key = s_keys[e];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += s_keys[j] > key;
+    if (rank < KP) s_out[rank] = key;
+  }
+  __syncthreads();
+  dense_finalize_tail<KP>(s_out, s_score, emb, dim, queries + (size_t)qi * dim, row_offset, k, cert_eps,
+                          total > cap ? CMR_FLAG_UNCERTIFIED : 0, qi, out_scores, out_ids, out_counts, out_flags);
+}
+
+// ---- host side ------------------------------------------------------------------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+// [n_rows, dim] bf16 row-major matrix, boxes of [box_rows, 64] columns, 128-byte swizzle,
+// out-of-bounds elements read as zero
+static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int dim, int box_rows) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return CMR_ECUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)dim * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)MM_K, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%lld, %d] box %d", (int)r, n_rows, dim, box_rows);
+    return CMR_ECUDA;
+  }
+  return CMR_OK;
+}
+
+struct MmaPlan {
+  int kpl, kp, cap;
+  int n_mb, n_chunks, q_box_rows, bpad;
+  int n_tiles, n_sample, sample_stride, gpt, n_groups;
+  size_t off_cnt, off_thr, off_gmax, total;
+};
+
+static void mma_plan(long long n_rows, int dim, int n_queries, int k, MmaPlan* p) {
+  const int need = k + CMR_SLACK;
+  p->kpl = need <= 32 ? 1 : (need <= 64 ? 2 : 4);
+  p->kp = 32 * p->kpl;
+  p->cap = MM_CAP_PER_KP * p->kp;
+  p->n_mb = (n_queries + MM_Q - 1) / MM_Q;
+  p->n_chunks = (dim + MM_K - 1) / MM_K;
+  p->q_box_rows = n_queries >= MM_Q ? MM_Q : (n_queries + 7) / 8 * 8;
+  p->bpad = (n_queries + 31) / 32 * 32;
+  p->n_tiles = (int)((n_rows + MM_R - 1) / MM_R);
+  const int full_tiles = (int)(n_rows / MM_R);
+  int stride = full_tiles / MM_SAMPLE_STRIDE;  // small matrices: sample (nearly) every tile
+  if (stride < 1) stride = 1;
+  if (stride > MM_SAMPLE_STRIDE) stride = MM_SAMPLE_STRIDE;
+  for (;;) {
+    p->sample_stride = stride;
+    p->n_sample = full_tiles > 0 ? (full_tiles + stride - 1) / stride : 0;
+    p->gpt = p->n_sample < 8 * p->kp ? 8 : 1;
+    p->n_groups = p->n_sample * p->gpt;
+    if (p->n_groups <= MM_MAX_GROUPS) break;
+    stride *= 2;
+  }
+  size_t off = (size_t)n_queries * p->cap * sizeof(u64);
+  p->off_cnt = off;
+  off += ((size_t)p->bpad * 4 + 15) / 16 * 16;
+  p->off_thr = off;
+  off += ((size_t)p->bpad * 4 + 15) / 16 * 16;
+  p->off_gmax = off;
+  off += (size_t)(p->n_groups > 0 ? p->n_groups : 1) * p->bpad * 4;
+  p->total = off;
+}
+
+bool dense_mma_eligible(long long n_rows, int dim, int n_queries, int k, bool has_mask) {
+  return !has_mask && dim >= MM_K && n_rows >= MM_R && n_rows < 0x7FFFFF00ll && n_queries >= 1 && k >= 1 &&
+         k <= CMR_MAX_K;
+}
+
+size_t dense_mma_workspace_bytes(long long n_rows, int dim, int n_queries, int k) {
+  MmaPlan p;
+  mma_plan(n_rows, dim, n_queries, k, &p);
+  return p.total;
+}
+
+template <int KPL>
+static int launch_finalize_cand(const DenseArgs& a, const MmaPlan& p, const u64* cand, const int* cnt) {
+  const size_t smem = (size_t)p.cap * 8 + (size_t)p.kp * 16 + 16;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(dense_finalize_cand_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MM_CAP_PER_KP * 32 * KPL * 8 + 32 * KPL * 16 + 16);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_finalize_cand)");
+    attr_dev_mask |= (1 << dev);
+  }
+  dense_finalize_cand_kernel<KPL><<<a.n_queries, FIN_THREADS, smem, a.stream>>>(
+      cand, cnt, p.cap, a.emb, a.dim, a.queries, a.row_offset, a.k, a.cert_eps, a.out_scores, a.out_ids,
+      a.out_counts, a.out_flags);
+  return CMR_OK;
+}
+
+int dense_mma_topk(const DenseArgs& a) {
+  MmaPlan p;
+  mma_plan(a.n_rows, a.dim, a.n_queries, a.k, &p);
+  if (!a.workspace || a.workspace_bytes < p.total) {
+    set_error("workspace too small: %zu < %zu", a.workspace_bytes, p.total);
+    return CMR_EWORKSPACE;
+  }
+  CMR_CHECK_ARG(((uintptr_t)a.workspace % 16) == 0, "workspace must be 16-byte aligned");
+  const int sms = sm_count();
+  if (sms <= 0) return CMR_ECUDA;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel<MM_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_mma_kernel<MM_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_thresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_MAX_GROUPS * 4);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_mma)");
+    attr_dev_mask |= (1 << dev);
+  }
+  alignas(64) CUtensorMap tm_q, tm_rows;
+  int rc = make_tmap(&tm_q, a.queries, a.n_queries, a.dim, p.q_box_rows);
+  if (rc != CMR_OK) return rc;
+  rc = make_tmap(&tm_rows, a.emb, a.n_rows, a.dim, MM_R);
+  if (rc != CMR_OK) return rc;
+
+  unsigned char* ws = (unsigned char*)a.workspace;
+  u64* cand = (u64*)ws;
+  int* cnt = (int*)(ws + p.off_cnt);
+  float* thr = (float*)(ws + p.off_thr);
+  float* gmax = (float*)(ws + p.off_gmax);
+  const u32 tx_bytes = (u32)(p.q_box_rows * MM_K * 2 + MM_B_BYTES);
+
+  if (p.n_sample > 0) {
+    const int grid = p.n_sample < sms ? p.n_sample : sms;
+    dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(
+        tm_q, tm_rows, a.n_queries, a.n_rows, p.n_chunks, p.n_mb, p.n_sample, p.sample_stride, tx_bytes,
+        /*rows_evict_first=*/0, thr, gmax, p.bpad, p.gpt, cand, cnt, p.cap);
+  }
+  dense_thresh_kernel<<<a.n_queries, 256, (size_t)(p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
+      gmax, p.n_groups, p.bpad, p.kp, thr, cnt);
+  {
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    dense_mma_kernel<MM_MAIN><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(
+        tm_q, tm_rows, a.n_queries, a.n_rows, p.n_chunks, p.n_mb, p.n_tiles, 1, tx_bytes,
+        /*rows_evict_first=*/p.n_mb == 1, thr, gmax, p.bpad, p.gpt, cand, cnt, p.cap);
+  }
+  switch (p.kpl) {
+    case 1: rc = launch_finalize_cand<1>(a, p, cand, cnt); break;
+    case 2: rc = launch_finalize_cand<2>(a, p, cand, cnt); break;
+    default: rc = launch_finalize_cand<4>(a, p, cand, cnt); break;
+  }
+  if (rc != CMR_OK) return rc;
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+}  // namespace cmr

@@ -32,6 +32,9 @@ def device_info() -> Tuple[int, int, int]:
     return a.value, b.value, c.value
 
 
+_DENSE_ALGO = {"auto": _lib.CMR_DENSE_AUTO, "scan": _lib.CMR_DENSE_SCAN, "mma": _lib.CMR_DENSE_MMA}
+
+
 def f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 bits (round to nearest even) with the library's kernel."""
     _require_cuda(src, "src")
@@ -63,8 +66,11 @@ class DenseWorkspace:
 
 def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Optional[torch.Tensor] = None,
                row_offset: int = 0, cert_eps: Optional[float] = None,
-               workspace: Optional[DenseWorkspace] = None):
+               workspace: Optional[DenseWorkspace] = None, algo: str = "auto"):
     """Exact top-k of queries (bf16 [B, D]) against emb (bf16 [N, D]).
+
+    algo: "auto" | "scan" (HBM-streaming mma.sync scan) | "mma" (tcgen05/TMA GEMM
+    with the top-k epilogue); see cmr_dense_topk_ex in include/cmrag.h.
 
     Returns (scores f64 [B,k], ids i64 [B,k], counts i32 [B], flags i32 [B]) on
     the device, enqueued on the current stream (no synchronisation)."""
@@ -88,11 +94,11 @@ def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Op
         workspace = DenseWorkspace(n_rows, dim, b, k, emb.device)
     lib = _lib.load()
     with torch.cuda.device(emb.device):
-        rc = lib.cmr_dense_topk(emb.data_ptr(), n_rows, dim, queries.data_ptr(), b, k, _ptr(row_mask),
-                                row_offset, float(cert_eps), workspace.scores.data_ptr(),
-                                workspace.ids.data_ptr(), workspace.counts.data_ptr(),
-                                workspace.flags.data_ptr(), workspace.ws.data_ptr(), workspace.ws.numel(),
-                                _stream())
+        rc = lib.cmr_dense_topk_ex(emb.data_ptr(), n_rows, dim, queries.data_ptr(), b, k, _ptr(row_mask),
+                                   row_offset, float(cert_eps), workspace.scores.data_ptr(),
+                                   workspace.ids.data_ptr(), workspace.counts.data_ptr(),
+                                   workspace.flags.data_ptr(), workspace.ws.data_ptr(), workspace.ws.numel(),
+                                   _stream(), _DENSE_ALGO[algo])
     _lib.check(rc)
     return workspace.scores, workspace.ids, workspace.counts, workspace.flags
 

@@ -76,6 +76,32 @@ int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
                    double* out_scores, int64_t* out_ids, int32_t* out_counts, int32_t* out_flags,
                    void* workspace, size_t workspace_bytes, cmr_stream_t stream);
 
+/* Same call with an explicit choice of kernel (tests, benchmarks).
+ *   CMR_DENSE_SCAN  HBM-streaming scan: coalesced 16-byte loads feed mma.sync tiles, up to
+ *                   32 queries per pass over the matrix; warp-private top-k lists.  The
+ *                   single-query (GEMV-shaped) path; the only one that takes a row_mask.
+ *   CMR_DENSE_MMA   batched q.C^T on the tcgen05 tensor cores: TMA stages 128-byte-swizzled
+ *                   tiles of queries and rows in shared memory, one thread issues
+ *                   tcgen05.mma (M = 128 queries, N = 256 rows, K = 16) into double-buffered
+ *                   TMEM accumulators, four epilogue warps read them back with tcgen05.ld
+ *                   (one query per thread) and keep only scores that reach the query's
+ *                   admission bound; scores never go to HBM.  The matrix is read once per
+ *                   128 queries.  The bound comes from a first pass of the same kernel over
+ *                   1/16 of the row tiles (k-th largest of the tile maxima: a valid lower
+ *                   bound of the k-th best score), so both passes are exact.
+ *                   CMR_EUNSUPPORTED when the shape is outside that path (row_mask given,
+ *                   dim < 64, fewer than 256 rows).
+ *   CMR_DENSE_AUTO  SCAN for <= 8 queries or masked calls, MMA above.
+ * Results are bit-identical between the two (ids, order and float64 scores). */
+#define CMR_DENSE_AUTO 0
+#define CMR_DENSE_SCAN 1
+#define CMR_DENSE_MMA 2
+int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim,
+                      const uint16_t* queries, int n_queries, int k,
+                      const uint8_t* row_mask, int64_t row_offset, double cert_eps,
+                      double* out_scores, int64_t* out_ids, int32_t* out_counts, int32_t* out_flags,
+                      void* workspace, size_t workspace_bytes, cmr_stream_t stream, int algo);
+
 /* fp32 -> bf16 (round to nearest even) on device; used for queries and upserts
  * (E5 hands the store fp32, rag/embeddings/__init__.py:85-105). */
 int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t stream);

@@ -115,3 +115,111 @@ def test_f32_to_bf16_kernel_is_rne():
     x = torch.randn(100003, device="cuda")
     got = ops.f32_to_bf16(x)
     assert torch.equal(got.view(torch.int16), x.to(torch.bfloat16).view(torch.int16))
+
+
+# ---- batched path: tcgen05/TMA GEMM with the top-k epilogue (cmr_dense_topk_ex, CMR_DENSE_MMA) ----
+
+def _check_mma(bits, qbits, k, row_offset=0, also_scan=True):
+    from classmate_rag_b200 import ops
+    emb, q = _to_dev(bits), _to_dev(qbits)
+    s, i, c, f = [t.clone() for t in ops.dense_topk(emb, q, k, row_offset=row_offset, algo="mma")]
+    torch.cuda.synchronize()
+    scores, ids, counts, flags = s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy(), f.cpu().numpy()
+    for b in range(qbits.shape[0]):
+        want_ids, want_sc = o.dense_topk(qbits[b], bits, k, row_offset=row_offset)
+        n = len(want_ids)
+        assert counts[b] == n, (b, counts[b], n)
+        assert ids[b, :n].tolist() == want_ids.tolist(), b
+        assert scores[b, :n].tobytes() == want_sc.tobytes(), b
+        assert (ids[b, n:] == -1).all()
+        assert flags[b] == 0
+    if also_scan:  # the two kernels must agree bit for bit
+        s2, i2, c2, f2 = ops.dense_topk(emb, q, k, row_offset=row_offset, algo="scan")
+        torch.cuda.synchronize()
+        assert torch.equal(i, i2) and torch.equal(c, c2)
+        assert s.cpu().numpy().tobytes() == s2.cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize("n,d,k,b", [(20000, 768, 10, 32), (5000, 1024, 24, 7), (3000, 384, 10, 128),
+                                      (4096, 64, 10, 33), (2600, 136, 3, 16), (1500, 2048, 10, 3),
+                                      (1111, 1536, 5, 40), (256, 64, 10, 1), (300, 72, 40, 9)])
+def test_dense_mma_matches_oracle(n, d, k, b):
+    rng = np.random.default_rng(n + d + b)
+    bits = _corpus(rng, n, d, dup_every=100)
+    _check_mma(bits, _queries(rng, bits, b), k)
+
+
+@pytest.mark.parametrize("k", [1, 24, 25, 56, 57, 120])
+def test_dense_mma_k_ranges(k):
+    rng = np.random.default_rng(100 + k)
+    bits = _corpus(rng, 6000, 128, dup_every=50)
+    _check_mma(bits, _queries(rng, bits, 12), k, row_offset=5_000_000_000)
+
+
+def test_dense_mma_many_queries_multiple_blocks():
+    """More than 128 queries: several query blocks per row tile, last block ragged."""
+    rng = np.random.default_rng(77)
+    bits = _corpus(rng, 9000, 256, dup_every=64)
+    _check_mma(bits, _queries(rng, bits, 300), 10)
+
+
+def test_dense_mma_sampled_bound_large_matrix():
+    """Enough tiles that the sample pass really strides (every 16th tile) and uses
+    whole-tile maxima; oracle on a subset of the queries, scan kernel on all."""
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(78)
+    n, d, b, k = 300_000, 128, 64, 10
+    bits = _corpus(rng, n, d, dup_every=1000)
+    qbits = _queries(rng, bits, b)
+    emb, q = _to_dev(bits), _to_dev(qbits)
+    s, i, c, f = [t.clone() for t in ops.dense_topk(emb, q, k, algo="mma")]
+    s2, i2, c2, f2 = [t.clone() for t in ops.dense_topk(emb, q, k, algo="scan")]
+    torch.cuda.synchronize()
+    assert torch.equal(i, i2) and torch.equal(c, c2) and torch.equal(f, f2)
+    assert s.cpu().numpy().tobytes() == s2.cpu().numpy().tobytes()
+    for bb in range(4):
+        want_ids, want_sc = o.dense_topk(qbits[bb], bits, k)
+        assert i[bb].cpu().numpy().tolist() == want_ids.tolist()
+        assert s[bb].cpu().numpy().tobytes() == want_sc.tobytes()
+
+
+def test_dense_mma_adversarial_order_flags_or_exact():
+    """Rows sorted by similarity to the query (every later tile beats the sampled ones):
+    the candidate buffer may overflow; the call must then say so, never return a wrong
+    certified answer."""
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(79)
+    n, d, k = 40_000, 64, 10
+    bits = _corpus(rng, n, d)
+    qbits = _queries(rng, bits, 9)
+    sc = o.exact_dots(qbits[0], bits)
+    bits = bits[np.argsort(sc, kind="stable")]          # ascending similarity to query 0
+    s, i, c, f = [t.cpu().numpy() for t in ops.dense_topk(_to_dev(bits), _to_dev(qbits), k, algo="mma")]
+    for bb in range(qbits.shape[0]):
+        if f[bb] == 0:
+            want_ids, want_sc = o.dense_topk(qbits[bb], bits, k)
+            assert i[bb].tolist() == want_ids.tolist() and s[bb].tobytes() == want_sc.tobytes()
+
+
+def test_dense_mma_all_duplicates():
+    rng = np.random.default_rng(3)
+    bits = np.repeat(_corpus(rng, 1, 128), 5000, axis=0)
+    from classmate_rag_b200 import ops
+    s, i, c, f = ops.dense_topk(_to_dev(bits), _to_dev(np.repeat(bits[:1], 9, axis=0)), 10, algo="mma")
+    torch.cuda.synchronize()
+    # 5000 identical scores: far more candidates than slots -> flagged, as documented
+    assert (f.cpu().numpy() == 1).all()
+
+
+def test_dense_mma_unsupported_shapes_raise():
+    from classmate_rag_b200 import ops
+    emb = torch.zeros((100, 64), dtype=torch.bfloat16, device="cuda")
+    q = torch.zeros((9, 64), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.dense_topk(emb, q, 4, algo="mma")          # fewer than 256 rows
+    emb = torch.zeros((1000, 64), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.dense_topk(emb, q, 4, algo="mma", row_mask=torch.ones(1000, dtype=torch.uint8, device="cuda"))
+    s, i, c, f = ops.dense_topk(emb, q, 4, row_mask=torch.ones(1000, dtype=torch.uint8, device="cuda"))  # auto -> scan
+    torch.cuda.synchronize()
+    assert (c.cpu().numpy() == 4).all()
