@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libcmrag.so"
+# CMRAG_LIB: development override (kernel experiments built beside the product library)
+LIB_PATH = Path(os.environ["CMRAG_LIB"]) if os.environ.get("CMRAG_LIB") else _PKG / "libcmrag.so"
 
 CMR_OK, CMR_EINVAL, CMR_ECUDA, CMR_EWORKSPACE, CMR_EUNSUPPORTED = 0, -1, -2, -3, -4
 CMR_FLAG_UNCERTIFIED = 1
@@ -48,7 +51,7 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("CMRAG_LIB"):
         from . import build as _build
         try:
             if _build.needs_build():

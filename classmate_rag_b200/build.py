@@ -32,24 +32,27 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path = None) -> Path:
+    """Compile and link.  ``defines`` / ``out``: experiment builds (extra -D flags into a
+    separately named library, loaded through the CMRAG_LIB environment variable)."""
+    lib_out = LIB if out is None else Path(out)
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = PKG / "build"
+    build_dir = PKG / ("build" if out is None else "build_" + lib_out.stem)
     build_dir.mkdir(exist_ok=True)
     log = []
     for src in SOURCES:
         obj = build_dir / (src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib_out), *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -57,9 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (build_dir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print(LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

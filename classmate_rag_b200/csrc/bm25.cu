@@ -31,7 +31,19 @@
 namespace cmr {
 
 typedef void (*tile_fn_t)(cmr_lex_index, const int*, const int*, const uint8_t*, KeyD*);
-constexpr int BM_THREADS = 512;
+#ifndef CMR_BM_THREADS
+#define CMR_BM_THREADS 512
+#endif
+#ifndef CMR_BM_MINCTAS
+#define CMR_BM_MINCTAS 2
+#endif
+#ifndef CMR_BM_SWEEP_U
+#define CMR_BM_SWEEP_U 4
+#endif
+#ifndef CMR_BM_RUN
+#define CMR_BM_RUN 2
+#endif
+constexpr int BM_THREADS = CMR_BM_THREADS;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BMF_THREADS = 1024;
 
@@ -48,6 +60,9 @@ __device__ __forceinline__ double ldg_stream_f64(const double* p) {
 
 constexpr int BM_MAXQ = 64;  // query tokens staged per chunk
 constexpr int BM_U = 8;      // postings in flight per thread
+constexpr int BM_RUN = CMR_BM_RUN;  static_assert(BM_RUN == 1 || BM_RUN == 2, "sweep is specialised for runs of 1 or 2");
+//    // consecutive dense tokens fused into one sweep
+constexpr int BM_SWEEP_U = CMR_BM_SWEEP_U;  // documents per thread in flight in a dense sweep
 
 __device__ __forceinline__ u32 ldg_stream_u32(const u32* p) {
   u32 r;
@@ -55,10 +70,36 @@ __device__ __forceinline__ u32 ldg_stream_u32(const u32* p) {
   return r;
 }
 
+// Dense sweep over a FULL tile whose size is a multiple of BM_SWEEP_U * BM_THREADS: no
+// bounds or run predicates in the loop.  RUN consecutive dense tokens (columns c0, c1 with
+// weights w0, w1) share one read-modify-write of the accumulators; FRESH: the accumulators
+// have not been written for this tile yet, start from 0.0 instead of reading them.
+template <int RUN, bool FRESH>
+__device__ __forceinline__ void bm25_sweep_full(double* __restrict__ acc, int tile_docs,
+                                                const double* __restrict__ c0,
+                                                const double* __restrict__ c1, double w0, double w1,
+                                                int tid) {
+  for (int i0 = tid; i0 < tile_docs; i0 += BM_SWEEP_U * BM_THREADS) {
+    double f0[BM_SWEEP_U], f1[BM_SWEEP_U];
+#pragma unroll
+    for (int u = 0; u < BM_SWEEP_U; ++u) {
+      f0[u] = ldg_stream_f64(c0 + i0 + u * BM_THREADS);
+      if (RUN == 2) f1[u] = ldg_stream_f64(c1 + i0 + u * BM_THREADS);
+    }
+#pragma unroll
+    for (int u = 0; u < BM_SWEEP_U; ++u) {
+      double a = FRESH ? 0.0 : acc[i0 + u * BM_THREADS];
+      a = __dadd_rn(a, __dmul_rn(w0, f0[u]));  // no fma: rank_bm25 rounds the product first
+      if (RUN == 2) a = __dadd_rn(a, __dmul_rn(w1, f1[u]));
+      acc[i0 + u * BM_THREADS] = a;
+    }
+  }
+}
+
 // PACKED: 4-byte postings (code << 16 | tile-local doc) + float64 factor table;
 // otherwise int32 doc + float64 factor per posting.
 template <int KPL, bool PACKED>
-__global__ void __launch_bounds__(BM_THREADS)
+__global__ void __launch_bounds__(BM_THREADS, CMR_BM_MINCTAS)
 bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr,
                  const uint8_t* __restrict__ row_mask, KeyD* __restrict__ part) {
   constexpr int KP = 32 * KPL;
@@ -73,6 +114,7 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   long long* s_lo = reinterpret_cast<long long*>(s_skip + BM_MAXQ);  // [2][MAXQ] slice bounds
   long long* s_hi = s_lo + 2 * BM_MAXQ;
   double* s_seed_buf = reinterpret_cast<double*>(s_hi + 2 * BM_MAXQ);  // [128] group maxima (seeding)
+  int* s_slot = reinterpret_cast<int*>(s_seed_buf + 128);              // [MAXQ] dense column of the token or -1
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,74 +132,99 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
     const long long tile_lo = (long long)tile * ix.tile_docs;
     const long long rem = ix.n_docs - tile_lo;
     const int n_here = rem < ix.tile_docs ? (int)rem : ix.tile_docs;
-    for (int i = tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;
+    bool fresh = true;  // accumulators of this tile not written yet (a leading dense sweep starts from 0.0)
+    const bool full_tile = n_here == ix.tile_docs && (ix.tile_docs % (BM_SWEEP_U * BM_THREADS)) == 0;
+    for (int i = n_here + tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;  // ragged last tile
 
     for (int c0 = qlo; c0 < qhi; c0 += BM_MAXQ) {
       const int m = (qhi - c0) < BM_MAXQ ? (qhi - c0) : BM_MAXQ;
-      __syncthreads();  // previous users of the staging arrays are done; acc zeroed
+      __syncthreads();  // previous users of the staging arrays and of the accumulators are done
       if (tid < m) {
         const int t = q_terms[c0 + tid];
         long long lo = 0, hi = 0;
         double w = 0.0;
+        int slot = -1;
         if (t >= 0 && t < ix.n_terms) {  // unknown token: empty slice
           const long long base = ix.term_ptr[t];
           const uint32_t* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
           lo = base + sk[0];
           hi = base + sk[1];
           w = ix.idf[t];
+          if (ix.dense_slot != nullptr) slot = ix.dense_slot[t];
         }
         s_w[tid] = w;
         s_lo[tid] = lo;
         s_hi[tid] = hi;
+        s_slot[tid] = slot;
       }
       __syncthreads();
 
-      // token passes, in query order; loads of pass j+1 are issued before pass j is applied
-      u32 pk[2][BM_U];      // packed postings / tile-local docs
-      double pv[2][BM_U];   // wide format: factors
-      auto issue = [&](int j, int buf) {
-        const long long lo = s_lo[j];
-        const int n = (int)(s_hi[j] - lo);  // <= tile_docs
-        const u32* pp = ix.post_pack + lo;
-        const int* pd = ix.post_doc + lo;
-        const double* pi = ix.post_imp + lo;
-#pragma unroll
-        for (int u = 0; u < BM_U; ++u) {
-          const int i = tid + u * BM_THREADS;
-          if (i < n) {
-            if (PACKED) {
-              pk[buf][u] = ldg_stream_u32(pp + i);
+      // token passes, strictly in query order (float64 addition order = rank_bm25's)
+      int j = 0;
+      while (j < m) {
+        if (s_slot[j] >= 0) {
+          // ---- dense term(s): owner-computes sweep over the tile ------------------------
+          // Up to BM_RUN consecutive dense tokens share one read-modify-write of the
+          // accumulators.  Thread t owns documents t, t+512, ...: coalesced 8-byte loads of
+          // the terms' factor columns (0.0 where the term is absent: x + 0.0 == x), conflict
+          // free shared-memory accesses, no atomics.
+          int run = 1;
+          while (run < BM_RUN && j + run < m && s_slot[j + run] >= 0) ++run;
+          if (full_tile) {
+            const double* c0p = ix.dense_imp + (size_t)s_slot[j] * ix.n_docs + tile_lo;
+            const double w0 = s_w[j];
+            if (run == 2) {
+              const double* c1p = ix.dense_imp + (size_t)s_slot[j + 1] * ix.n_docs + tile_lo;
+              const double w1 = s_w[j + 1];
+              if (fresh) bm25_sweep_full<2, true>(acc, ix.tile_docs, c0p, c1p, w0, w1, tid);
+              else bm25_sweep_full<2, false>(acc, ix.tile_docs, c0p, c1p, w0, w1, tid);
             } else {
-              pk[buf][u] = (u32)(ldg_stream_i32(pd + i) - (int)tile_lo);
-              pv[buf][u] = ldg_stream_f64(pi + i);
+              if (fresh) bm25_sweep_full<1, true>(acc, ix.tile_docs, c0p, c0p, w0, w0, tid);
+              else bm25_sweep_full<1, false>(acc, ix.tile_docs, c0p, c0p, w0, w0, tid);
+            }
+          } else {
+            // ragged last tile / odd tile size: predicated version
+            const double* col[BM_RUN];
+            double w[BM_RUN];
+#pragma unroll
+            for (int r = 0; r < BM_RUN; ++r) {
+              const int jj = j + (r < run ? r : 0);
+              col[r] = ix.dense_imp + (size_t)s_slot[jj] * ix.n_docs + tile_lo;
+              w[r] = s_w[jj];
+            }
+            for (int i = tid; i < n_here; i += BM_THREADS) {
+              double a = fresh ? 0.0 : acc[i];
+#pragma unroll
+              for (int r = 0; r < BM_RUN; ++r)
+                if (r < run) a = __dadd_rn(a, __dmul_rn(w[r], ldg_stream_f64(col[r] + i)));
+              acc[i] = a;
             }
           }
+          fresh = false;
+          j += run;
+          __syncthreads();
+          continue;
         }
-      };
-      auto apply = [&](int j, int buf) {
+        // ---- sparse term: scatter its slice of postings into the accumulators -----------
         const long long lo = s_lo[j];
-        const int n = (int)(s_hi[j] - lo);
-        const double w = s_w[j];
-#pragma unroll
-        for (int u = 0; u < BM_U; ++u) {
-          const int i = tid + u * BM_THREADS;
-          if (i < n) {
-            const u32 loc = PACKED ? (pk[buf][u] & 0xFFFFu) : pk[buf][u];
-            const double imp = PACKED ? __ldg(ix.imp_table + (pk[buf][u] >> 16)) : pv[buf][u];
-            acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));  // no fma: rank_bm25 rounds the product
+        const int n = (int)(s_hi[j] - lo);  // <= tile_docs
+        if (n > 0) {
+          if (fresh) {
+            for (int i = tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;
+            fresh = false;
+            __syncthreads();
           }
-        }
-        // long slices (tile_docs > BM_U * BM_THREADS): the rest, BM_U at a time
-        const u32* pp = ix.post_pack + lo;
-        const int* pd = ix.post_doc + lo;
-        const double* pi = ix.post_imp + lo;
-        for (int i0 = BM_U * BM_THREADS; i0 < n; i0 += BM_U * BM_THREADS) {
-          u32 k2[BM_U];
-          double v2[BM_U];
+          const double w = s_w[j];
+          const u32* pp = ix.post_pack + lo;
+          const int* pd = ix.post_doc + lo;
+          const double* pi = ix.post_imp + lo;
+          int i0 = 0;
+          for (; i0 + BM_U * BM_THREADS <= n; i0 += BM_U * BM_THREADS) {  // full chunks: no predicates
+            u32 k2[BM_U];
+            double v2[BM_U];
 #pragma unroll
-          for (int u = 0; u < BM_U; ++u) {
-            const int i = i0 + tid + u * BM_THREADS;
-            if (i < n) {
+            for (int u = 0; u < BM_U; ++u) {
+              const int i = i0 + tid + u * BM_THREADS;
               if (PACKED) {
                 k2[u] = ldg_stream_u32(pp + i);
               } else {
@@ -165,32 +232,38 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
                 v2[u] = ldg_stream_f64(pi + i);
               }
             }
-          }
 #pragma unroll
-          for (int u = 0; u < BM_U; ++u) {
-            const int i = i0 + tid + u * BM_THREADS;
-            if (i < n) {
+            for (int u = 0; u < BM_U; ++u) {
               const u32 loc = PACKED ? (k2[u] & 0xFFFFu) : k2[u];
               const double imp = PACKED ? __ldg(ix.imp_table + (k2[u] >> 16)) : v2[u];
-              acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));
+              acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));  // documents are unique within a list
             }
           }
+          // tail (for a sparse term usually the whole slice): warps past the end skip at once
+          for (int i = i0 + tid; i < n; i += BM_THREADS) {
+            u32 loc;
+            double imp;
+            if (PACKED) {
+              const u32 pk = ldg_stream_u32(pp + i);
+              loc = pk & 0xFFFFu;
+              imp = __ldg(ix.imp_table + (pk >> 16));
+            } else {
+              loc = (u32)(ldg_stream_i32(pd + i) - (int)tile_lo);
+              imp = ldg_stream_f64(pi + i);
+            }
+            acc[loc] = __dadd_rn(acc[loc], __dmul_rn(w, imp));
+          }
+          __syncthreads();  // a document may appear in the next token's list too
         }
-      };
-      if (m > 0) issue(0, 0);
-      for (int j = 0; j < m; ++j) {
-        if (j + 1 < m) {
-          if ((j & 1) == 0) issue(j + 1, 1);
-          else issue(j + 1, 0);
-        }
-        if ((j & 1) == 0) apply(j, 0);
-        else apply(j, 1);
-        __syncthreads();  // a document may appear in the next token's list too
+        ++j;
       }
+    }
+    if (fresh) {  // no token touched this tile: every document scores 0.0
+      for (int i = tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;
     }
     __syncthreads();
 
-    // Threshold seeding (first tile of this CTA only).  Split the tile into 128
+    // Threshold seeding (first tile of this CTA only).  Split the tile into BM_THREADS/4
     // groups of documents and take each group's best score: the KP-th largest of
     // those 128 maxima is reached by at least KP documents, so nothing below it can
     // be in this CTA's top KP.  Every warp starts from the largest double below
@@ -207,10 +280,12 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
       m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
       if ((tid & 3) == 0) s_seed_buf[tid >> 2] = m;
       __syncthreads();
-      if (tid < 128) {
+      constexpr int SEED_GROUPS = BM_THREADS / 4;  // <= 128 slots in s_seed_buf
+      static_assert(SEED_GROUPS <= 128, "s_seed_buf holds 128 group maxima");
+      if (tid < SEED_GROUPS) {
         const double mine = s_seed_buf[tid];
         int cnt = 0;
-        for (int j = 0; j < 128; ++j) {
+        for (int j = 0; j < SEED_GROUPS; ++j) {
           const double o = s_seed_buf[j];
           cnt += (o > mine) || (o == mine && j < tid);
         }
@@ -332,6 +407,7 @@ static int check_index(const cmr_lex_index* ix) {
   CMR_CHECK_ARG(ix->n_tiles >= 1 && (long long)ix->n_tiles * ix->tile_docs >= ix->n_docs, "n_tiles inconsistent with n_docs/tile_docs");
   CMR_CHECK_ARG(ix->n_terms >= 0, "n_terms negative");
   CMR_CHECK_ARG(ix->n_terms == 0 || (ix->term_ptr && ix->tile_skip && ix->idf), "null index arrays");
+  CMR_CHECK_ARG(ix->n_dense >= 0 && (ix->n_dense == 0 || (ix->dense_imp && ix->dense_slot)), "dense columns inconsistent");
   return CMR_OK;
 }
 
@@ -339,7 +415,7 @@ static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p)
   p->kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
   const int kp = 32 * p->kpl;
   p->smem_tile = (size_t)ix.tile_docs * 8 + (size_t)BM_WARPS * kp * 16 + (size_t)kp * 16 + BM_WARPS * 8 +
-                 (size_t)BM_MAXQ * (8 + 8 + 8 + 4 * 8) + 128 * 8 + 16;
+                 (size_t)BM_MAXQ * (8 + 8 + 8 + 4 * 8) + 128 * 8 + (size_t)BM_MAXQ * 4 + 16;
   p->packed = ix.post_pack != nullptr && ix.imp_table != nullptr;
   if (p->smem_tile > 220 * 1024) {
     set_error("bm25 tile shared memory %zu too large: lower tile_docs", p->smem_tile);

@@ -21,6 +21,8 @@ BM25_K1 = 1.5
 BM25_B = 0.75
 BM25_EPS = 0.25
 DEFAULT_TILE_DOCS = 8192
+DENSE_DENSITY = 0.125    # terms in at least this share of the documents get a factor column
+DENSE_MAX_TERMS = 64     # 8 B x n_docs each
 
 
 class LexIndexStruct(C.Structure):
@@ -28,9 +30,10 @@ class LexIndexStruct(C.Structure):
     _fields_ = [
         ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_pack", C.c_void_p), ("imp_table", C.c_void_p),
         ("post_doc", C.c_void_p), ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p),
-        ("idf", C.c_void_p),
+        ("idf", C.c_void_p), ("dense_imp", C.c_void_p), ("dense_slot", C.c_void_p),
         ("n_docs", C.c_int64), ("n_terms", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
-        ("n_codes", C.c_int32), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
+        ("n_codes", C.c_int32), ("n_dense", C.c_int32), ("reserved_", C.c_int32),
+        ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
     ]
 
 
@@ -73,6 +76,9 @@ class LexicalIndex:
     imp_table: Optional[torch.Tensor] = None   # float64 [n_codes]: factor of each distinct (tf, doc_len) pair
     pair_tf: Optional[torch.Tensor] = None     # int32 [n_codes]
     pair_dl: Optional[torch.Tensor] = None     # int32 [n_codes]
+    dense_imp: Optional[torch.Tensor] = None   # float64 [n_dense, N]: factor column of each dense term
+    dense_slot: Optional[torch.Tensor] = None  # int32 [V]: column of the term or -1
+    dense_terms: Optional[np.ndarray] = field(default=None, repr=False)  # term id of each column
     idf_host: np.ndarray = field(default=None, repr=False)
     df_host: np.ndarray = field(default=None, repr=False)        # corpus-wide df
     shard_df_host: np.ndarray = field(default=None, repr=False)  # postings per term in THIS shard
@@ -92,15 +98,23 @@ class LexicalIndex:
             self._struct = LexIndexStruct(
                 self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), opt(self.post_pack), opt(self.imp_table),
                 self.post_doc.data_ptr(), opt(self.post_imp), self.post_tf.data_ptr(), self.doc_len.data_ptr(),
-                self.idf.data_ptr(), self.n_docs, self.n_terms, self.tile_docs, self.n_tiles,
-                0 if self.imp_table is None else int(self.imp_table.numel()), self.avgdl, self.k1, self.b)
+                self.idf.data_ptr(), opt(self.dense_imp), opt(self.dense_slot),
+                self.n_docs, self.n_terms, self.tile_docs, self.n_tiles,
+                0 if self.imp_table is None else int(self.imp_table.numel()),
+                0 if self.dense_imp is None else int(self.dense_imp.shape[0]), 0, self.avgdl, self.k1, self.b)
         return self._struct
 
     def posting_bytes(self, terms: Sequence[int]) -> int:
-        """Algorithmic bytes one query streams: 4 B per packed posting (12 B wide:
-        int32 doc + float64 factor) of every query token, multiplicity counted."""
+        """Algorithmic bytes one query streams, multiplicity counted: 4 B per packed
+        posting (12 B wide: int32 doc + float64 factor) of every sparse query token,
+        8 B per document (the float64 factor column) of every dense one."""
         per = 4 if self.post_pack is not None else 12
-        return per * int(sum(int(self.shard_df_host[t]) for t in terms if 0 <= t < self.n_terms))
+        dense = set() if self.dense_terms is None else set(int(t) for t in self.dense_terms)
+        total = 0
+        for t in terms:
+            if 0 <= t < self.n_terms:
+                total += 8 * self.n_docs if t in dense else per * int(self.shard_df_host[t])
+        return total
 
 
 @dataclass
@@ -144,11 +158,15 @@ def bm25_factor(tf: torch.Tensor, dl: torch.Tensor, avgdl: float, k1: float, b: 
 def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int, *,
                         device=None, tile_docs: int = DEFAULT_TILE_DOCS,
                         stats: Optional[GlobalStats] = None, fmt: str = "auto",
-                        k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS) -> LexicalIndex:
+                        k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS,
+                        dense_density: Optional[float] = DENSE_DENSITY,
+                        dense_max_terms: int = DENSE_MAX_TERMS) -> LexicalIndex:
     """Build the CSR index of the documents ``tokens[doc_ptr[i]:doc_ptr[i+1]]``.
 
     ``stats`` (optional) supplies corpus-wide df / N / total tokens when this
-    call builds one shard of a larger corpus."""
+    call builds one shard of a larger corpus.  ``dense_density`` (None = off):
+    terms present in at least that share of the documents also get a dense
+    float64 factor column, swept instead of scattered by the kernel."""
     if device is None:
         device = tokens.device
     doc_ptr = doc_ptr.to(device).long()
@@ -209,12 +227,34 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
             raise ValueError("corpus has more than 65536 distinct (tf, doc_len) pairs: packed postings impossible")
         imp = (bm25_factor(counts, dl_post, avgdl, k1, b) if avgdl > 0
                else torch.zeros(counts.numel(), dtype=torch.float64, device=device))
+    # dense terms: full float64 factor columns (cmr_lex_index.dense_imp)
+    dense_imp = dense_slot = dense_terms = None
+    if dense_density is not None and total > 0 and n_docs > 0:
+        shard_df = (term_ptr[1:] - term_ptr[:-1])
+        cand = torch.nonzero(shard_df.double() >= dense_density * n_docs).flatten()
+        if cand.numel() > dense_max_terms:
+            cand = cand[torch.argsort(shard_df[cand], descending=True)[:dense_max_terms]].sort().values
+        if cand.numel() > 0:
+            dense_terms = cand.cpu().numpy()
+            dense_imp = torch.zeros((cand.numel(), n_docs), dtype=torch.float64, device=device)
+            slot = torch.full((n_terms,), -1, dtype=torch.int32, device=device)
+            slot[cand] = torch.arange(cand.numel(), dtype=torch.int32, device=device)
+            dense_slot = slot
+            for c, t in enumerate(dense_terms.tolist()):
+                a, z = int(term_ptr[t]), int(term_ptr[t + 1])
+                d_t = doc[a:z]
+                if imp_table is not None:
+                    f_t = imp_table[((post_pack[a:z].long() >> 16) & 0xFFFF)]
+                else:
+                    f_t = imp[a:z]
+                dense_imp[c, d_t] = f_t
     tf32 = counts.clamp(max=65535).to(torch.int32)
     tf16 = torch.where(tf32 >= 32768, tf32 - 65536, tf32).to(torch.int16)
     return LexicalIndex(
         term_ptr=term_ptr.contiguous(), tile_skip=skip.to(torch.int32).contiguous(),
         post_doc=doc.to(torch.int32).contiguous(), post_imp=None if imp is None else imp.contiguous(),
         post_pack=post_pack, imp_table=imp_table, pair_tf=pair_tf, pair_dl=pair_dl,
+        dense_imp=dense_imp, dense_slot=dense_slot, dense_terms=dense_terms,
         post_tf=tf16.contiguous(), doc_len=doc_len.to(torch.int32).contiguous(),
         idf=torch.from_numpy(idf_host).to(device), n_docs=n_docs, n_terms=n_terms, tile_docs=tile_docs,
         n_tiles=n_tiles, avgdl=float(avgdl), k1=k1, b=b, idf_host=idf_host, df_host=stats.df,

@@ -115,7 +115,7 @@ int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t str
  * of a term sorted by document, plus a skip table that gives, per term, the
  * posting offset at which every tile of `tile_docs` documents starts.
  * Scores are accumulated in float64 in query-token order with rank_bm25's own
- * operation order (the per-posting factor is an exact float64, stored either per
+ * operation order (idf * factor rounded, then added; no fma) (the per-posting factor is an exact float64, stored either per
  * posting or once per distinct (tf, doc_len) pair), so they are bit-identical to the reference arithmetic and
  * no rescoring pass (and no certificate) is needed: out_flags is always 0.
  * All pointers are device memory.
@@ -133,11 +133,19 @@ typedef struct cmr_lex_index {
   const uint16_t* post_tf;   /* [P] term frequency (saturated at 65535); may be NULL    */
   const int32_t* doc_len;    /* [n_docs] tokens per document; may be NULL               */
   const double* idf;         /* [n_terms] float64 idf with the epsilon floor            */
+  /* dense terms (optional): terms present in a large share of the shard's documents also
+   * get a full per-document column of their float64 factor (0.0 where absent), which the
+   * kernel sweeps with coalesced loads instead of scattering their postings.  The CSR
+   * arrays still hold their postings (filtered scoring, statistics).                    */
+  const double* dense_imp;   /* [n_dense, n_docs] or NULL                               */
+  const int32_t* dense_slot; /* [n_terms] column of the term in dense_imp, -1 = sparse; NULL when n_dense == 0 */
   int64_t n_docs;
   int32_t n_terms;
   int32_t tile_docs;         /* multiple of 512, <= 65536                               */
   int32_t n_tiles;
   int32_t n_codes;
+  int32_t n_dense;
+  int32_t reserved_;
   double avgdl;
   double k1;
   double b;

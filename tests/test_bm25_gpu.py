@@ -9,9 +9,9 @@ from tests.synth_small import zipf_corpus, zipf_queries
 pytestmark = pytest.mark.gpu
 
 
-def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0, fmt="auto"):
+def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0, fmt="auto", **build_kw):
     from classmate_rag_b200 import lexical, ops
-    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs, fmt=fmt)
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs, fmt=fmt, **build_kw)
     assert (ix.post_pack is None) == (fmt == "wide")
     qt, qp = lexical.pack_queries(queries)
     m = None if mask is None else torch.from_numpy(mask).cuda()
@@ -87,3 +87,23 @@ def test_bm25_wide_format_and_long_queries():
     queries = zipf_queries(3, 5, 200) + [long_q]
     _run(docs, doc_ptr, tokens, v, queries, 10, 1024, fmt="wide")
     _run(docs, doc_ptr, tokens, v, queries, 10, 1024, fmt="packed")
+
+
+@pytest.mark.parametrize("density,max_terms", [(None, 0), (0.125, 64), (0.0001, 64), (0.0001, 3), (0.5, 64)])
+def test_bm25_dense_columns_do_not_change_results(density, max_terms):
+    """Dense factor columns are only a different way to walk the same postings: off, default,
+    (nearly) every term dense, a capped number of columns.  Queries mix dense and sparse
+    tokens in every order, repeat dense tokens (runs longer than the fused sweep) and start
+    with sparse ones."""
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=21, n_docs=11000, vocab=120, mean_len=14)
+    queries = zipf_queries(5, 10, 120) + [[0, 1, 2, 3, 4, 5, 6], [100, 0, 0, 0, 0, 0, 1], [0], [119, 118], [1, 117, 2, 116, 3]]
+    kw = {} if density is None else {"dense_max_terms": max_terms}
+    ix = _run(docs, doc_ptr, tokens, v, queries, 10, 2048, dense_density=density, **kw)
+    if density is None:
+        assert ix.dense_imp is None
+    elif density <= 0.001:
+        assert ix.dense_imp.shape[0] == min(max_terms, int((ix.shard_df_host >= density * 11000).sum()))
+    _run(docs, doc_ptr, tokens, v, queries, 10, 1024, fmt="wide", dense_density=density, **kw)
+    rng = np.random.default_rng(5)
+    _run(docs, doc_ptr, tokens, v, queries, 10, 2048, mask=(rng.random(11000) < 0.5).astype(np.uint8),
+         dense_density=density, **kw)

@@ -66,3 +66,30 @@ def test_empty_corpus_builds():
     ix = lexical.build_lexical_index(torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=torch.int32), 5,
                                      device="cpu", tile_docs=512)
     assert ix.n_docs == 0 and ix.n_postings == 0 and ix.n_tiles == 1
+
+
+def test_dense_columns_hold_the_posting_factors():
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=6, n_docs=900, vocab=60, mean_len=12)
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512, dense_density=0.2)
+    assert ix.dense_imp is not None and ix.dense_imp.shape[1] == 900
+    df = ix.shard_df_host
+    assert sorted(ix.dense_terms.tolist()) == [t for t in range(v) if df[t] >= 0.2 * 900]
+    slot = ix.dense_slot.numpy()
+    assert (slot >= 0).sum() == len(ix.dense_terms)
+    tp = ix.term_ptr.numpy()
+    code = (ix.post_pack.numpy().view(np.uint32) >> 16).astype(np.int64)
+    for t in ix.dense_terms.tolist():
+        col = ix.dense_imp[slot[t]].numpy()
+        lo, hi = tp[t], tp[t + 1]
+        d = ix.post_doc[lo:hi].numpy()
+        assert np.array_equal(col[d], ix.imp_table.numpy()[code[lo:hi]])
+        rest = np.ones(900, dtype=bool)
+        rest[d] = False
+        assert (col[rest] == 0.0).all()
+    st = ix.struct()
+    assert st.n_dense == len(ix.dense_terms) and st.dense_imp == ix.dense_imp.data_ptr()
+    off = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512, dense_density=None)
+    assert off.dense_imp is None and off.struct().n_dense == 0
+    # algorithmic bytes: a dense token streams its 8-byte column, a sparse one its 4-byte postings
+    t_dense, t_sparse = int(ix.dense_terms[0]), int(np.argmin(np.where(df > 0, df, 1 << 30)))
+    assert ix.posting_bytes([t_dense, t_sparse, -1]) == 8 * 900 + 4 * int(df[t_sparse])
