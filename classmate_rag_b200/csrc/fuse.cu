@@ -244,6 +244,82 @@ topk_merge_kernel(const double* __restrict__ in_scores, const long long* __restr
   if (tid == 0) out_counts[qi] = n_out;
 }
 
+// A3 standalone: rrf_fuse over any number of rank lists (rag/retrieval/fusion.py:17-36).
+// One CTA.  Thread i owns entry i of the concatenated lists; an entry that is the first
+// occurrence of its id walks every list in order and adds w * (1.0 / (rrf_k + rank)) exactly
+// as the reference's dict accumulation does (list by list, rank by rank).  Output keeps the
+// dict's insertion order (first appearance).
+constexpr int RRF_THREADS = 256;
+constexpr int RRF_MAX_ENTRIES = 4096;
+
+__global__ void __launch_bounds__(RRF_THREADS)
+rrf_fuse_kernel(const long long* __restrict__ ids, const int* __restrict__ counts, int n_lists, int max_len,
+                const double* __restrict__ weights, int rrf_k, long long* __restrict__ out_ids,
+                double* __restrict__ out_scores, int* __restrict__ out_count) {
+  __shared__ unsigned char s_first[RRF_MAX_ENTRIES];
+  __shared__ int s_pos[RRF_MAX_ENTRIES];
+  const int tid = threadIdx.x;
+  const int total = n_lists * max_len;
+  for (int e = tid; e < total; e += RRF_THREADS) {
+    const int l = e / max_len, r = e - l * max_len;
+    bool first = r < counts[l];
+    if (first) {
+      const long long id = ids[e];
+      for (int l2 = 0; l2 <= l && first; ++l2) {
+        const int lim = l2 < l ? counts[l2] : r;
+        for (int r2 = 0; r2 < lim; ++r2)
+          if (ids[(size_t)l2 * max_len + r2] == id) {
+            first = false;
+            break;
+          }
+      }
+    }
+    s_first[e] = first ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive scan over <= 4096 flags: output slot of every first occurrence
+    int n = 0;
+    for (int e = 0; e < total; ++e) {
+      s_pos[e] = n;
+      n += s_first[e];
+    }
+    *out_count = n;
+  }
+  __syncthreads();
+  for (int e = tid; e < total; e += RRF_THREADS) {
+    if (!s_first[e]) continue;
+    const long long id = ids[e];
+    double score = 0.0;
+    for (int l = 0; l < n_lists; ++l) {
+      const double w = weights[l];
+      for (int r = 0; r < counts[l]; ++r)
+        if (ids[(size_t)l * max_len + r] == id)
+          score = __dadd_rn(score, __dmul_rn(w, __ddiv_rn(1.0, (double)(rrf_k + (r + 1)))));
+    }
+    out_ids[s_pos[e]] = id;
+    out_scores[s_pos[e]] = score;
+  }
+}
+
+// N1: metadata `where` evaluated on the device.  Every filterable field is a dictionary-coded
+// int32 column ([n_fields][n_rows], -1 = field absent); a clause list is a conjunction of
+// (field, code) equalities.  code -1 asks for "field absent" (the reference's BM25 filter
+// matches a None-valued filter key only against documents lacking the field, quirk Q1);
+// the host encodes a value that is not in the dictionary as code -2, which matches nothing.
+// `alive` (optional) carries tombstones of deleted rows.
+__global__ void filter_mask_kernel(const int* __restrict__ cols, long long n_rows, const int* __restrict__ clause_field,
+                                   const int* __restrict__ clause_code, int n_clauses,
+                                   const uint8_t* __restrict__ alive, uint8_t* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_rows; i += stride) {
+    bool ok = alive == nullptr || alive[i] != 0;
+    for (int c = 0; c < n_clauses && ok; ++c)
+      ok = cols[(size_t)clause_field[c] * n_rows + i] == clause_code[c];
+    out[i] = ok ? 1 : 0;
+  }
+}
+
 }  // namespace cmr
 
 using namespace cmr;
@@ -313,6 +389,34 @@ extern "C" int cmr_topk_merge(const double* in_scores, const int64_t* in_ids, co
   topk_merge_kernel<<<n_queries, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
       in_scores, (const long long*)in_ids, in_counts, n_parts, n_queries, k, out_scores, (long long*)out_ids,
       out_counts);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_rrf_fuse(const int64_t* list_ids, const int32_t* list_counts, int n_lists, int max_len,
+                            const double* weights, int rrf_k, int64_t* out_ids, double* out_scores,
+                            int32_t* out_count, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_lists >= 1 && max_len >= 1 && (long long)n_lists * max_len <= RRF_MAX_ENTRIES,
+                "rrf_fuse: n_lists * max_len must be in 1..%d", RRF_MAX_ENTRIES);
+  CMR_CHECK_ARG(list_ids && list_counts && weights && out_ids && out_scores && out_count, "null pointer argument");
+  rrf_fuse_kernel<<<1, RRF_THREADS, 0, (cudaStream_t)stream>>>((const long long*)list_ids, list_counts, n_lists,
+                                                               max_len, weights, rrf_k, (long long*)out_ids,
+                                                               out_scores, out_count);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_filter_mask(const int32_t* field_codes, int64_t n_rows, int n_fields,
+                               const int32_t* clause_field, const int32_t* clause_code, int n_clauses,
+                               const uint8_t* alive, uint8_t* out_mask, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_rows >= 0 && n_fields >= 0 && n_clauses >= 0 && n_clauses <= 64, "bad filter shape");
+  CMR_CHECK_ARG(n_rows == 0 || out_mask, "null output mask");
+  CMR_CHECK_ARG(n_clauses == 0 || (field_codes && clause_field && clause_code), "null clause arrays");
+  if (n_rows == 0) return CMR_OK;
+  long long blocks = (n_rows + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  filter_mask_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(field_codes, n_rows, clause_field, clause_code,
+                                                                    n_clauses, alive, out_mask);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }

@@ -227,3 +227,47 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor, counts: torch.Tensor):
         _lib.check(_lib.load().cmr_topk_merge(scores.data_ptr(), ids.data_ptr(), counts.data_ptr(), g, b, k,
                                               out_s.data_ptr(), out_i.data_ptr(), out_c.data_ptr(), _stream()))
     return out_s, out_i, out_c
+
+
+def rrf_fuse_lists(list_ids: torch.Tensor, list_counts: torch.Tensor, weights: torch.Tensor, rrf_k: int = 60):
+    """rrf_fuse over L rank lists.  list_ids i64 [L, max_len], list_counts i32 [L],
+    weights f64 [L] (device).  Returns (ids i64 [L*max_len], scores f64 [L*max_len],
+    count i32 [1]): distinct ids in first-appearance order."""
+    for name, t in (("list_ids", list_ids), ("list_counts", list_counts), ("weights", weights)):
+        _require_cuda(t, name)
+    if list_ids.dtype != torch.int64 or list_counts.dtype != torch.int32 or weights.dtype != torch.float64:
+        raise ValueError("rrf_fuse_lists: list_ids int64, list_counts int32, weights float64")
+    n_lists, max_len = list_ids.shape
+    dev = list_ids.device
+    out_ids = torch.empty((n_lists * max_len,), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((n_lists * max_len,), dtype=torch.float64, device=dev)
+    out_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_rrf_fuse(list_ids.data_ptr(), list_counts.data_ptr(), n_lists, max_len,
+                                            weights.data_ptr(), int(rrf_k), out_ids.data_ptr(),
+                                            out_scores.data_ptr(), out_count.data_ptr(), _stream()))
+    return out_ids, out_scores, out_count
+
+
+def filter_mask(field_codes: torch.Tensor, clause_field: torch.Tensor, clause_code: torch.Tensor,
+                alive: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 [n_rows] mask of the rows whose dictionary-coded metadata satisfy every
+    (field, code) clause (cmr_filter_mask).  field_codes int32 [n_fields, n_rows]."""
+    _require_cuda(field_codes, "field_codes")
+    if field_codes.dtype != torch.int32 or field_codes.dim() != 2:
+        raise ValueError("field_codes must be int32 [n_fields, n_rows]")
+    n_fields, n_rows = field_codes.shape
+    n_clauses = int(clause_field.numel())
+    if n_clauses:
+        _require_cuda(clause_field, "clause_field")
+        _require_cuda(clause_code, "clause_code")
+    if alive is not None:
+        _require_cuda(alive, "alive")
+    if out is None:
+        out = torch.empty((n_rows,), dtype=torch.uint8, device=field_codes.device)
+    with torch.cuda.device(field_codes.device):
+        _lib.check(_lib.load().cmr_filter_mask(field_codes.data_ptr(), n_rows, n_fields,
+                                               clause_field.data_ptr() if n_clauses else None,
+                                               clause_code.data_ptr() if n_clauses else None, n_clauses,
+                                               _ptr(alive), out.data_ptr(), _stream()))
+    return out

@@ -1,0 +1,270 @@
+"""Lexical store on one B200: the drop-in for the reference's BM25Store
+(rag/retrieval/bm25.py:110-256).
+
+Same dataclass fields, method names, keyword-only arguments, JSONL persistence format and
+result dicts.  The per-query ``BM25Okapi`` rebuild + Python scoring + full sort of the
+reference is replaced by a device-resident inverted index (classmate_rag_b200.lexical) and
+``cmr_bm25_topk``; scores are bit-identical to rank_bm25's float64 arithmetic and ties keep
+insertion order, so the ranked ids match the reference's stable sort exactly.
+
+Filters follow ``_matches_filter`` to the letter (filters.bm25_clauses).  Like the
+reference, a filtered search scores over the statistics of the FILTERED subset (N, df,
+avgdl all change): the subset's index is built on the device once per distinct filter and
+cached until the store changes.
+"""
+from __future__ import annotations
+
+import json
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _lib, lexical, ops
+from .filters import MetaColumns, bm25_clauses
+from .ids import REGISTRY
+from .text import detect_lang_tag, tokenize
+
+
+@dataclass
+class _Entry:
+    id: str
+    text: str
+    tokens: List[str]
+    metadata: Dict[str, Any]
+
+
+class _DeviceIndex:
+    """Inverted index of a list of entries (the whole store or a filtered subset)."""
+
+    def __init__(self, rows: Sequence[int], doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int,
+                 all_doc_ptr_host: np.ndarray, device):
+        # rows: positions (in store order) of the documents this index covers
+        self.rows = np.asarray(rows, dtype=np.int64)
+        if len(rows) == all_doc_ptr_host.shape[0] - 1:
+            sub_ptr, sub_tok = doc_ptr, tokens
+        else:
+            r = torch.from_numpy(self.rows).to(device)
+            lens = (doc_ptr[1:] - doc_ptr[:-1])[r]
+            sub_ptr = torch.zeros(len(rows) + 1, dtype=torch.int64, device=device)
+            sub_ptr[1:] = torch.cumsum(lens, 0)
+            total = int(sub_ptr[-1])
+            if total:
+                doc_of = torch.repeat_interleave(torch.arange(len(rows), device=device), lens)
+                pos = torch.arange(total, device=device) - sub_ptr[doc_of] + doc_ptr[r][doc_of]
+                sub_tok = tokens[pos]
+            else:
+                sub_tok = tokens[:0]
+        n_docs = len(rows)
+        tile = 512
+        while tile < 8192 and tile * 4 < n_docs:
+            tile *= 2
+        self.lex = lexical.build_lexical_index(sub_ptr, sub_tok, max(n_terms, 1), device=device, tile_docs=tile)
+        self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
+
+
+@dataclass
+class BM25Store:
+    index_dir: Path = Path("./indexes/bm25")
+    index_file: str = "bm25_index.jsonl"
+    device: str = "cuda"
+
+    _entries: Dict[str, _Entry] = field(default_factory=dict)   # id -> entry, insertion ordered
+    _id_list: List[str] = field(default_factory=list)           # order of the index rows
+    _vocab: Dict[str, int] = field(default_factory=dict, repr=False)
+    _full: Optional[_DeviceIndex] = field(default=None, repr=False)
+    _subsets: "OrderedDict[tuple, _DeviceIndex]" = field(default_factory=OrderedDict, repr=False)
+    _columns: Optional[MetaColumns] = field(default=None, repr=False)
+    _dirty: bool = field(default=True, repr=False)
+    _dev_tokens: Optional[Tuple[torch.Tensor, torch.Tensor, np.ndarray]] = field(default=None, repr=False)
+    _gids: Optional[torch.Tensor] = field(default=None, repr=False)
+
+    # ---------- core ops ----------
+    def _rebuild(self) -> None:
+        """Reference: rebuild BM25Okapi from the token lists after every mutation.  Here the
+        id order is refreshed at once and the device index lazily, on the next search."""
+        self._id_list = list(self._entries.keys())
+        self._dirty = True
+        self._full = None
+        self._subsets.clear()
+
+    def _ensure_index(self) -> None:
+        if not self._dirty and self._full is not None:
+            return
+        if not torch.cuda.is_available():
+            raise RuntimeError("BM25Store needs a CUDA device: classmate_rag_b200 has no CPU path")
+        dev = torch.device(self.device)
+        vocab = self._vocab
+        lens = np.zeros(len(self._id_list), dtype=np.int64)
+        flat: List[int] = []
+        for i, cid in enumerate(self._id_list):
+            toks = self._entries[cid].tokens
+            lens[i] = len(toks)
+            for t in toks:
+                n = vocab.get(t)
+                if n is None:
+                    n = vocab[t] = len(vocab)
+                flat.append(n)
+        ptr = np.zeros(len(lens) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(lens)
+        doc_ptr = torch.from_numpy(ptr).to(dev)
+        tokens = torch.from_numpy(np.asarray(flat, dtype=np.int32)).to(dev)
+        self._dev_tokens = (doc_ptr, tokens, ptr)
+        self._columns = MetaColumns(dev)
+        self._columns.reset([self._entries[c].metadata for c in self._id_list])
+        self._gids = torch.tensor([REGISTRY.intern(c) for c in self._id_list], dtype=torch.int64, device=dev)
+        self._full = _DeviceIndex(range(len(self._id_list)), doc_ptr, tokens, len(vocab), ptr, dev)
+        self._subsets.clear()
+        self._dirty = False
+
+    def upsert_many(self, *, ids: Sequence[str], texts: Sequence[str], metadatas: Sequence[Mapping[str, Any]]) -> None:
+        """Add or replace documents; tokenised with the metadata language, detected when it is
+        missing or "auto" (and then written back into the stored metadata)."""
+        if not (len(ids) == len(texts) == len(metadatas)):
+            raise ValueError("ids, texts, metadatas must have the same length")
+        for i, doc_id in enumerate(ids):
+            text = texts[i] or ""
+            meta = dict(metadatas[i] or {})
+            lang = meta.get("language")
+            if not lang or lang == "auto":
+                lang = detect_lang_tag(text)
+                meta["language"] = lang
+            self._entries[doc_id] = _Entry(id=doc_id, text=text, tokens=tokenize(text, lang_hint=lang), metadata=meta)
+        self._rebuild()
+
+    def delete_many(self, ids: Sequence[str]) -> int:
+        """Returns how many ids were present (the reference returns None although its
+        callers report the value as a count, rag/admin/manage.py:191-195)."""
+        n = 0
+        for doc_id in ids:
+            n += self._entries.pop(doc_id, None) is not None
+        self._rebuild()
+        return n
+
+    def count(self) -> int:
+        return len(self._entries)
+
+    # ---------- query ----------
+    def _index_for(self, where: Optional[Mapping[str, Any]]) -> Optional[_DeviceIndex]:
+        """The index a search with this filter scores against; None = no candidate."""
+        self._ensure_index()
+        clauses = bm25_clauses(where)
+        if not clauses:
+            return self._full
+        try:
+            key = tuple((k, repr(v)) for k, v in clauses)
+        except Exception:
+            key = None
+        if key is not None and key in self._subsets:
+            self._subsets.move_to_end(key)
+            return self._subsets[key]
+        mask = self._columns.mask(clauses).cpu().numpy().astype(bool)
+        rows = np.nonzero(mask)[0]
+        if rows.size == 0:
+            return None
+        if rows.size == len(self._id_list):
+            return self._full
+        doc_ptr, tokens, ptr = self._dev_tokens
+        sub = _DeviceIndex(rows, doc_ptr, tokens, len(self._vocab), ptr, torch.device(self.device))
+        if key is not None:
+            self._subsets[key] = sub
+            while len(self._subsets) > 8:
+                self._subsets.popitem(last=False)
+        return sub
+
+    def _query_terms(self, query: str) -> List[int]:
+        q_tokens = tokenize(query, lang_hint=detect_lang_tag(query))
+        return [self._vocab.get(t, -1) for t in q_tokens]
+
+    def search_device(self, queries: Sequence[str], where: Optional[Mapping[str, Any]], top_k: int):
+        """Batched device-level search: (index, scores f64 [B,k], local docs i64 [B,k], counts
+        i32 [B]) on the device, not synchronised; None when no document qualifies."""
+        ix = self._index_for(where)
+        if ix is None:
+            return None
+        k = min(int(top_k), _lib.CMR_MAX_K)
+        if k <= 0:
+            raise ValueError("top_k must be positive")
+        qt, qp = lexical.pack_queries([self._query_terms(q) for q in queries])
+        dev = torch.device(self.device)
+        key = (len(queries), k)
+        buf = ix.buffers.get(key)
+        if buf is None:
+            import ctypes as C
+            st = ix.lex.struct()
+            with torch.cuda.device(dev):
+                nbytes = _lib.load().cmr_bm25_workspace_bytes(C.byref(st), len(queries), k)
+            if nbytes == 0:
+                raise ValueError("unsupported bm25 shape: " + _lib.last_error())
+            buf = ix.buffers[key] = ops.TopkBuffers(len(queries), k, nbytes, dev)
+        sc, docs, cnt, _ = ops.bm25_topk(ix.lex, qt.to(dev), qp.to(dev), k, buffers=buf)
+        return ix, sc, docs, cnt
+
+    def search(self, *, query: str, where: Optional[Mapping[str, Any]] = None, top_k: int = 8) -> List[Dict[str, Any]]:
+        """BM25 over the (optionally) filtered subset: id, document, metadata, score (higher
+        is better).  Zero-score documents are ranked too, in insertion order."""
+        if not query.strip() or not self._entries:
+            return []
+        res = self.search_batch(queries=[query], where=where, top_k=top_k)
+        return res[0]
+
+    def search_batch(self, *, queries: Sequence[str], where: Optional[Mapping[str, Any]] = None,
+                     top_k: int = 8) -> List[List[Dict[str, Any]]]:
+        """Extension: many queries in one launch (blank queries give [])."""
+        if not self._entries:
+            return [[] for _ in queries]
+        live = [i for i, q in enumerate(queries) if q.strip()]
+        out: List[List[Dict[str, Any]]] = [[] for _ in queries]
+        if not live:
+            return out
+        got = self.search_device([queries[i] for i in live], where, top_k)
+        if got is None:
+            return out
+        ix, sc, docs, cnt = got
+        sc_h, docs_h, cnt_h = sc.cpu().numpy(), docs.cpu().numpy(), cnt.cpu().numpy()
+        for j, qi in enumerate(live):
+            items = []
+            for r in range(int(cnt_h[j])):
+                e = self._entries[self._id_list[int(ix.rows[int(docs_h[j, r])])]]
+                items.append({"id": e.id, "document": e.text, "metadata": e.metadata, "score": float(sc_h[j, r])})
+            out[qi] = items
+        return out
+
+    # ---------- persistence (same JSONL records as the reference) ----------
+    @property
+    def index_path(self) -> Path:
+        return Path(self.index_dir) / self.index_file
+
+    def save(self) -> None:
+        Path(self.index_dir).mkdir(parents=True, exist_ok=True)
+        with self.index_path.open("w", encoding="utf-8") as f:
+            for e in self._entries.values():
+                f.write(json.dumps({"id": e.id, "text": e.text, "tokens": e.tokens, "metadata": e.metadata},
+                                   ensure_ascii=False) + "\n")
+
+    def load(self) -> None:
+        self._entries.clear()
+        self._vocab = {}
+        if self.index_path.exists():
+            with self.index_path.open("r", encoding="utf-8") as f:
+                for line in f:
+                    if not line.strip():
+                        continue
+                    rec = json.loads(line)
+                    self._entries[rec["id"]] = _Entry(id=rec["id"], text=rec.get("text", ""),
+                                                      tokens=list(rec.get("tokens", [])),
+                                                      metadata=dict(rec.get("metadata", {})))
+        self._rebuild()
+
+    def catalog(self) -> Dict[str, Tuple[str, Dict[str, Any]]]:
+        """id -> (text, metadata): what expand_with_neighbors reads from the JSONL file."""
+        return {e.id: (e.text, dict(e.metadata)) for e in self._entries.values()}
+
+    @classmethod
+    def load_or_create(cls, index_dir: Union[str, Path] = "./indexes/bm25") -> "BM25Store":
+        store = cls(index_dir=Path(index_dir))
+        store.load()
+        return store

@@ -201,6 +201,30 @@ int cmr_hybrid_fuse(const int64_t* vec_ids, const double* vec_sims, const int32_
                     int64_t* out_ids, double* out_fused, double* out_vdist, double* out_bm25,
                     int32_t* out_counts, cmr_stream_t stream);
 
+/* A3 standalone: rrf_fuse over any number of rank lists (rag/retrieval/fusion.py:17-36).
+ *     list_ids [n_lists, max_len] int64 (the caller's integer image of the string ids),
+ *     list_counts [n_lists], weights [n_lists] float64 (device).  Output: the distinct ids in
+ *     first-appearance order (the reference dict's insertion order) with
+ *     score = sum over lists, in list order, of w * (1.0 / (rrf_k + rank)), float64;
+ *     out_ids / out_scores hold up to n_lists * max_len entries, out_count [1].
+ *     n_lists * max_len <= 4096. */
+int cmr_rrf_fuse(const int64_t* list_ids, const int32_t* list_counts, int n_lists, int max_len,
+                 const double* weights, int rrf_k, int64_t* out_ids, double* out_scores,
+                 int32_t* out_count, cmr_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * N1  Metadata `where` filter on the device (ChromaVectorStore.query's where,
+ *     rag/retrieval/vector_chroma.py:45-78,204-253; BM25Store._matches_filter,
+ *     rag/retrieval/bm25.py:79-107).  field_codes [n_fields, n_rows] int32: dictionary code
+ *     of every row's value per field, -1 = field absent.  The filter is a conjunction of
+ *     n_clauses (field, code) equalities; code -1 asks for "absent", a value unknown to the
+ *     dictionary is encoded by the host as -2 (matches nothing).  alive (uint8 [n_rows] or
+ *     NULL) carries tombstones.  out_mask uint8 [n_rows] feeds row_mask of the top-k calls.
+ * ---------------------------------------------------------------------- */
+int cmr_filter_mask(const int32_t* field_codes, int64_t n_rows, int n_fields,
+                    const int32_t* clause_field, const int32_t* clause_code, int n_clauses,
+                    const uint8_t* alive, uint8_t* out_mask, cmr_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * K7  Merge of per-shard top-k lists after the all-gather (multi-GPU; no
  *     reference counterpart).  in_* are [n_parts, n_queries, k]; order is

@@ -1,0 +1,162 @@
+"""GPU parity of the drop-in retrieval classes (classmate_rag_b200.retrieval) against the
+golden vectors produced by the LIVE reference code (tests/golden/make_golden.py):
+BM25Store.search, HybridRetriever.retrieve, rrf_fuse, the filters, neighbor expansion.
+
+The reference's third-party numeric cores were substituted when the vectors were made
+(rank_bm25 -> oracle restatement, Chroma/hnswlib -> exact brute-force cosine); everything
+else in the expected outputs is the reference's own code."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import bits_from_hex, unhex
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+class _Emb:
+    """Embedder stub with the E5 contract: encode_queries(list[str]) -> float32 [B, dim]."""
+
+    def __init__(self):
+        self.vec = None
+
+    def encode_queries(self, texts):
+        return np.stack([self.vec for _ in texts])
+
+
+@pytest.fixture(scope="module")
+def world(golden, tmp_path_factory):
+    from classmate_rag_b200.retrieval import BM25Store, ChromaVectorStore
+    c = golden["corpus"]
+    td = tmp_path_factory.mktemp("dropin")
+    emb_bits = bits_from_hex(c["emb_bits"], (c["n"], c["d"]))
+    emb_f32 = o.bf16_bits_to_f32(emb_bits)
+    store = BM25Store(index_dir=td / "bm25")
+    store.upsert_many(ids=c["ids"], texts=c["docs"], metadatas=c["metas"])
+    vs = ChromaVectorStore(persist_dir=td / "chroma", collection_name="golden")
+    vs.upsert(ids=c["ids"], documents=c["docs"], metadatas=c["metas"], embeddings=emb_f32)
+    return store, vs, c, emb_bits, emb_f32, td
+
+
+def test_bm25store_search_golden(world, golden):
+    store = world[0]
+    for case in golden["bm25_search"]:
+        res = store.search(query=case["query"], where=case["where"], top_k=case["top_k"])
+        assert [[x["id"], x["score"]] for x in res] == [[i, unhex(s)] for i, s in case["out"]], case["query"]
+        for x in res:
+            assert set(x) == {"id", "document", "metadata", "score"} and isinstance(x["score"], float)
+
+
+def test_bm25store_search_batch_equals_single(world, golden):
+    store = world[0]
+    queries = sorted({c["query"] for c in golden["bm25_search"]})
+    for where in (None, {"course": "Math101"}):
+        batch = store.search_batch(queries=queries, where=where, top_k=8)
+        for q, got in zip(queries, batch):
+            assert got == store.search(query=q, where=where, top_k=8)
+
+
+def test_hybrid_retriever_golden(world, golden):
+    from classmate_rag_b200.retrieval import HybridRetriever
+    store, vs, c, emb_bits, emb_f32, _ = world
+    emb = _Emb()
+    for case in golden["retrieve"]:
+        emb.vec = o.bf16_bits_to_f32(bits_from_hex(case["q_bits"], (c["d"],)))
+        hr = HybridRetriever(vector_store=vs, bm25_store=store, embedder=emb, k_vector=8, k_bm25=8,
+                             use_mmr=case["use_mmr"])
+        out = hr.retrieve(question=case["question"], filters=case["filters"], top_k=8, hybrid=case["hybrid"])
+        assert [x["id"] for x in out] == [w["id"] for w in case["out"]], case
+        for x, w in zip(out, case["out"]):
+            assert set(x) == {"id", "document", "metadata", "scores"}
+            s = x["scores"]
+            assert s["fused"] == unhex(w["fused"])                      # RRF: bit-exact
+            assert s["bm25_score"] == unhex(w["bm25_score"])            # BM25: bit-exact
+            wd = unhex(w["vector_distance"])
+            if wd is None:
+                assert s["vector_distance"] is None
+            else:  # same bf16 inputs, float64 sums in a different order than NumPy's matmul
+                assert math.isclose(s["vector_distance"], wd, rel_tol=0, abs_tol=1e-12)
+            i = c["ids"].index(x["id"])
+            assert x["metadata"] == c["metas"][i]
+            assert x["document"] == (c["docs"][i] or (None if s["vector_distance"] is None else c["docs"][i]))
+
+
+def test_rrf_fuse_golden(golden):
+    from classmate_rag_b200.retrieval import rrf_fuse
+    for case in golden["rrf_fuse"]:
+        out = rrf_fuse(rank_lists=case["rank_lists"], weights=case["weights"], rrf_k=case["rrf_k"])
+        assert list(out.items()) == [(i, unhex(s)) for i, s in case["out"]]
+
+
+def test_device_filter_masks_golden(golden):
+    from classmate_rag_b200.retrieval.filters import MetaColumns, bm25_clauses
+    metas = []
+    for case in golden["matches_filter"]:
+        if case["meta"] not in metas:
+            metas.append(case["meta"])
+    mc = MetaColumns(torch.device("cuda"))
+    mc.reset(metas)
+    for case in golden["matches_filter"]:
+        got = mc.mask(bm25_clauses(case["where"])).cpu().numpy()[metas.index(case["meta"])]
+        assert bool(got) == case["out"], case
+
+
+def test_vector_store_behaviour(world, golden):
+    from classmate_rag_b200.retrieval import ChromaVectorStore, build_where_filter
+    store, vs, c, emb_bits, emb_f32, td = world
+    assert vs.count() == c["n"]
+    q = emb_f32[5]
+    res = vs.query(query_embeddings=q, top_k=5, include_embeddings=True)
+    want_ids, want_sc = o.dense_topk(emb_bits[5], emb_bits, 5)
+    assert [r["id"] for r in res] == [c["ids"][i] for i in want_ids]
+    assert [r["distance"] for r in res] == [1.0 - float(s) for s in want_sc]
+    assert res[0]["id"] == c["ids"][5] and np.array_equal(res[0]["embedding"], emb_f32[5])
+    assert set(res[0]) == {"id", "document", "metadata", "distance", "embedding"}
+    # 2-D input: only the first query's hits come back (reference behaviour); batch API returns all
+    two = np.stack([emb_f32[5], emb_f32[9]])
+    assert [r["id"] for r in vs.query(query_embeddings=two, top_k=3)] == [r["id"] for r in res[:3]]
+    both = vs.query_batch(query_embeddings=two, top_k=3)
+    assert len(both) == 2 and both[1][0]["id"] == c["ids"][9]
+    # where filter (Chroma-style) == oracle mask
+    where = build_where_filter({"course": "Phys202", "tags": ["exam"]})
+    keep = np.array([o.chroma_where_matches(m, where) for m in c["metas"]], dtype=np.uint8)
+    got = vs.query(query_embeddings=q, where=where, top_k=6)
+    want_ids, _ = o.dense_topk(emb_bits[5], emb_bits, 6, mask=keep)
+    assert [r["id"] for r in got] == [c["ids"][i] for i in want_ids]
+    assert vs.query(query_embeddings=q, where={"course": "Nope"}, top_k=6) == []
+    # a second handle on the same collection sees the same rows; upsert moves an id to the end
+    vs2 = ChromaVectorStore(persist_dir=td / "chroma", collection_name="golden")
+    assert vs2.count() == c["n"]
+    side = ChromaVectorStore(persist_dir=td / "side", collection_name="t")
+    side.upsert(ids=["a", "b", "c"], documents=["A", "B", "C"], metadatas=[{}, {}, {}], embeddings=emb_f32[:3])
+    side.upsert(ids=["a"], documents=["A2"], metadatas=[{"v": 2}], embeddings=emb_f32[3:4])
+    assert side.count() == 3
+    r = side.query(query_embeddings=emb_f32[3], top_k=3)
+    assert r[0]["id"] == "a" and r[0]["document"] == "A2" and r[0]["metadata"] == {"v": 2}
+    assert side.delete(["b", "zzz"]) == 1 and side.count() == 2
+    assert [x["id"] for x in side.query(query_embeddings=emb_f32[1], top_k=3)] != [] and \
+        "b" not in [x["id"] for x in side.query(query_embeddings=emb_f32[1], top_k=3)]
+    snap = side.persist()
+    assert (snap / "embeddings_bf16.npy").exists()
+    from classmate_rag_b200.retrieval import vector_store as vsm
+    vsm._COLLECTIONS.pop(side._key())
+    again = ChromaVectorStore(persist_dir=td / "side", collection_name="t")
+    assert again.count() == 2 and again.query(query_embeddings=emb_f32[3], top_k=1)[0]["document"] == "A2"
+    again.reset_collection()
+    assert again.count() == 0 and again.query(query_embeddings=emb_f32[3], top_k=1) == []
+
+
+def test_expand_uses_store_catalog(world, golden):
+    from classmate_rag_b200.retrieval import expand as ex
+    store, vs, c = world[0], world[1], world[2]
+    ex.use_catalog(store)
+    try:
+        for case in golden["expand"]:
+            results = [{"id": c["ids"][i], "document": c["docs"][i], "metadata": c["metas"][i]} for i in case["seeds"]]
+            out = ex.expand_with_neighbors(results, radius=case["radius"], max_per_doc=case["max_per_doc"])
+            assert [[x["id"], x["score"]] for x in out] == [[i, unhex(s)] for i, s in case["out"]]
+    finally:
+        ex.use_catalog(None)
