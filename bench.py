@@ -66,15 +66,22 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
-    def start(self):
+    def start(self, settle_s: float = 0.6):
+        """nvidia-smi needs a few hundred ms before its first sample: start early, then
+        mark() the beginning of the region whose samples count."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(settle_s)
         except Exception:
             self.proc = None
+        self.first = 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -90,7 +97,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
@@ -236,8 +243,9 @@ def main():
     dense_ms, lex_ms = [], []
     for s in range(a.warmup):
         eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p)
-    barrier()
     clocks.start()
+    barrier()
+    clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for s in range(a.warmup, n_steps):
@@ -270,13 +278,26 @@ def main():
         hbm_peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s"
-    dense_bytes = (hi - lo) * a.dim * 2  # one scan pass serves the whole batch (<= 32 queries)
-    passes = (a.batch + 31) // 32
+    # the matrix is read once per 128 queries (tcgen05 path, batch > 8) or per 8 (scan path)
+    dense_bytes = (hi - lo) * a.dim * 2
+    passes = (a.batch + 127) // 128 if a.batch > 8 else 1
     achieved = dense_bytes * passes / (dense_avg * 1e-3) / 1e9
+    dense_kernel = ("dense_mma_kernel<MAIN> (tcgen05/TMA; events bracket cmr_dense_topk = 1/16 sample pass + bound + "
+                    "main pass + finalize)" if a.batch > 8 else
+                    "dense_scan_kernel (events bracket cmr_dense_topk = scan + finalize)")
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            t = json.loads(tpath.read_text())
+            key = f"{'dense_mma_main' if a.batch > 8 else 'dense_scan'}:{hi - lo}x{a.dim}"
+            traffic = t.get(key)
+        except Exception:
+            traffic = None
     lex_bytes = float(np.mean(posting_bytes[a.warmup:]))
-    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel (events bracket cmr_dense_topk = scan + finalize)",
+    roofline = {"bound": "hbm", "kernel": dense_kernel,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dense_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dense_bytes,
                 "avg_launch_ms": dense_avg, "share_of_step": dense_avg / ms_per_step,
                 "bm25": {"kernel": "bm25_tile_kernel (+finalize)", "algorithmic_bytes_per_step": lex_bytes,
                          "avg_ms_per_step": lex_avg, "achieved": lex_bytes / (lex_avg * 1e-3) / 1e9, "unit": "GB/s",
@@ -319,8 +340,9 @@ def main():
                "qps_serial": float(1e3 / np.mean(lat)),
                "hbm_frac_at_p50": (hi - lo) * a.dim * 2 / (float(np.percentile(lat, 50)) * 1e-3) / 1e9 / hbm_peak}
 
-    # kernels per step: f32->bf16 is outside the resident loop; scan, finalize, gather, mmr, bm25 tile, bm25 finalize, fuse
-    launches_per_step = 7 + (2 if world > 1 else 0)
+    # kernels per step (resident loop): dense = sample pass, bound, main pass, finalize (tcgen05 path)
+    # or scan, finalize; then gather, mmr, bm25 tile, bm25 finalize, fuse; sharded: + 2 merges
+    launches_per_step = (4 if a.batch > 8 else 2) + 5 + (2 if world > 1 else 0)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic",

@@ -45,7 +45,7 @@ constexpr int MM_B_BYTES = MM_R * MM_K * 2;  // 32 KiB
 constexpr int MM_STAGE_BYTES = MM_A_BYTES + MM_B_BYTES;
 constexpr int MM_THREADS = 192;
 constexpr int MM_SMEM_BYTES = MM_STAGES * MM_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int MM_SAMPLE = 0, MM_MAIN = 1;
+constexpr int MM_SAMPLE = 0, MM_MAIN = 1, MM_NEARDUP = 2;
 constexpr int MM_CAP_PER_KP = 64;    // candidate slots per query = 64 * KP
 constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile
 constexpr int MM_MAX_GROUPS = 49152; // threshold kernel keeps the group maxima in shared memory
@@ -131,19 +131,78 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------
-// MODE == MM_SAMPLE: work item w is row tile w * tile_stride (always a full tile); the
-//   epilogue writes group maxima: gmax[(w * gpt + g) * gstride + query], gpt = 8 (groups of
-//   32 rows) or 1 (the whole tile).
-// MODE == MM_MAIN:   work item w is row tile w; scores >= thr[query] are appended to
-//   cand[query * cap + atomicAdd(cnt[query])] as (orderable fp32 score, ~row) keys.
+// Work enumeration shared by the three warp roles.  An item is one (A block of 128 rows of
+// the left operand, B tile of 256 rows of the right operand) pair = one TMEM accumulator.
+//   MM_SAMPLE / MM_MAIN  left = queries, right = matrix.  outer = row tile (CTA c owns tiles
+//       c, c+grid, ...; SAMPLE: every `stride`-th full tile), inner = query block, so a row
+//       tile is fetched from HBM once and re-read from L2 for further query blocks.
+//   MM_NEARDUP           left = right = matrix, lower triangle only: outer = block of 128
+//       rows i (blocks begin, begin+step, ... of this rank, dealt round-robin to the CTAs),
+//       inner = every 256-row tile that holds some j < i.
 // ---------------------------------------------------------------------------------------
+struct MmParams {
+  int n_left;          // rows of the left operand (queries; NEARDUP: matrix rows)
+  long long n_rows;    // rows of the right operand
+  int n_chunks;        // K chunks of 64 columns
+  int n_outer;         // outer items in total
+  int n_inner;         // SAMPLE/MAIN: query blocks
+  int stride;          // SAMPLE: tile stride; NEARDUP: block step of this rank
+  int begin;           // NEARDUP: first block of this rank
+  u32 tx_bytes;        // bytes per ring stage (both TMA boxes)
+  int rows_evict_first;
+  // SAMPLE / MAIN
+  const float* thr;
+  float* gmax;
+  int gstride, gpt;
+  u64* cand;
+  int* cnt;
+  int cap;
+  // NEARDUP
+  float nd_bound;      // emit pairs with fp32 score >= nd_bound (= threshold - error bound)
+  u64* edges;          // (i << 32) | j
+  unsigned long long* edge_count;
+  unsigned long long edge_cap;
+};
+
+template <int MODE>
+struct MmIter {
+  const MmParams& p;
+  int outer_idx, outer, inner, inner_end;
+  __device__ __forceinline__ MmIter(const MmParams& pp) : p(pp), outer_idx((int)blockIdx.x), inner(0), inner_end(0) {
+    load_outer();
+  }
+  __device__ __forceinline__ void load_outer() {
+    if (outer_idx >= p.n_outer) return;
+    if (MODE == MM_NEARDUP) {
+      outer = p.begin + outer_idx * p.stride;                  // block of rows i
+      inner_end = (outer * MM_Q + MM_Q - 2) / MM_R + 1;        // tiles holding some j <= i_max - 1
+    } else {
+      outer = outer_idx * (MODE == MM_SAMPLE ? p.stride : 1);  // row tile
+      inner_end = p.n_inner;
+    }
+    inner = 0;
+  }
+  __device__ __forceinline__ bool valid() const { return outer_idx < p.n_outer; }
+  __device__ __forceinline__ void advance() {
+    if (++inner >= inner_end) {
+      outer_idx += (int)gridDim.x;
+      load_outer();
+    }
+  }
+  // first row of the left (A) and right (B) boxes of the current item
+  __device__ __forceinline__ int a_row0() const { return (MODE == MM_NEARDUP ? outer : inner) * MM_Q; }
+  __device__ __forceinline__ int b_row0() const { return (MODE == MM_NEARDUP ? inner : outer) * MM_R; }
+};
+
+// MODE == MM_SAMPLE: the epilogue writes group maxima gmax[(item * gpt + g) * gstride + query],
+//   gpt = 8 (groups of 32 rows) or 1 (the whole tile); sampled tiles are always full tiles.
+// MODE == MM_MAIN:   scores >= thr[query] are appended to cand[query * cap + atomicAdd(cnt[query])]
+//   as (orderable fp32 score, ~row) keys.
+// MODE == MM_NEARDUP: pairs (i, j < i) with score >= nd_bound are appended to `edges`.
 template <int MODE>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_rows,
-                 int n_queries, long long n_rows, int n_chunks, int n_mb, int n_work, int tile_stride,
-                 u32 tx_bytes, int rows_evict_first, const float* __restrict__ thr,
-                 float* __restrict__ gmax, int gstride, int gpt, u64* __restrict__ cand,
-                 int* __restrict__ cnt, int cap) {
+                 const MmParams p) {
   extern __shared__ unsigned char smem_raw[];
   const u32 raw = smem_u32(smem_raw);
   const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -178,20 +237,19 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const unsigned long long hint_rows = rows_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+      const unsigned long long hint_rows = p.rows_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+      const unsigned long long hint_left = MODE == MM_NEARDUP ? TMA_EVICT_NORMAL : TMA_EVICT_LAST;
       u32 it = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int row0 = w * tile_stride * MM_R;
-        for (int mb = 0; mb < n_mb; ++mb) {
-          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-            const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
-            mbar_wait(bars + 32 + 8 * s, ph ^ 1u);
-            const u32 full = bars + 8 * s;
-            mbar_expect_tx(full, tx_bytes);
-            const u32 sa = base + s * MM_STAGE_BYTES;
-            tma_load_2d(sa, &tm_q, full, kc * MM_K, mb * MM_Q, TMA_EVICT_LAST);
-            tma_load_2d(sa + MM_A_BYTES, &tm_rows, full, kc * MM_K, row0, hint_rows);
-          }
+      for (MmIter<MODE> w(p); w.valid(); w.advance()) {
+        const int a0 = w.a_row0(), b0 = w.b_row0();
+        for (int kc = 0; kc < p.n_chunks; ++kc, ++it) {
+          const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+          mbar_wait(bars + 32 + 8 * s, ph ^ 1u);
+          const u32 full = bars + 8 * s;
+          mbar_expect_tx(full, p.tx_bytes);
+          const u32 sa = base + s * MM_STAGE_BYTES;
+          tma_load_2d(sa, &tm_q, full, kc * MM_K, a0, hint_left);
+          tma_load_2d(sa + MM_A_BYTES, &tm_rows, full, kc * MM_K, b0, hint_rows);
         }
       }
     }
@@ -200,26 +258,24 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (lane == 0) {
       // ===== MMA issuer =====
       u32 it = 0, ai = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        for (int mb = 0; mb < n_mb; ++mb, ++ai) {
-          const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
-          mbar_wait(bars + 80 + 8 * ab, aph ^ 1u);  // epilogue has drained this accumulator
+      for (MmIter<MODE> w(p); w.valid(); w.advance(), ++ai) {
+        const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
+        mbar_wait(bars + 80 + 8 * ab, aph ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const u32 d_tmem = tmem_base + ab * MM_R;
+        for (int kc = 0; kc < p.n_chunks; ++kc, ++it) {
+          const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+          mbar_wait(bars + 8 * s, ph);  // TMA bytes have landed
           tc_fence_after();
-          const u32 d_tmem = tmem_base + ab * MM_R;
-          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-            const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
-            mbar_wait(bars + 8 * s, ph);  // TMA bytes have landed
-            tc_fence_after();
-            const u32 sa = base + s * MM_STAGE_BYTES;
-            const unsigned long long da = umma_desc_sw128(sa);
-            const unsigned long long db = umma_desc_sw128(sa + MM_A_BYTES);
+          const u32 sa = base + s * MM_STAGE_BYTES;
+          const unsigned long long da = umma_desc_sw128(sa);
+          const unsigned long long db = umma_desc_sw128(sa + MM_A_BYTES);
 #pragma unroll
-            for (int k = 0; k < MM_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
-              tc_mma_bf16(d_tmem, da + 2ull * k, db + 2ull * k, MM_IDESC, (kc | k) != 0);
-            tc_commit(bars + 32 + 8 * s);  // frees the ring slot when these MMAs retire
-          }
-          tc_commit(bars + 64 + 8 * ab);   // accumulator complete
+          for (int k = 0; k < MM_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
+            tc_mma_bf16(d_tmem, da + 2ull * k, db + 2ull * k, MM_IDESC, (kc | k) != 0);
+          tc_commit(bars + 32 + 8 * s);  // frees the ring slot when these MMAs retire
         }
+        tc_commit(bars + 64 + 8 * ab);   // accumulator complete
       }
     }
     __syncwarp();
@@ -228,51 +284,55 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int lg = warp & 3;
     const int lane_row = lg * 32 + lane;
     u32 ai = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const long long row0 = (long long)w * tile_stride * MM_R;
-      for (int mb = 0; mb < n_mb; ++mb, ++ai) {
-        const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
-        const int qi = mb * MM_Q + lane_row;
-        const bool q_ok = qi < n_queries;
-        float bound = INFINITY;
-        if (MODE == MM_MAIN && q_ok) bound = thr[qi];
-        mbar_wait(bars + 64 + 8 * ab, aph);
-        tc_fence_after();
-        const u32 taddr = tmem_base + ((u32)(lg * 32) << 16) + ab * MM_R;
-        float tile_max = -INFINITY;
+    for (MmIter<MODE> w(p); w.valid(); w.advance(), ++ai) {
+      const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
+      const long long row0 = w.b_row0();
+      const int qi = w.a_row0() + lane_row;     // query (NEARDUP: row i) of this thread
+      const bool q_ok = qi < p.n_left;
+      float bound = INFINITY;
+      if (MODE == MM_MAIN && q_ok) bound = p.thr[qi];
+      if (MODE == MM_NEARDUP && q_ok) bound = p.nd_bound;
+      mbar_wait(bars + 64 + 8 * ab, aph);
+      tc_fence_after();
+      const u32 taddr = tmem_base + ((u32)(lg * 32) << 16) + ab * MM_R;
+      float tile_max = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < MM_R / 32; ++c) {
-          __syncwarp();
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          float m = v[0];
+      for (int c = 0; c < MM_R / 32; ++c) {
+        __syncwarp();
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        float m = v[0];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-          if (MODE == MM_SAMPLE) {
-            if (gpt == 8) {
-              if (q_ok) gmax[((size_t)w * 8 + c) * gstride + qi] = m;
-            } else {
-              tile_max = fmaxf(tile_max, m);
-            }
-          } else if (q_ok && m >= bound) {
-            // rare: about 16*KP rows per query over the whole scan
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        if (MODE == MM_SAMPLE) {
+          if (p.gpt == 8) {
+            if (q_ok) p.gmax[((size_t)w.outer_idx * 8 + c) * p.gstride + qi] = m;
+          } else {
+            tile_max = fmaxf(tile_max, m);
+          }
+        } else if (q_ok && m >= bound) {
+          // rare: about 16*KP rows per query over the whole scan (MAIN); near-duplicate pairs (NEARDUP)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= bound) {
-                const long long row = row0 + c * 32 + j;
-                if (row < n_rows) {
-                  const int slot = atomicAdd(&cnt[qi], 1);
-                  if (slot < cap) cand[(size_t)qi * cap + slot] = make_key(v[j], (u32)row);
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] >= bound) {
+              const long long row = row0 + c * 32 + j;
+              if (MODE == MM_MAIN) {
+                if (row < p.n_rows) {
+                  const int slot = atomicAdd(&p.cnt[qi], 1);
+                  if (slot < p.cap) p.cand[(size_t)qi * p.cap + slot] = make_key(v[j], (u32)row);
                 }
+              } else if (row < (long long)qi) {
+                const unsigned long long slot = atomicAdd(p.edge_count, 1ull);
+                if (slot < p.edge_cap) p.edges[slot] = ((u64)(u32)qi << 32) | (u64)(u32)row;
               }
             }
           }
         }
-        if (MODE == MM_SAMPLE && gpt != 8 && q_ok) gmax[(size_t)w * gstride + qi] = tile_max;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 80 + 8 * ab);
       }
+      if (MODE == MM_SAMPLE && p.gpt != 8 && q_ok) p.gmax[(size_t)w.outer_idx * p.gstride + qi] = tile_max;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 80 + 8 * ab);
     }
   }
 
@@ -455,6 +515,25 @@ static int launch_finalize_cand(const DenseArgs& a, const MmaPlan& p, const u64*
   return CMR_OK;
 }
 
+// one-time (per device) opt-in of the GEMM kernels to their dynamic shared memory
+static int mma_opt_in() {
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel<MM_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_mma_kernel<MM_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_mma_kernel<MM_NEARDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_thresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_MAX_GROUPS * 4);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_mma)");
+    attr_dev_mask |= (1 << dev);
+  }
+  return CMR_OK;
+}
+
 int dense_mma_topk(const DenseArgs& a) {
   MmaPlan p;
   mma_plan(a.n_rows, a.dim, a.n_queries, a.k, &p);
@@ -465,18 +544,7 @@ int dense_mma_topk(const DenseArgs& a) {
   CMR_CHECK_ARG(((uintptr_t)a.workspace % 16) == 0, "workspace must be 16-byte aligned");
   const int sms = sm_count();
   if (sms <= 0) return CMR_ECUDA;
-  static int attr_dev_mask = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!(attr_dev_mask & (1 << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel<MM_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_mma_kernel<MM_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_thresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_MAX_GROUPS * 4);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_mma)");
-    attr_dev_mask |= (1 << dev);
-  }
+  { const int rc_attr = mma_opt_in(); if (rc_attr != CMR_OK) return rc_attr; }
   alignas(64) CUtensorMap tm_q, tm_rows;
   int rc = make_tmap(&tm_q, a.queries, a.n_queries, a.dim, p.q_box_rows);
   if (rc != CMR_OK) return rc;
@@ -490,19 +558,34 @@ int dense_mma_topk(const DenseArgs& a) {
   float* gmax = (float*)(ws + p.off_gmax);
   const u32 tx_bytes = (u32)(p.q_box_rows * MM_K * 2 + MM_B_BYTES);
 
+  MmParams kp{};
+  kp.n_left = a.n_queries;
+  kp.n_rows = a.n_rows;
+  kp.n_chunks = p.n_chunks;
+  kp.n_inner = p.n_mb;
+  kp.tx_bytes = tx_bytes;
+  kp.thr = thr;
+  kp.gmax = gmax;
+  kp.gstride = p.bpad;
+  kp.gpt = p.gpt;
+  kp.cand = cand;
+  kp.cnt = cnt;
+  kp.cap = p.cap;
   if (p.n_sample > 0) {
     const int grid = p.n_sample < sms ? p.n_sample : sms;
-    dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(
-        tm_q, tm_rows, a.n_queries, a.n_rows, p.n_chunks, p.n_mb, p.n_sample, p.sample_stride, tx_bytes,
-        /*rows_evict_first=*/0, thr, gmax, p.bpad, p.gpt, cand, cnt, p.cap);
+    kp.n_outer = p.n_sample;
+    kp.stride = p.sample_stride;
+    kp.rows_evict_first = 0;
+    dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(tm_q, tm_rows, kp);
   }
   dense_thresh_kernel<<<a.n_queries, 256, (size_t)(p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
       gmax, p.n_groups, p.bpad, p.kp, thr, cnt);
   {
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    dense_mma_kernel<MM_MAIN><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(
-        tm_q, tm_rows, a.n_queries, a.n_rows, p.n_chunks, p.n_mb, p.n_tiles, 1, tx_bytes,
-        /*rows_evict_first=*/p.n_mb == 1, thr, gmax, p.bpad, p.gpt, cand, cnt, p.cap);
+    kp.n_outer = p.n_tiles;
+    kp.stride = 1;
+    kp.rows_evict_first = p.n_mb == 1;
+    dense_mma_kernel<MM_MAIN><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(tm_q, tm_rows, kp);
   }
   switch (p.kpl) {
     case 1: rc = launch_finalize_cand<1>(a, p, cand, cnt); break;
@@ -514,4 +597,132 @@ int dense_mma_topk(const DenseArgs& a) {
   return CMR_OK;
 }
 
+// ---- A9 / K6: near-duplicate filter ---------------------------------------------------------
+// (extension; greedy keep-first rule of rag/utils/dedup.py:40-55 with its '>=' comparison,
+//  hook rag/admin/backup.py:226-233)
+//
+// 1. dense_mma_kernel<MM_NEARDUP>: C . C^T on the tensor cores over the lower triangle, pairs
+//    (i, j < i) with fp32 score >= threshold - error bound go to the edge buffer.
+// 2. neardup_rescore_kernel: one warp per candidate pair recomputes the exact float64 dot
+//    (pinned order) and keeps the pair iff exact >= threshold; survivors are compacted.
+// 3. the caller sorts the surviving edges by (i, j) (they are 64-bit keys i << 32 | j).
+// 4. neardup_resolve_kernel: keep[i] = no edge (i, j) with keep[j]; rows in ascending order, one
+//    warp, lanes share the edges of a row.
+
+__global__ void __launch_bounds__(256)
+neardup_rescore_kernel(const uint16_t* __restrict__ emb, int dim, const u64* __restrict__ edges,
+                       unsigned long long n_edges, double threshold, u64* __restrict__ out_edges,
+                       unsigned long long* __restrict__ out_count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long e = warp0; e < n_edges; e += n_warps) {
+    const u64 key = edges[e];
+    const u32 i = (u32)(key >> 32), j = (u32)key;
+    const double s = warp_exact_dot(emb + (size_t)i * dim, emb + (size_t)j * dim, dim, lane);
+    if (lane == 0 && s >= threshold) out_edges[atomicAdd(out_count, 1ull)] = key;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+neardup_resolve_kernel(const u64* __restrict__ sorted_edges, unsigned long long n_edges, long long n_rows,
+                       uint8_t* __restrict__ keep) {
+  const int lane = threadIdx.x;
+  volatile uint8_t* vkeep = keep;  // rows decided earlier in this loop are read back
+  for (long long r = lane; r < n_rows; r += 32) keep[r] = 1;
+  __syncwarp();
+  unsigned long long e = 0;
+  while (e < n_edges) {
+    const u32 i = (u32)(sorted_edges[e] >> 32);
+    bool dup = false;
+    unsigned long long e2 = e;
+    // edges of row i are contiguous; every j < i is already final
+    for (;;) {
+      const unsigned long long idx = e2 + lane;
+      bool mine = false, same = false;
+      if (idx < n_edges) {
+        const u64 key = sorted_edges[idx];
+        same = (u32)(key >> 32) == i;
+        if (same) mine = vkeep[(u32)key] != 0;
+      }
+      dup |= __any_sync(0xFFFFFFFFu, mine);
+      const unsigned ok = __ballot_sync(0xFFFFFFFFu, same);
+      e2 += __popc(ok);
+      if (ok != 0xFFFFFFFFu) break;
+    }
+    if (lane == 0 && dup) vkeep[i] = 0;
+    __syncwarp();
+    __threadfence_block();
+    e = e2;
+  }
+}
+
 }  // namespace cmr
+
+using namespace cmr;
+
+extern "C" int cmr_neardup_edges(const uint16_t* emb, int64_t n_rows, int dim, float bound, int block_begin,
+                                 int block_step, uint64_t* out_edges, uint64_t edge_cap, uint64_t* out_count,
+                                 cmr_stream_t stream) {
+  CMR_CHECK_ARG(emb && out_edges && out_count, "null pointer argument");
+  CMR_CHECK_ARG(n_rows >= 2 && n_rows < 0x7FFFFF00ll, "n_rows %lld out of range", (long long)n_rows);
+  CMR_CHECK_ARG(dim >= MM_K && dim % 8 == 0 && dim <= 2048, "dim %d must be a multiple of 8 in [64, 2048]", dim);
+  CMR_CHECK_ARG(block_begin >= 0 && block_step >= 1, "bad block range");
+  CMR_CHECK_ARG(((uintptr_t)emb % 16) == 0, "emb must be 16-byte aligned");
+  const int sms = sm_count();
+  if (sms <= 0) return CMR_ECUDA;
+  int rc = mma_opt_in();
+  if (rc != CMR_OK) return rc;
+  alignas(64) CUtensorMap tm_left, tm_right;
+  rc = make_tmap(&tm_left, emb, n_rows, dim, MM_Q);
+  if (rc != CMR_OK) return rc;
+  rc = make_tmap(&tm_right, emb, n_rows, dim, MM_R);
+  if (rc != CMR_OK) return rc;
+  const int n_blocks = (int)((n_rows + MM_Q - 1) / MM_Q);
+  const int mine = block_begin < n_blocks ? (n_blocks - block_begin + block_step - 1) / block_step : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CMR_CUDA(cudaMemsetAsync(out_count, 0, sizeof(uint64_t), st));
+  if (mine == 0) return CMR_OK;
+  MmParams kp{};
+  kp.n_left = (int)n_rows;
+  kp.n_rows = n_rows;
+  kp.n_chunks = (dim + MM_K - 1) / MM_K;
+  kp.n_outer = mine;
+  kp.n_inner = 0;
+  kp.stride = block_step;
+  kp.begin = block_begin;
+  kp.tx_bytes = (u32)(MM_A_BYTES + MM_B_BYTES);
+  kp.rows_evict_first = 0;
+  kp.nd_bound = bound;
+  kp.edges = (u64*)out_edges;
+  kp.edge_count = (unsigned long long*)out_count;
+  kp.edge_cap = edge_cap;
+  const int grid = mine < sms ? mine : sms;
+  dense_mma_kernel<MM_NEARDUP><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(tm_left, tm_right, kp);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_neardup_rescore(const uint16_t* emb, int dim, const uint64_t* edges, uint64_t n_edges,
+                                   double threshold, uint64_t* out_edges, uint64_t* out_count, cmr_stream_t stream) {
+  CMR_CHECK_ARG(emb && out_count && (n_edges == 0 || (edges && out_edges)), "null pointer argument");
+  CMR_CHECK_ARG(dim > 0 && dim % 8 == 0, "dim must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  CMR_CUDA(cudaMemsetAsync(out_count, 0, sizeof(uint64_t), st));
+  if (n_edges == 0) return CMR_OK;
+  unsigned long long blocks = (n_edges + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  neardup_rescore_kernel<<<(int)blocks, 256, 0, st>>>(emb, dim, (const u64*)edges, n_edges, threshold,
+                                                      (u64*)out_edges, (unsigned long long*)out_count);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_neardup_resolve(const uint64_t* sorted_edges, uint64_t n_edges, int64_t n_rows, uint8_t* keep,
+                                   cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || keep) && (n_edges == 0 || sorted_edges), "bad arguments");
+  if (n_rows == 0) return CMR_OK;
+  neardup_resolve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const u64*)sorted_edges, n_edges, n_rows, keep);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}

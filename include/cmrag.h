@@ -234,6 +234,31 @@ int cmr_topk_merge(const double* in_scores, const int64_t* in_ids, const int32_t
                    int n_parts, int n_queries, int k, double* out_scores, int64_t* out_ids,
                    int32_t* out_counts, cmr_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * A9 / K6  Near-duplicate cosine filter over the embedding matrix (extension used by
+ *     `rag rebuild`; greedy keep-first rule of rag/utils/dedup.py:40-55: row i is kept iff
+ *     no previously KEPT row j < i has q.c >= threshold; hook rag/admin/backup.py:226-233).
+ *
+ *  cmr_neardup_edges    C . C^T on the tcgen05 tensor cores over the lower triangle (the GEMM
+ *                       pipeline of CMR_DENSE_MMA with a threshold epilogue).  Pairs (i, j < i)
+ *                       whose fp32 score is >= bound (caller: threshold - error bound) are
+ *                       appended to out_edges as (i << 32 | j).  The 128-row blocks
+ *                       block_begin, block_begin + block_step, ... are this call's share
+ *                       (one call with (0, 1) on a single GPU; rank r of G uses (r, G)).
+ *                       out_count may exceed edge_cap: the caller then retries with more room.
+ *  cmr_neardup_rescore  exact float64 dot (pinned order) of every candidate pair; pairs with
+ *                       exact >= threshold are compacted into out_edges (unordered).
+ *  cmr_neardup_resolve  sorted_edges: the surviving keys in ascending order (all shards
+ *                       merged).  keep[i] = 1 iff no edge (i, j) has keep[j] = 1.
+ * ---------------------------------------------------------------------- */
+int cmr_neardup_edges(const uint16_t* emb, int64_t n_rows, int dim, float bound, int block_begin,
+                      int block_step, uint64_t* out_edges, uint64_t edge_cap, uint64_t* out_count,
+                      cmr_stream_t stream);
+int cmr_neardup_rescore(const uint16_t* emb, int dim, const uint64_t* edges, uint64_t n_edges,
+                        double threshold, uint64_t* out_edges, uint64_t* out_count, cmr_stream_t stream);
+int cmr_neardup_resolve(const uint64_t* sorted_edges, uint64_t n_edges, int64_t n_rows, uint8_t* keep,
+                        cmr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
