@@ -360,9 +360,18 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured CUDA graphs hold NCCL kernels of this communicator; tearing the
+        # process group down under them can block forever.  Drop the graphs, drain the
+        # device, and leave without destroy_process_group (exit code 0 on every rank).
+        del gs, g1
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

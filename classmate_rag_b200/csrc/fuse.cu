@@ -244,6 +244,152 @@ topk_merge_kernel(const double* __restrict__ in_scores, const long long* __restr
   if (tid == 0) out_counts[qi] = n_out;
 }
 
+// ---- K7, single exchange ------------------------------------------------------------------
+// On a row-sharded corpus a step needs the other shards' dense pool (scores, ids AND the
+// embedding rows the MMR step reads) and their BM25 lists.  shard_pack_kernel writes all of it
+// into one message per rank, so the step has ONE collective (an all-gather of the messages);
+// shard_merge_kernel then merges the G messages per query.  Message of one query (bytes):
+//   [dense scores f64 x pool][dense ids i64 x pool][bm scores f64 x kb][bm ids i64 x kb]
+//   [int32 x 4: dense count, dense flag, bm count, 0][rows bf16 x pool x dim]
+__host__ __device__ inline size_t shard_msg_bytes(int pool, int kb, int dim) {
+  return (size_t)16 * pool + (size_t)16 * kb + 16 + (size_t)2 * pool * dim;
+}
+
+constexpr int SHARD_THREADS = 256;
+
+__global__ void __launch_bounds__(SHARD_THREADS)
+shard_pack_kernel(const double* __restrict__ d_scores, const long long* __restrict__ d_ids,
+                  const int* __restrict__ d_counts, const int* __restrict__ d_flags, int pool,
+                  const double* __restrict__ b_scores, const long long* __restrict__ b_ids,
+                  const int* __restrict__ b_counts, int kb, const uint4* __restrict__ emb, long long n_rows,
+                  int dim, long long row_offset, unsigned char* __restrict__ msg) {
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const size_t mb = shard_msg_bytes(pool, kb, dim);
+  unsigned char* m = msg + (size_t)qi * mb;
+  double* ms = reinterpret_cast<double*>(m);
+  long long* mi = reinterpret_cast<long long*>(m + (size_t)8 * pool);
+  double* bs = reinterpret_cast<double*>(m + (size_t)16 * pool);
+  long long* bi = reinterpret_cast<long long*>(m + (size_t)16 * pool + (size_t)8 * kb);
+  int* hdr = reinterpret_cast<int*>(m + (size_t)16 * pool + (size_t)16 * kb);
+  uint4* rows = reinterpret_cast<uint4*>(m + (size_t)16 * pool + (size_t)16 * kb + 16);
+  for (int i = tid; i < pool; i += SHARD_THREADS) {
+    ms[i] = d_scores[(size_t)qi * pool + i];
+    mi[i] = d_ids[(size_t)qi * pool + i];
+  }
+  for (int i = tid; i < kb; i += SHARD_THREADS) {
+    bs[i] = b_scores[(size_t)qi * kb + i];
+    bi[i] = b_ids[(size_t)qi * kb + i];
+  }
+  if (tid == 0) {
+    hdr[0] = d_counts[qi];
+    hdr[1] = d_flags != nullptr ? d_flags[qi] : 0;
+    hdr[2] = kb > 0 ? b_counts[qi] : 0;
+    hdr[3] = 0;
+  }
+  if (dim > 0) {
+    const int dim_vec = dim / 8;
+    const int cnt = d_counts[qi];
+    for (int e = tid; e < pool * dim_vec; e += SHARD_THREADS) {
+      const int r = e / dim_vec, v = e - r * dim_vec;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (r < cnt) {
+        const long long local = d_ids[(size_t)qi * pool + r] - row_offset;
+        if (local >= 0 && local < n_rows) val = emb[(size_t)local * dim_vec + v];
+      }
+      rows[e] = val;
+    }
+  }
+}
+
+// One CTA per query over the gathered messages [G][B][msg].  Ranking by counting over the
+// G*pool (G*kb) entries with the total order (score desc, id asc): identical for any G.
+__global__ void __launch_bounds__(SHARD_THREADS)
+shard_merge_kernel(const unsigned char* __restrict__ gathered, int n_parts, int n_queries, int pool, int kb,
+                   int dim, double* __restrict__ d_scores, long long* __restrict__ d_ids,
+                   int* __restrict__ d_counts, int* __restrict__ d_flags, uint4* __restrict__ d_rows,
+                   double* __restrict__ b_scores, long long* __restrict__ b_ids, int* __restrict__ b_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_d = n_parts * pool, n_b = n_parts * kb;
+  double* s_s = reinterpret_cast<double*>(smem_raw);        // [max(n_d, n_b)]
+  long long* s_i = reinterpret_cast<long long*>(s_s + (n_d > n_b ? n_d : n_b));
+  int* s_src = reinterpret_cast<int*>(s_i + (n_d > n_b ? n_d : n_b));  // [pool] entry feeding each output slot
+  __shared__ int s_total, s_flag;
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const size_t mb = shard_msg_bytes(pool, kb, dim);
+  auto msg_of = [&](int g) { return gathered + ((size_t)g * n_queries + qi) * mb; };
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int k = pass == 0 ? pool : kb;
+    if (k == 0) continue;
+    const int n = n_parts * k;
+    if (tid == 0) {
+      s_total = 0;
+      s_flag = 0;
+    }
+    for (int i = tid; i < pool; i += SHARD_THREADS) s_src[i] = -1;
+    __syncthreads();
+    for (int e = tid; e < n; e += SHARD_THREADS) {
+      const int g = e / k, r = e - g * k;
+      const unsigned char* m = msg_of(g);
+      const int* hdr = reinterpret_cast<const int*>(m + (size_t)16 * pool + (size_t)16 * kb);
+      const double* sc = reinterpret_cast<const double*>(m + (pass == 0 ? 0 : (size_t)16 * pool));
+      const long long* id = reinterpret_cast<const long long*>(m + (pass == 0 ? (size_t)8 * pool
+                                                                                : (size_t)16 * pool + (size_t)8 * kb));
+      const int cnt = hdr[pass == 0 ? 0 : 2];
+      const bool valid = r < cnt && id[r] >= 0;
+      s_s[e] = valid ? sc[r] : 0.0;
+      s_i[e] = valid ? id[r] : -1;
+      if (valid) atomicAdd(&s_total, 1);
+      if (pass == 0 && r == 0 && hdr[1]) atomicOr(&s_flag, hdr[1]);
+    }
+    __syncthreads();
+    const int n_out = s_total < k ? s_total : k;
+    double* o_s = pass == 0 ? d_scores : b_scores;
+    long long* o_i = pass == 0 ? d_ids : b_ids;
+    for (int e = tid; e < n; e += SHARD_THREADS) {
+      const long long id = s_i[e];
+      if (id < 0) continue;
+      const double sv = s_s[e];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const long long idj = s_i[j];
+        if (idj < 0) continue;
+        const double sj = s_s[j];
+        rank += (sj > sv) || (sj == sv && idj < id);
+      }
+      if (rank < n_out) {
+        o_s[(size_t)qi * k + rank] = sv;
+        o_i[(size_t)qi * k + rank] = id;
+        if (pass == 0) s_src[rank] = e;
+      }
+    }
+    for (int i = n_out + tid; i < k; i += SHARD_THREADS) {
+      o_s[(size_t)qi * k + i] = 0.0;
+      o_i[(size_t)qi * k + i] = -1;
+    }
+    if (tid == 0) {
+      (pass == 0 ? d_counts : b_counts)[qi] = n_out;
+      if (pass == 0) d_flags[qi] = s_flag;
+    }
+    __syncthreads();
+    if (pass == 0 && dim > 0 && d_rows != nullptr) {
+      const int dim_vec = dim / 8;
+      for (int e = tid; e < pool * dim_vec; e += SHARD_THREADS) {
+        const int r = e / dim_vec, v = e - r * dim_vec;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        const int src = s_src[r];
+        if (src >= 0) {
+          const int g = src / pool, rr = src - g * pool;
+          const uint4* rows = reinterpret_cast<const uint4*>(msg_of(g) + (size_t)16 * pool + (size_t)16 * kb + 16);
+          val = rows[(size_t)rr * dim_vec + v];
+        }
+        d_rows[((size_t)qi * pool + r) * dim_vec + v] = val;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // A3 standalone: rrf_fuse over any number of rank lists (rag/retrieval/fusion.py:17-36).
 // One CTA.  Thread i owns entry i of the concatenated lists; an entry that is the first
 // occurrence of its id walks every list in order and adds w * (1.0 / (rrf_k + rank)) exactly
@@ -417,6 +563,44 @@ extern "C" int cmr_filter_mask(const int32_t* field_codes, int64_t n_rows, int n
   if (blocks > 148 * 8) blocks = 148 * 8;
   filter_mask_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(field_codes, n_rows, clause_field, clause_code,
                                                                     n_clauses, alive, out_mask);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" size_t cmr_shard_msg_bytes(int pool, int kb, int dim) {
+  if (pool < 0 || kb < 0 || dim < 0 || dim % 8 != 0) return 0;
+  return shard_msg_bytes(pool, kb, dim);
+}
+
+extern "C" int cmr_shard_pack(const double* dense_scores, const int64_t* dense_ids, const int32_t* dense_counts,
+                              const int32_t* dense_flags, int pool, const double* bm_scores, const int64_t* bm_ids,
+                              const int32_t* bm_counts, int kb, const uint16_t* emb, int64_t n_rows, int dim,
+                              int64_t row_offset, int n_queries, void* msg, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
+  CMR_CHECK_ARG(dense_scores && dense_ids && dense_counts && msg, "null pointer argument");
+  CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 list");
+  CMR_CHECK_ARG(dim == 0 || n_rows == 0 || emb, "null embedding matrix");
+  CMR_CHECK_ARG(((uintptr_t)msg % 16) == 0, "message buffer must be 16-byte aligned");
+  shard_pack_kernel<<<n_queries, SHARD_THREADS, 0, (cudaStream_t)stream>>>(
+      dense_scores, (const long long*)dense_ids, dense_counts, dense_flags, pool, bm_scores, (const long long*)bm_ids,
+      bm_counts, kb, reinterpret_cast<const uint4*>(emb), n_rows, dim, row_offset, (unsigned char*)msg);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_shard_merge(const void* gathered, int n_parts, int n_queries, int pool, int kb, int dim,
+                               double* dense_scores, int64_t* dense_ids, int32_t* dense_counts, int32_t* dense_flags,
+                               uint16_t* dense_rows, double* bm_scores, int64_t* bm_ids, int32_t* bm_counts,
+                               cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_parts >= 1 && n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
+  CMR_CHECK_ARG(gathered && dense_scores && dense_ids && dense_counts && dense_flags, "null pointer argument");
+  CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 output");
+  const int n = n_parts * (pool > kb ? pool : kb);
+  const size_t smem = (size_t)n * 16 + (size_t)pool * 4 + 16;
+  CMR_CHECK_ARG(smem <= 48 * 1024, "too many shards x list entries for one merge (%d)", n);
+  shard_merge_kernel<<<n_queries, SHARD_THREADS, smem, (cudaStream_t)stream>>>(
+      (const unsigned char*)gathered, n_parts, n_queries, pool, kb, dim, dense_scores, (long long*)dense_ids,
+      dense_counts, dense_flags, reinterpret_cast<uint4*>(dense_rows), bm_scores, (long long*)bm_ids, bm_counts);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }

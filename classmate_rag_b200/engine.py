@@ -115,6 +115,8 @@ class HybridEngine:
         k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
         pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
         pool = min(pool, 64) if p.use_mmr else pool
+        if self.comm is not None:
+            return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
         scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
         self.last_dense_flags = flags
         if p.use_mmr:
@@ -130,6 +132,32 @@ class HybridEngine:
                                w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
 
 
+    def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask):
+        """Row-sharded step with ONE collective: local dense pool + local BM25 list ->
+        cmr_shard_pack -> all-gather -> cmr_shard_merge -> MMR -> fuse."""
+        comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
+        try:
+            dense = self.dense_pool(q_bf16, pool, dense_mask)
+            bm_local = None
+            if hybrid:
+                b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+                bm_local = (b_sc, b_ids, b_cnt)
+        finally:
+            self.comm = comm
+        dim = self.emb.shape[1] if p.use_mmr else 0
+        msg = ops.shard_pack(dense, bm_local, self.emb if p.use_mmr else None, row_offset=self.row_offset)
+        gathered = comm.all_gather_bytes(msg)
+        d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_merge(gathered, pool, p.k_bm25 if hybrid else 0, dim)
+        self.last_dense_flags = d_f
+        if p.use_mmr:
+            v_ids, v_sims, v_cnt = ops.mmr_select(rows, d_s, d_i, d_c, min(k_vec, pool), p.mmr_lambda)
+        else:
+            v_ids, v_sims, v_cnt = d_i, d_s, d_c
+        bm = (g_bi, g_bs, g_bc) if hybrid else None
+        return ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
+                               w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+
+
 class GraphedSearch:
     """One fixed-shape hybrid search captured in a CUDA graph: host inputs are
     copied into static device buffers, the whole kernel sequence replays as one
@@ -137,8 +165,10 @@ class GraphedSearch:
 
     This is the end-to-end call with HOST buffers that bench.py's ``e2e`` times."""
 
-    def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64):
+    def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64,
+                 graph_collectives: bool = True):
         self.engine, self.p, self.b = engine, p, n_queries
+        self.graph_collectives = graph_collectives
         dev = engine.device
         d = engine.emb.shape[1]
         self.hybrid = p.hybrid and engine.lex is not None
@@ -165,7 +195,9 @@ class GraphedSearch:
             for _ in range(2):  # warm-up: one-time attribute / occupancy calls, allocations
                 self.out = self._run()
             self.stream.synchronize()
-            if self.engine.comm is None:
+            if self.engine.comm is None or self.graph_collectives:
+                # with a communicator the graph holds the step's single NCCL all-gather too
+                # (every rank captures and replays the same sequence)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.stream):
                     self.out = self._run()

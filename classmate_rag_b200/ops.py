@@ -271,3 +271,55 @@ def filter_mask(field_codes: torch.Tensor, clause_field: torch.Tensor, clause_co
                                                clause_code.data_ptr() if n_clauses else None, n_clauses,
                                                _ptr(alive), out.data_ptr(), _stream()))
     return out
+
+
+def shard_msg_bytes(pool: int, kb: int, dim: int) -> int:
+    n = _lib.load().cmr_shard_msg_bytes(pool, kb, dim)
+    if n == 0:
+        raise ValueError("bad shard message shape")
+    return int(n)
+
+
+def shard_pack(dense, bm, emb: Optional[torch.Tensor], *, row_offset: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One rank's message of a sharded step (cmr_shard_pack).  dense = (scores f64 [B,pool],
+    ids i64 [B,pool], counts i32 [B], flags i32 [B] or None); bm = (scores, ids, counts) or
+    None; emb: this shard's matrix (its rows are copied for the dense candidates) or None
+    when the step does not need rows.  Returns uint8 [B, msg_bytes]."""
+    d_s, d_i, d_c, d_f = dense
+    b, pool = d_s.shape
+    kb = 0 if bm is None else bm[0].shape[1]
+    dim = 0 if emb is None else emb.shape[1]
+    nbytes = shard_msg_bytes(pool, kb, dim)
+    if out is None:
+        out = torch.empty((b, nbytes), dtype=torch.uint8, device=d_s.device)
+    bp = (None, None, None) if bm is None else (bm[0].data_ptr(), bm[1].data_ptr(), bm[2].data_ptr())
+    with torch.cuda.device(d_s.device):
+        _lib.check(_lib.load().cmr_shard_pack(d_s.data_ptr(), d_i.data_ptr(), d_c.data_ptr(), _ptr(d_f), pool, *bp, kb,
+                                              _ptr(emb), 0 if emb is None else emb.shape[0], dim, row_offset, b,
+                                              out.data_ptr(), _stream()))
+    return out
+
+
+def shard_merge(gathered: torch.Tensor, pool: int, kb: int, dim: int):
+    """Merge the all-gathered messages uint8 [G, B, msg_bytes] (cmr_shard_merge).  Returns
+    (d_scores [B,pool], d_ids, d_counts, d_flags, d_rows bf16 [B,pool,dim] or None,
+    b_scores [B,kb] or None, b_ids, b_counts)."""
+    _require_cuda(gathered, "gathered")
+    g, b, nbytes = gathered.shape
+    if nbytes != shard_msg_bytes(pool, kb, dim):
+        raise ValueError("gathered message size does not match (pool, kb, dim)")
+    dev = gathered.device
+    d_s = torch.empty((b, pool), dtype=torch.float64, device=dev)
+    d_i = torch.empty((b, pool), dtype=torch.int64, device=dev)
+    d_c = torch.empty((b,), dtype=torch.int32, device=dev)
+    d_f = torch.empty((b,), dtype=torch.int32, device=dev)
+    rows = torch.empty((b, pool, dim), dtype=torch.bfloat16, device=dev) if dim else None
+    b_s = torch.empty((b, kb), dtype=torch.float64, device=dev) if kb else None
+    b_i = torch.empty((b, kb), dtype=torch.int64, device=dev) if kb else None
+    b_c = torch.empty((b,), dtype=torch.int32, device=dev) if kb else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_shard_merge(gathered.data_ptr(), g, b, pool, kb, dim, d_s.data_ptr(), d_i.data_ptr(),
+                                               d_c.data_ptr(), d_f.data_ptr(), _ptr(rows), _ptr(b_s), _ptr(b_i),
+                                               _ptr(b_c), _stream()))
+    return d_s, d_i, d_c, d_f, rows, b_s, b_i, b_c

@@ -2,11 +2,14 @@
 
 The dense matrix and the inverted index are partitioned by contiguous row
 ranges; every rank scores the same queries against its shard and only the
-per-shard top-k candidates travel: one all-gather of B x k x (score, id) per
-retriever, merged by cmr_topk_merge with the total order (score desc, id asc),
-so the result is identical for any number of shards.  The MMR pool's embedding
-rows are reassembled with one all-reduce (each row is non-zero on exactly one
-rank).  Index build needs one all-reduce of df[V] / token totals / first
+per-shard top-k candidates travel.  The hot path (engine.HybridEngine.search) packs a
+rank's dense pool (scores, ids and the embedding rows MMR needs) and its BM25
+list into ONE message (cmr_shard_pack), all-gathers the messages (the only
+collective of a step) and merges them with cmr_shard_merge under the total order
+(score desc, id asc), so the result is identical for any number of shards.  The
+per-retriever exchange (merge_topk: one all-gather of B x k x (score, id);
+sum_rows: one all-reduce of the pool rows) remains for callers that run a single
+retriever.  Index build needs one all-reduce of df[V] / token totals / first
 positions so that every shard scores with the corpus-wide idf and avgdl.
 The reference has no distributed code; this is new.
 """
@@ -62,6 +65,14 @@ class ShardComm:
         m_scores, m_ids, m_counts = self._merge(g_scores, g_ids, g_counts)
         m_flags = out[:, :, 2 * k + 1].amax(dim=0).to(torch.int32)
         return m_scores, m_ids, m_counts, m_flags
+
+    def all_gather_bytes(self, msg: torch.Tensor) -> torch.Tensor:
+        """The single collective of a sharded step: every rank's packed message
+        (uint8 [B, msg_bytes], see cmr_shard_pack) -> uint8 [G, B, msg_bytes]."""
+        out = torch.empty((self.world, *msg.shape), dtype=msg.dtype, device=msg.device)
+        dist.all_gather_into_tensor(out.view(self.world * msg.shape[0], *msg.shape[1:]), msg.contiguous(),
+                                    group=self.group)
+        return out
 
     def sum_rows(self, rows: torch.Tensor) -> torch.Tensor:
         """Reassemble gathered bf16 rows: exactly one rank holds each row, the

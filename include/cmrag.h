@@ -234,6 +234,23 @@ int cmr_topk_merge(const double* in_scores, const int64_t* in_ids, const int32_t
                    int n_parts, int n_queries, int k, double* out_scores, int64_t* out_ids,
                    int32_t* out_counts, cmr_stream_t stream);
 
+/* K7, single exchange: everything a rank contributes to one step -- its dense pool (scores,
+ *     ids, flags and the bf16 rows the MMR step reads) and its BM25 list -- packed into one
+ *     message per query, so a sharded step has ONE collective: an all-gather of
+ *     n_queries * cmr_shard_msg_bytes() bytes per rank.  cmr_shard_merge then merges the
+ *     G messages ([n_parts][n_queries][msg]) by (score desc, id asc): dense pool + its rows
+ *     ([n_queries, pool, dim], ready for cmr_mmr_select) and the BM25 list.  kb = 0: no
+ *     lexical list (non-hybrid); dim = 0: no rows (MMR off). */
+size_t cmr_shard_msg_bytes(int pool, int kb, int dim);
+int cmr_shard_pack(const double* dense_scores, const int64_t* dense_ids, const int32_t* dense_counts,
+                   const int32_t* dense_flags, int pool, const double* bm_scores, const int64_t* bm_ids,
+                   const int32_t* bm_counts, int kb, const uint16_t* emb, int64_t n_rows, int dim,
+                   int64_t row_offset, int n_queries, void* msg, cmr_stream_t stream);
+int cmr_shard_merge(const void* gathered, int n_parts, int n_queries, int pool, int kb, int dim,
+                    double* dense_scores, int64_t* dense_ids, int32_t* dense_counts, int32_t* dense_flags,
+                    uint16_t* dense_rows, double* bm_scores, int64_t* bm_ids, int32_t* bm_counts,
+                    cmr_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * A9 / K6  Near-duplicate cosine filter over the embedding matrix (extension used by
  *     `rag rebuild`; greedy keep-first rule of rag/utils/dedup.py:40-55: row i is kept iff

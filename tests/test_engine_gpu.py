@@ -106,3 +106,53 @@ def test_graphed_search_equals_eager_and_is_deterministic(small_world):
         for a, c in zip(got, eager):
             assert a.tobytes() == c.cpu().numpy().tobytes()
     assert gs.h2d_bytes > 0 and gs.d2h_bytes > 0
+
+
+@pytest.mark.parametrize("n_shards,hybrid,use_mmr", [(2, True, True), (3, True, False), (8, False, True), (5, True, True)])
+def test_single_exchange_shard_merge_equals_unsharded(small_world, n_shards, hybrid, use_mmr):
+    """The sharded step's message protocol (cmr_shard_pack -> all-gather -> cmr_shard_merge),
+    with the ranks emulated one after the other on one GPU: the concatenation of the ranks'
+    messages is exactly what the all-gather delivers.  Result must equal the unsharded
+    search bit for bit, for any number of shards."""
+    from classmate_rag_b200 import lexical, ops, sharding, synth
+    from classmate_rag_b200.engine import HybridEngine, SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    n, d = emb.shape
+    vocab = lex.n_terms
+    p = SearchParams(top_k=9, hybrid=hybrid, use_mmr=use_mmr)
+    q_bf16 = ops.f32_to_bf16(q)
+    qt, qp = lexical.pack_queries(terms)
+    qt, qp = qt.cuda(), qp.cuda()
+    want = [t.clone() for t in eng.search(q_bf16, qt, qp, p)]
+
+    doc_ptr, tokens = synth.lexical_corpus(n, vocab, 24, "cuda")
+    stats = lexical.corpus_stats(doc_ptr, tokens, vocab)
+    k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
+    pool = min(max(k_vec, p.mmr_max_pool), 64) if use_mmr else k_vec
+    msgs = []
+    for r in range(n_shards):
+        lo, hi = sharding.shard_range(n, r, n_shards)
+        t_lo, t_hi = int(doc_ptr[lo]), int(doc_ptr[hi])
+        sh_lex = lexical.build_lexical_index(doc_ptr[lo:hi + 1] - doc_ptr[lo], tokens[t_lo:t_hi], vocab,
+                                             tile_docs=2048, stats=stats)
+        sh = HybridEngine(emb[lo:hi].contiguous(), sh_lex, row_offset=lo)
+        dense = sh.dense_pool(q_bf16, pool)
+        bm = None
+        if hybrid:
+            b_sc, b_ids, b_cnt, _ = sh.lexical_topk(qt, qp, p.k_bm25)
+            bm = (b_sc, b_ids, b_cnt)
+        msgs.append(ops.shard_pack(dense, bm, sh.emb if use_mmr else None, row_offset=lo).clone())
+    gathered = torch.stack(msgs)
+    assert gathered.shape[2] == ops.shard_msg_bytes(pool, p.k_bm25 if hybrid else 0, d if use_mmr else 0)
+    d_s, d_i, d_c, d_f, rows, b_s, b_i, b_c = ops.shard_merge(gathered, pool, p.k_bm25 if hybrid else 0,
+                                                               d if use_mmr else 0)
+    if use_mmr:
+        v_ids, v_sims, v_cnt = ops.mmr_select(rows, d_s, d_i, d_c, min(k_vec, pool), p.mmr_lambda)
+    else:
+        v_ids, v_sims, v_cnt = d_i, d_s, d_c
+    got = ops.hybrid_fuse((v_ids, v_sims, v_cnt), (b_i, b_s, b_c) if hybrid else None, top_k=p.top_k, rrf_k=p.rrf_k,
+                          w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+    torch.cuda.synchronize()
+    assert int(d_f.sum()) == 0
+    for a, b in zip(got, want):
+        assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()

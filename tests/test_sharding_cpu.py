@@ -61,6 +61,10 @@ def _worker(rank, world, port, ret):
             want = np.lexsort((np.arange(n), -scores_all[q]))[:k]
             assert m_i[q].tolist() == want.tolist()
             assert m_s[q].tolist() == scores_all[q][want].tolist()
+        # ---- the single-exchange all-gather of packed messages: [G, B, bytes], rank-major
+        msg = torch.full((3, 48), rank + 1, dtype=torch.uint8)
+        got = comm.all_gather_bytes(msg)
+        assert got.shape == (world, 3, 48) and all(int(got[r].min()) == r + 1 == int(got[r].max()) for r in range(world))
         # ---- pool rows: exactly one rank holds each row
         rows = torch.zeros((4, 16), dtype=torch.bfloat16)
         full = (torch.arange(64, dtype=torch.float32).reshape(4, 16) / 7).to(torch.bfloat16)
