@@ -149,6 +149,9 @@ struct MmParams {
   int stride;          // SAMPLE: tile stride; NEARDUP: block step of this rank
   int begin;           // NEARDUP: first block of this rank
   u32 tx_bytes;        // bytes per ring stage (both TMA boxes)
+  u32 a_bytes;         // shared memory reserved for the left box of a stage (multiple of 1024;
+                       // < 16 KiB when fewer than 128 queries: the MMA then reads past it into
+                       // the stage's own right tile for lanes nobody looks at)
   int rows_evict_first;
   // SAMPLE / MAIN
   const float* thr;
@@ -206,7 +209,8 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   extern __shared__ unsigned char smem_raw[];
   const u32 raw = smem_u32(smem_raw);
   const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  const u32 bars = base + MM_STAGES * MM_STAGE_BYTES;
+  const u32 stage_bytes = p.a_bytes + MM_B_BYTES;
+  const u32 bars = base + MM_STAGES * stage_bytes;
   // barrier slots: full[s] at +8s, empty[s] at +32+8s, tmem_full[b] at +64+8b, tmem_empty[b] at +80+8b
   volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(smem_raw + (bars - raw) + 96);
 
@@ -247,9 +251,9 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           mbar_wait(bars + 32 + 8 * s, ph ^ 1u);
           const u32 full = bars + 8 * s;
           mbar_expect_tx(full, p.tx_bytes);
-          const u32 sa = base + s * MM_STAGE_BYTES;
+          const u32 sa = base + s * stage_bytes;
           tma_load_2d(sa, &tm_q, full, kc * MM_K, a0, hint_left);
-          tma_load_2d(sa + MM_A_BYTES, &tm_rows, full, kc * MM_K, b0, hint_rows);
+          tma_load_2d(sa + p.a_bytes, &tm_rows, full, kc * MM_K, b0, hint_rows);
         }
       }
     }
@@ -267,9 +271,9 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
           mbar_wait(bars + 8 * s, ph);  // TMA bytes have landed
           tc_fence_after();
-          const u32 sa = base + s * MM_STAGE_BYTES;
+          const u32 sa = base + s * stage_bytes;
           const unsigned long long da = umma_desc_sw128(sa);
-          const unsigned long long db = umma_desc_sw128(sa + MM_A_BYTES);
+          const unsigned long long db = umma_desc_sw128(sa + p.a_bytes);
 #pragma unroll
           for (int k = 0; k < MM_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
             tc_mma_bf16(d_tmem, da + 2ull * k, db + 2ull * k, MM_IDESC, (kc | k) != 0);
@@ -447,6 +451,10 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int di
   return CMR_OK;
 }
 
+static inline size_t mma_smem_bytes(u32 a_bytes) {
+  return (size_t)MM_STAGES * (a_bytes + MM_B_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
+}
+
 struct MmaPlan {
   int kpl, kp, cap;
   int n_mb, n_chunks, q_box_rows, bpad;
@@ -564,6 +572,8 @@ int dense_mma_topk(const DenseArgs& a) {
   kp.n_chunks = p.n_chunks;
   kp.n_inner = p.n_mb;
   kp.tx_bytes = tx_bytes;
+  kp.a_bytes = (u32)(p.q_box_rows * MM_K * 2 + 1023) / 1024 * 1024;
+  const size_t smem_bytes = mma_smem_bytes(kp.a_bytes);
   kp.thr = thr;
   kp.gmax = gmax;
   kp.gstride = p.bpad;
@@ -576,7 +586,7 @@ int dense_mma_topk(const DenseArgs& a) {
     kp.n_outer = p.n_sample;
     kp.stride = p.sample_stride;
     kp.rows_evict_first = 0;
-    dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(tm_q, tm_rows, kp);
+    dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, smem_bytes, a.stream>>>(tm_q, tm_rows, kp);
   }
   dense_thresh_kernel<<<a.n_queries, 256, (size_t)(p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
       gmax, p.n_groups, p.bpad, p.kp, thr, cnt);
@@ -585,7 +595,7 @@ int dense_mma_topk(const DenseArgs& a) {
     kp.n_outer = p.n_tiles;
     kp.stride = 1;
     kp.rows_evict_first = p.n_mb == 1;
-    dense_mma_kernel<MM_MAIN><<<grid, MM_THREADS, MM_SMEM_BYTES, a.stream>>>(tm_q, tm_rows, kp);
+    dense_mma_kernel<MM_MAIN><<<grid, MM_THREADS, smem_bytes, a.stream>>>(tm_q, tm_rows, kp);
   }
   switch (p.kpl) {
     case 1: rc = launch_finalize_cand<1>(a, p, cand, cnt); break;
@@ -692,6 +702,7 @@ extern "C" int cmr_neardup_edges(const uint16_t* emb, int64_t n_rows, int dim, f
   kp.stride = block_step;
   kp.begin = block_begin;
   kp.tx_bytes = (u32)(MM_A_BYTES + MM_B_BYTES);
+  kp.a_bytes = MM_A_BYTES;
   kp.rows_evict_first = 0;
   kp.nd_bound = bound;
   kp.edges = (u64*)out_edges;

@@ -29,7 +29,7 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ emb, long long n_ro
     out[(size_t)i * dim_vec + v] = mine ? emb[(size_t)local * dim_vec + v] : make_uint4(0, 0, 0, 0);
 }
 
-constexpr int MMR_THREADS = 256;
+constexpr int MMR_THREADS = 1024;
 constexpr int MMR_MAX_POOL = 64;
 
 // One CTA per query.  cand_rows [B][pool][dim] bf16, cand_sims [B][pool] (exact
@@ -63,7 +63,9 @@ mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restri
     }
   }
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
+    // greedy selection by one warp: lane l scores candidates l and l+32, the best
+    // (score desc, index asc -- the reference's strict '>' over ascending i) wins
     const int target = k < n ? k : n;
     int n_sel = 0;
     unsigned long long remaining = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
@@ -71,31 +73,47 @@ mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restri
       int first = 0;  // np.argmax: lowest index on ties
       for (int i = 1; i < n; ++i)
         if (s_q[i] > s_q[first]) first = i;
-      s_sel[n_sel++] = first;
+      if (lane == 0) s_sel[0] = first;
+      n_sel = 1;
       remaining &= ~(1ull << first);
     }
+    __syncwarp();
     const double one_minus = __dsub_rn(1.0, lambda);
     while (remaining && n_sel < target) {
-      int best = -1;
       double best_score = -1e9;
-      for (int i = 0; i < n; ++i) {
-        if (!((remaining >> i) & 1ull)) continue;
-        double div = s_cc[i * MMR_MAX_POOL + s_sel[0]];
-        for (int j = 1; j < n_sel; ++j) {
-          const double v = s_cc[i * MMR_MAX_POOL + s_sel[j]];
-          if (v > div) div = v;
+      int best = -1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < n && ((remaining >> i) & 1ull)) {
+          double div = s_cc[i * MMR_MAX_POOL + s_sel[0]];
+          for (int j = 1; j < n_sel; ++j) {
+            const double v = s_cc[i * MMR_MAX_POOL + s_sel[j]];
+            if (v > div) div = v;
+          }
+          const double sc = __dsub_rn(__dmul_rn(lambda, s_q[i]), __dmul_rn(one_minus, div));
+          if (sc > best_score) {  // h = 0 first: the lower index keeps a tie
+            best_score = sc;
+            best = i;
+          }
         }
-        const double sc = __dsub_rn(__dmul_rn(lambda, s_q[i]), __dmul_rn(one_minus, div));
-        if (sc > best_score) {
-          best_score = sc;
-          best = i;
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, off);
+        const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+        if (ob >= 0 && (best < 0 || os > best_score || (os == best_score && ob < best))) {
+          best_score = os;
+          best = ob;
         }
       }
       if (best < 0) break;
-      s_sel[n_sel++] = best;
+      if (lane == 0) s_sel[n_sel] = best;
+      ++n_sel;
       remaining &= ~(1ull << best);
+      __syncwarp();
     }
-    for (int i = 0; i < k; ++i) {
+    for (int i = lane; i < k; i += 32) {
       if (i < n_sel) {
         out_ids[(size_t)qi * k + i] = cand_ids[(size_t)qi * pool + s_sel[i]];
         out_sims[(size_t)qi * k + i] = s_q[s_sel[i]];
@@ -104,7 +122,7 @@ mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restri
         out_sims[(size_t)qi * k + i] = 0.0;
       }
     }
-    out_counts[qi] = n_sel;
+    if (lane == 0) out_counts[qi] = n_sel;
   }
 }
 
