@@ -42,9 +42,7 @@ constexpr int MM_K = 64;      // bf16 per K chunk: one 128-byte swizzle span
 constexpr int MM_STAGES = 4;
 constexpr int MM_A_BYTES = MM_Q * MM_K * 2;  // 16 KiB
 constexpr int MM_B_BYTES = MM_R * MM_K * 2;  // 32 KiB
-constexpr int MM_STAGE_BYTES = MM_A_BYTES + MM_B_BYTES;
 constexpr int MM_THREADS = 192;
-constexpr int MM_SMEM_BYTES = MM_STAGES * MM_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int MM_SAMPLE = 0, MM_MAIN = 1, MM_NEARDUP = 2;
 constexpr int MM_CAP_PER_KP = 64;    // candidate slots per query = 64 * KP
 constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile
@@ -157,9 +155,9 @@ struct MmParams {
   const float* thr;
   float* gmax;
   int gstride, gpt;
-  u64* cand;
-  int* cnt;
-  int cap;
+  u64* cand;           // [n_ctas][n_left][cap]: every CTA keeps private lists, so no atomics
+  int* cnt;            // [n_ctas][n_left] entries appended (may exceed cap: the excess was dropped)
+  int cap;             // slots per (CTA, query)
   // NEARDUP
   float nd_bound;      // emit pairs with fp32 score >= nd_bound (= threshold - error bound)
   u64* edges;          // (i << 32) | j
@@ -199,8 +197,9 @@ struct MmIter {
 
 // MODE == MM_SAMPLE: the epilogue writes group maxima gmax[(item * gpt + g) * gstride + query],
 //   gpt = 8 (groups of 32 rows) or 1 (the whole tile); sampled tiles are always full tiles.
-// MODE == MM_MAIN:   scores >= thr[query] are appended to cand[query * cap + atomicAdd(cnt[query])]
-//   as (orderable fp32 score, ~row) keys.
+// MODE == MM_MAIN:   scores >= thr[query] are appended to this CTA's private list of the query
+//   as (orderable fp32 score, ~row) keys.  A query is always handled by the same thread of a
+//   CTA, so the list counters live in shared memory and need no atomics.
 // MODE == MM_NEARDUP: pairs (i, j < i) with score >= nd_bound are appended to `edges`.
 template <int MODE>
 __global__ void __launch_bounds__(MM_THREADS, 1)
@@ -213,6 +212,9 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const u32 bars = base + MM_STAGES * stage_bytes;
   // barrier slots: full[s] at +8s, empty[s] at +32+8s, tmem_full[b] at +64+8b, tmem_empty[b] at +80+8b
   volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(smem_raw + (bars - raw) + 96);
+  int* s_cnt = reinterpret_cast<int*>(smem_raw + (bars - raw) + 128);  // MAIN: [n_inner * 128] list lengths
+  if (MODE == MM_MAIN)
+    for (int i = threadIdx.x; i < p.n_inner * MM_Q; i += MM_THREADS) s_cnt[i] = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -322,8 +324,9 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               const long long row = row0 + c * 32 + j;
               if (MODE == MM_MAIN) {
                 if (row < p.n_rows) {
-                  const int slot = atomicAdd(&p.cnt[qi], 1);
-                  if (slot < p.cap) p.cand[(size_t)qi * p.cap + slot] = make_key(v[j], (u32)row);
+                  const int slot = s_cnt[qi]++;   // only this thread touches query qi in this CTA
+                  if (slot < p.cap)
+                    p.cand[((size_t)blockIdx.x * p.n_left + qi) * p.cap + slot] = make_key(v[j], (u32)row);
                 }
               } else if (row < (long long)qi) {
                 const unsigned long long slot = atomicAdd(p.edge_count, 1ull);
@@ -342,6 +345,8 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (MODE == MM_MAIN)
+    for (int i = threadIdx.x; i < p.n_left; i += MM_THREADS) p.cnt[(size_t)blockIdx.x * p.n_left + i] = s_cnt[i];
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -350,14 +355,13 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 // One CTA per query: bound = the kp-th largest of the G sampled group maxima (bit-wise
 // bisection on the orderable integer image of the floats), -inf when there are fewer than
-// kp groups.  Also clears the query's candidate counter for the MAIN pass.
+// kp groups.
 __global__ void __launch_bounds__(256)
 dense_thresh_kernel(const float* __restrict__ gmax, int n_groups, int gstride, int kp,
-                    float* __restrict__ thr, int* __restrict__ cnt) {
+                    float* __restrict__ thr) {
   extern __shared__ u32 s_vals[];
   __shared__ int s_count;
   const int q = blockIdx.x, tid = threadIdx.x;
-  if (tid == 0) cnt[q] = 0;
   if (n_groups < kp) {
     if (tid == 0) thr[q] = -INFINITY;
     return;
@@ -381,26 +385,48 @@ dense_thresh_kernel(const float* __restrict__ gmax, int n_groups, int gstride, i
   if (tid == 0) thr[q] = orderable_f32(prefix);
 }
 
-// One CTA per query: the KP best of the query's candidates (unique keys, ranked by counting),
-// then the shared exact rescoring tail.  More candidates than slots -> CMR_FLAG_UNCERTIFIED.
+// One CTA per query: collect the query's candidates from every CTA's private list, take the KP
+// best (unique keys, ranked by counting), then the shared exact rescoring tail.  A list or the
+// collection buffer that overflowed -> CMR_FLAG_UNCERTIFIED.
 template <int KPL>
 __global__ void __launch_bounds__(FIN_THREADS)
-dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__ cnt, int cap,
-                           const uint16_t* __restrict__ emb, int dim, const uint16_t* __restrict__ queries,
-                           long long row_offset, int k, double cert_eps, double* __restrict__ out_scores,
-                           long long* __restrict__ out_ids, int* __restrict__ out_counts,
-                           int* __restrict__ out_flags) {
+dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__ cnt, int n_lists, int n_queries,
+                           int cap, int cap_total, const uint16_t* __restrict__ emb, int dim,
+                           const uint16_t* __restrict__ queries, long long row_offset, int k, double cert_eps,
+                           double* __restrict__ out_scores, long long* __restrict__ out_ids,
+                           int* __restrict__ out_counts, int* __restrict__ out_flags) {
   constexpr int KP = 32 * KPL;
   extern __shared__ __align__(16) unsigned char smem_fin[];
-  u64* s_keys = reinterpret_cast<u64*>(smem_fin);  // [cap]
-  u64* s_out = s_keys + cap;                       // [KP]
+  u64* s_keys = reinterpret_cast<u64*>(smem_fin);  // [cap_total]
+  u64* s_out = s_keys + cap_total;                 // [KP]
   double* s_score = reinterpret_cast<double*>(s_out + KP);
-  const int qi = blockIdx.x, tid = threadIdx.x;
-  const int total = cnt[qi];
-  const int m = total < cap ? total : cap;
-  for (int i = tid; i < m; i += FIN_THREADS) s_keys[i] = cand[(size_t)qi * cap + i];
+  __shared__ int s_total, s_over;
+  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_total = 0;
+    s_over = 0;
+  }
   for (int i = tid; i < KP; i += FIN_THREADS) s_out[i] = 0ull;
   __syncthreads();
+  // one warp per CTA list: claim a range of the shared buffer, copy the keys
+  for (int l = warp; l < n_lists; l += FIN_THREADS / 32) {
+    const int have = cnt[(size_t)l * n_queries + qi];
+    if (have == 0) continue;  // warp-uniform
+    const int take = have < cap ? have : cap;
+    int base = 0;
+    if (lane == 0) {
+      base = atomicAdd(&s_total, take);
+      if (have > cap) s_over = 1;
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const u64* src = cand + ((size_t)l * n_queries + qi) * cap;
+    for (int i = lane; i < take; i += 32) {
+      if (base + i < cap_total) s_keys[base + i] = src[i];
+      else s_over = 1;
+    }
+  }
+  __syncthreads();
+  const int m = s_total < cap_total ? s_total : cap_total;
   for (int e = tid; e < m; e += FIN_THREADS) {
     const u64 key = s_keys[e];
     int rank = 0;
@@ -409,7 +435,7 @@ dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__
   }
   __syncthreads();
   dense_finalize_tail<KP>(s_out, s_score, emb, dim, queries + (size_t)qi * dim, row_offset, k, cert_eps,
-                          total > cap ? CMR_FLAG_UNCERTIFIED : 0, qi, out_scores, out_ids, out_counts, out_flags);
+                          s_over ? CMR_FLAG_UNCERTIFIED : 0, qi, out_scores, out_ids, out_counts, out_flags);
 }
 
 // ---- host side ------------------------------------------------------------------------
@@ -451,22 +477,29 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int di
   return CMR_OK;
 }
 
-static inline size_t mma_smem_bytes(u32 a_bytes) {
-  return (size_t)MM_STAGES * (a_bytes + MM_B_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int MM_SMEM_MAX = 227 * 1024;
+constexpr int MM_MAX_QUERIES = 8192;  // list counters of all query blocks must fit in shared memory
+
+static inline size_t mma_smem_bytes(u32 a_bytes, int n_inner) {
+  return (size_t)MM_STAGES * (a_bytes + MM_B_BYTES) + 1024 /* alignment slack */ + 128 /* barriers */ +
+         (size_t)n_inner * MM_Q * 4 /* MAIN: list counters */;
 }
 
 struct MmaPlan {
-  int kpl, kp, cap;
+  int kpl, kp;
+  int cap;        // slots of one (CTA, query) list
+  int cap_total;  // candidates finalize can collect per query
+  int n_lists;    // CTAs of the MAIN pass
   int n_mb, n_chunks, q_box_rows, bpad;
   int n_tiles, n_sample, sample_stride, gpt, n_groups;
   size_t off_cnt, off_thr, off_gmax, total;
 };
 
-static void mma_plan(long long n_rows, int dim, int n_queries, int k, MmaPlan* p) {
+static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, MmaPlan* p) {
   const int need = k + CMR_SLACK;
   p->kpl = need <= 32 ? 1 : (need <= 64 ? 2 : 4);
   p->kp = 32 * p->kpl;
-  p->cap = MM_CAP_PER_KP * p->kp;
+  p->cap_total = MM_CAP_PER_KP * p->kp;
   p->n_mb = (n_queries + MM_Q - 1) / MM_Q;
   p->n_chunks = (dim + MM_K - 1) / MM_K;
   p->q_box_rows = n_queries >= MM_Q ? MM_Q : (n_queries + 7) / 8 * 8;
@@ -484,9 +517,18 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, MmaPlan* p
     if (p->n_groups <= MM_MAX_GROUPS) break;
     stride *= 2;
   }
-  size_t off = (size_t)n_queries * p->cap * sizeof(u64);
+  p->n_lists = p->n_tiles < sms ? p->n_tiles : sms;
+  if (p->n_groups < p->kp) {
+    // no bound (tiny matrix): every row of a CTA's tiles is a candidate
+    p->cap = MM_R * ((p->n_tiles + p->n_lists - 1) / p->n_lists);
+  } else {
+    // about MM_SAMPLE_STRIDE * KP candidates per query in all; 4x the even share + slack
+    p->cap = 4 * MM_SAMPLE_STRIDE * p->kp / p->n_lists + 32;
+  }
+  if (p->cap > p->cap_total) p->cap = p->cap_total;
+  size_t off = ((size_t)p->n_lists * n_queries * p->cap * sizeof(u64) + 15) / 16 * 16;
   p->off_cnt = off;
-  off += ((size_t)p->bpad * 4 + 15) / 16 * 16;
+  off += ((size_t)p->n_lists * n_queries * 4 + 15) / 16 * 16;
   p->off_thr = off;
   off += ((size_t)p->bpad * 4 + 15) / 16 * 16;
   p->off_gmax = off;
@@ -495,19 +537,20 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, MmaPlan* p
 }
 
 bool dense_mma_eligible(long long n_rows, int dim, int n_queries, int k, bool has_mask) {
-  return !has_mask && dim >= MM_K && n_rows >= MM_R && n_rows < 0x7FFFFF00ll && n_queries >= 1 && k >= 1 &&
-         k <= CMR_MAX_K;
+  return !has_mask && dim >= MM_K && n_rows >= MM_R && n_rows < 0x7FFFFF00ll && n_queries >= 1 &&
+         n_queries <= MM_MAX_QUERIES && k >= 1 && k <= CMR_MAX_K;
 }
 
 size_t dense_mma_workspace_bytes(long long n_rows, int dim, int n_queries, int k) {
   MmaPlan p;
-  mma_plan(n_rows, dim, n_queries, k, &p);
+  const int sms = sm_count();
+  mma_plan(n_rows, dim, n_queries, k, sms > 0 ? sms : 148, &p);
   return p.total;
 }
 
 template <int KPL>
 static int launch_finalize_cand(const DenseArgs& a, const MmaPlan& p, const u64* cand, const int* cnt) {
-  const size_t smem = (size_t)p.cap * 8 + (size_t)p.kp * 16 + 16;
+  const size_t smem = (size_t)p.cap_total * 8 + (size_t)p.kp * 16 + 16;
   static int attr_dev_mask = 0;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -518,8 +561,8 @@ static int launch_finalize_cand(const DenseArgs& a, const MmaPlan& p, const u64*
     attr_dev_mask |= (1 << dev);
   }
   dense_finalize_cand_kernel<KPL><<<a.n_queries, FIN_THREADS, smem, a.stream>>>(
-      cand, cnt, p.cap, a.emb, a.dim, a.queries, a.row_offset, a.k, a.cert_eps, a.out_scores, a.out_ids,
-      a.out_counts, a.out_flags);
+      cand, cnt, p.n_lists, a.n_queries, p.cap, p.cap_total, a.emb, a.dim, a.queries, a.row_offset, a.k, a.cert_eps,
+      a.out_scores, a.out_ids, a.out_counts, a.out_flags);
   return CMR_OK;
 }
 
@@ -529,11 +572,11 @@ static int mma_opt_in() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_dev_mask & (1 << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel<MM_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel<MM_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_mma_kernel<MM_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+      e = cudaFuncSetAttribute(dense_mma_kernel<MM_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_mma_kernel<MM_NEARDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES);
+      e = cudaFuncSetAttribute(dense_mma_kernel<MM_NEARDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(dense_thresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_MAX_GROUPS * 4);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_mma)");
@@ -544,14 +587,14 @@ static int mma_opt_in() {
 
 int dense_mma_topk(const DenseArgs& a) {
   MmaPlan p;
-  mma_plan(a.n_rows, a.dim, a.n_queries, a.k, &p);
+  const int sms = sm_count();
+  if (sms <= 0) return CMR_ECUDA;
+  mma_plan(a.n_rows, a.dim, a.n_queries, a.k, sms, &p);
   if (!a.workspace || a.workspace_bytes < p.total) {
     set_error("workspace too small: %zu < %zu", a.workspace_bytes, p.total);
     return CMR_EWORKSPACE;
   }
   CMR_CHECK_ARG(((uintptr_t)a.workspace % 16) == 0, "workspace must be 16-byte aligned");
-  const int sms = sm_count();
-  if (sms <= 0) return CMR_ECUDA;
   { const int rc_attr = mma_opt_in(); if (rc_attr != CMR_OK) return rc_attr; }
   alignas(64) CUtensorMap tm_q, tm_rows;
   int rc = make_tmap(&tm_q, a.queries, a.n_queries, a.dim, p.q_box_rows);
@@ -573,7 +616,11 @@ int dense_mma_topk(const DenseArgs& a) {
   kp.n_inner = p.n_mb;
   kp.tx_bytes = tx_bytes;
   kp.a_bytes = (u32)(p.q_box_rows * MM_K * 2 + 1023) / 1024 * 1024;
-  const size_t smem_bytes = mma_smem_bytes(kp.a_bytes);
+  const size_t smem_bytes = mma_smem_bytes(kp.a_bytes, p.n_mb);
+  if (smem_bytes > (size_t)MM_SMEM_MAX) {
+    set_error("tcgen05 path: %d queries need %zu bytes of shared memory", a.n_queries, smem_bytes);
+    return CMR_EUNSUPPORTED;
+  }
   kp.thr = thr;
   kp.gmax = gmax;
   kp.gstride = p.bpad;
@@ -589,9 +636,9 @@ int dense_mma_topk(const DenseArgs& a) {
     dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, smem_bytes, a.stream>>>(tm_q, tm_rows, kp);
   }
   dense_thresh_kernel<<<a.n_queries, 256, (size_t)(p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
-      gmax, p.n_groups, p.bpad, p.kp, thr, cnt);
+      gmax, p.n_groups, p.bpad, p.kp, thr);
   {
-    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    const int grid = p.n_lists;
     kp.n_outer = p.n_tiles;
     kp.stride = 1;
     kp.rows_evict_first = p.n_mb == 1;
@@ -709,7 +756,7 @@ extern "C" int cmr_neardup_edges(const uint16_t* emb, int64_t n_rows, int dim, f
   kp.edge_count = (unsigned long long*)out_count;
   kp.edge_cap = edge_cap;
   const int grid = mine < sms ? mine : sms;
-  dense_mma_kernel<MM_NEARDUP><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(tm_left, tm_right, kp);
+  dense_mma_kernel<MM_NEARDUP><<<grid, MM_THREADS, mma_smem_bytes(MM_A_BYTES, 0), st>>>(tm_left, tm_right, kp);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }
