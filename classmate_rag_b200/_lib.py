@@ -19,7 +19,7 @@ CMR_OK, CMR_EINVAL, CMR_ECUDA, CMR_EWORKSPACE, CMR_EUNSUPPORTED = 0, -1, -2, -3,
 CMR_FLAG_UNCERTIFIED = 1
 CMR_MAX_K = 120
 CMR_SLACK = 8
-CMR_DENSE_AUTO, CMR_DENSE_SCAN, CMR_DENSE_MMA = 0, 1, 2
+CMR_DENSE_AUTO, CMR_DENSE_SCAN, CMR_DENSE_MMA, CMR_DENSE_EXACT = 0, 1, 2, 3
 
 _lib = None
 

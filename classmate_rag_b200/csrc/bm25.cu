@@ -481,6 +481,35 @@ static int launch_bm25(const cmr_lex_index& ix, const Bm25Plan& p, const int* q_
   return CMR_OK;
 }
 
+// Shared with the exact dense scan (dense.cu): select the k best (float64 score, id) keys over
+// n_lists sorted lists per query.  kpl in {1, 2, 4}.
+int launch_keyd_finalize(const KeyD* part, int n_lists, int n_queries, int kpl, long long row_offset, int k,
+                         double* out_scores, long long* out_ids, int* out_counts, int* out_flags,
+                         cudaStream_t st) {
+  const int kp = 32 * kpl;
+  const int cap = kp * kp < 4096 ? kp * kp : 4096;
+  const size_t smem = (size_t)(n_lists + 1) * 16 + (size_t)cap * 16 + (size_t)kp * 16 + 16;
+  if (smem > 220 * 1024) {
+    set_error("finalize shared memory %zu too large", smem);
+    return CMR_EUNSUPPORTED;
+  }
+  static int attr_dev_mask[3] = {0, 0, 0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = kpl == 1 ? 0 : (kpl == 2 ? 1 : 2);
+  if (!(attr_dev_mask[slot] & (1 << dev))) {
+    cudaError_t e = kpl == 1 ? cudaFuncSetAttribute(bm25_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                  : kpl == 2 ? cudaFuncSetAttribute(bm25_finalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                             : cudaFuncSetAttribute(bm25_finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(keyd_finalize)");
+    attr_dev_mask[slot] |= (1 << dev);
+  }
+  if (kpl == 1) bm25_finalize_kernel<1><<<n_queries, BMF_THREADS, smem, st>>>(part, n_lists, row_offset, k, out_scores, out_ids, out_counts, out_flags);
+  else if (kpl == 2) bm25_finalize_kernel<2><<<n_queries, BMF_THREADS, smem, st>>>(part, n_lists, row_offset, k, out_scores, out_ids, out_counts, out_flags);
+  else bm25_finalize_kernel<4><<<n_queries, BMF_THREADS, smem, st>>>(part, n_lists, row_offset, k, out_scores, out_ids, out_counts, out_flags);
+  return CMR_OK;
+}
+
 }  // namespace cmr
 
 using namespace cmr;

@@ -224,6 +224,61 @@ dense_finalize_kernel(const u64* __restrict__ part, int n_lists,
                           out_scores, out_ids, out_counts, out_flags);
 }
 
+// ---- exhaustive exact scan (CMR_DENSE_EXACT) -----------------------------------------------
+// Every row is scored with the exact float64 dot in the pinned order and ranked on that
+// score, so there is nothing to certify: this is what a caller falls back to for the (rare)
+// queries the fp32 passes flag as CMR_FLAG_UNCERTIFIED -- e.g. more exact duplicates of the
+// k-th best row than the over-selection holds.  A warp owns rows w, w + W, ... in ascending
+// order (strict '>' admission is then exact) and keeps a sorted list of the KP best
+// (score, row) keys; about 40 instructions per lane and row: compute-bound (fp64 pipe), a few
+// times slower than the streaming scan, never wrong.
+constexpr int EXACT_THREADS = 256;
+constexpr int EXACT_WARPS = EXACT_THREADS / 32;
+
+template <int KPL>
+__global__ void __launch_bounds__(EXACT_THREADS)
+dense_exact_kernel(const uint16_t* __restrict__ emb, long long n_rows, int dim,
+                   const uint16_t* __restrict__ queries, const uint8_t* __restrict__ row_mask,
+                   KeyD* __restrict__ part) {
+  constexpr int KP = 32 * KPL;
+  __shared__ KeyD s_lists[EXACT_WARPS * KP];
+  __shared__ KeyD s_out[KP];
+  __shared__ double s_thr[EXACT_WARPS];
+  const int qi = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < EXACT_WARPS * KP; i += EXACT_THREADS) key_clear(s_lists[i]);
+  if (tid < EXACT_WARPS) s_thr[tid] = -INFINITY;
+  __syncthreads();
+  const uint16_t* q = queries + (size_t)qi * dim;
+  KeyD* w_list = s_lists + warp * KP;
+  volatile double* w_thr = s_thr + warp;
+  const long long w0 = (long long)blockIdx.x * EXACT_WARPS + warp;
+  const long long stride = (long long)gridDim.x * EXACT_WARPS;
+  bool full = false;
+  for (long long r = w0; r < n_rows; r += stride) {
+    if (row_mask != nullptr && row_mask[r] == 0) continue;  // warp-uniform
+    const double s = warp_exact_dot(q, emb + (size_t)r * dim, dim, lane);
+    if (full && !(s > *w_thr)) continue;
+    KeyD key;
+    key.s = s;
+    key.id = (u32)r;
+    key.pad = 0;
+    KeyD new_last;
+    key_clear(new_last);
+    if (warp_list_insert<KP, KeyD>(w_list, key, lane, new_last) && !key_empty(new_last)) {
+      full = true;
+      if (lane == 0) *w_thr = new_last.s;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < KP; i += EXACT_THREADS) key_clear(s_out[i]);
+  __syncthreads();
+  block_merge_lists<KP, KeyD>(s_lists, EXACT_WARPS, (size_t)KP, s_out, tid, EXACT_THREADS);
+  __syncthreads();
+  KeyD* dst = part + ((size_t)qi * gridDim.x + blockIdx.x) * KP;
+  for (int i = tid; i < KP; i += EXACT_THREADS) dst[i] = s_out[i];
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -353,6 +408,8 @@ static size_t scan_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k
   return (size_t)n_queries * p.grid_x * (32 * p.kpl) * sizeof(u64);
 }
 
+static size_t exact_workspace_bytes(int64_t n_rows, int n_queries, int k);
+
 extern "C" size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
   if (n_rows < 0 || dim <= 0 || dim % 8 != 0 || dim > 2048 || n_queries <= 0 || k <= 0 || k > CMR_MAX_K) {
     set_error("cmr_dense_workspace_bytes: bad shape");
@@ -365,6 +422,8 @@ extern "C" size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queri
     const size_t m = dense_mma_workspace_bytes(n_rows, dim, n_queries, k);
     if (m > need) need = m;
   }
+  const size_t e = exact_workspace_bytes(n_rows, n_queries, k);
+  if (e > need) need = e;
   return need;
 }
 
@@ -393,6 +452,44 @@ static int dense_scan_topk(const DenseArgs& a) {
   return CMR_OK;
 }
 
+static int exact_grid(long long n_rows) {
+  const int sms = sm_count();
+  if (sms <= 0) return -1;
+  long long ctas = (long long)sms * 8;
+  const long long max_ctas = (n_rows + EXACT_WARPS - 1) / EXACT_WARPS;
+  if (ctas > max_ctas) ctas = max_ctas;
+  return (int)(ctas < 1 ? 1 : ctas);
+}
+
+static size_t exact_workspace_bytes(int64_t n_rows, int n_queries, int k) {
+  const int kpl = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
+  const int g = exact_grid(n_rows);
+  return g < 0 ? 0 : (size_t)n_queries * g * (32 * kpl) * sizeof(KeyD);
+}
+
+static int dense_exact_topk(const DenseArgs& a) {
+  const int kpl = a.k <= 32 ? 1 : (a.k <= 64 ? 2 : 4);
+  const int g = exact_grid(a.n_rows);
+  if (g < 0) return CMR_ECUDA;
+  const size_t need = (size_t)a.n_queries * g * (32 * kpl) * sizeof(KeyD);
+  if (a.workspace_bytes < need || !a.workspace) {
+    set_error("workspace too small: %zu < %zu", a.workspace_bytes, need);
+    return CMR_EWORKSPACE;
+  }
+  CMR_CHECK_ARG(((uintptr_t)a.workspace % 16) == 0, "workspace must be 16-byte aligned");
+  CMR_CHECK_ARG(a.n_queries <= 65535, "exact scan takes at most 65535 queries per call");
+  KeyD* part = (KeyD*)a.workspace;
+  dim3 grid(g, a.n_queries);
+  if (kpl == 1) dense_exact_kernel<1><<<grid, EXACT_THREADS, 0, a.stream>>>(a.emb, a.n_rows, a.dim, a.queries, a.row_mask, part);
+  else if (kpl == 2) dense_exact_kernel<2><<<grid, EXACT_THREADS, 0, a.stream>>>(a.emb, a.n_rows, a.dim, a.queries, a.row_mask, part);
+  else dense_exact_kernel<4><<<grid, EXACT_THREADS, 0, a.stream>>>(a.emb, a.n_rows, a.dim, a.queries, a.row_mask, part);
+  int rc = launch_keyd_finalize(part, g, a.n_queries, kpl, a.row_offset, a.k, a.out_scores, a.out_ids, a.out_counts,
+                                a.out_flags, a.stream);
+  if (rc != CMR_OK) return rc;
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
 extern "C" int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim, const uint16_t* queries,
                                  int n_queries, int k, const uint8_t* row_mask, int64_t row_offset,
                                  double cert_eps, double* out_scores, int64_t* out_ids,
@@ -405,10 +502,12 @@ extern "C" int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim, c
   CMR_CHECK_ARG(queries && out_scores && out_ids && out_counts && out_flags, "null output/query pointer");
   CMR_CHECK_ARG(n_rows == 0 || emb, "null embedding matrix");
   CMR_CHECK_ARG(((uintptr_t)emb % 16) == 0 && ((uintptr_t)queries % 16) == 0, "emb/queries must be 16-byte aligned");
-  CMR_CHECK_ARG(algo == CMR_DENSE_AUTO || algo == CMR_DENSE_SCAN || algo == CMR_DENSE_MMA, "unknown algo %d", algo);
+  CMR_CHECK_ARG(algo == CMR_DENSE_AUTO || algo == CMR_DENSE_SCAN || algo == CMR_DENSE_MMA || algo == CMR_DENSE_EXACT,
+                "unknown algo %d", algo);
   DenseArgs a{emb, (long long)n_rows, dim, queries, n_queries, k, row_mask, (long long)row_offset, cert_eps,
               out_scores, (long long*)out_ids, out_counts, out_flags, workspace, workspace_bytes,
               (cudaStream_t)stream};
+  if (algo == CMR_DENSE_EXACT) return dense_exact_topk(a);
   const bool can_mma = dense_mma_eligible(n_rows, dim, n_queries, k, row_mask != nullptr);
   if (algo == CMR_DENSE_MMA && !can_mma) {
     set_error("tcgen05 path does not cover this shape (n_rows=%lld dim=%d B=%d k=%d mask=%d)",

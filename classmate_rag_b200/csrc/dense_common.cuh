@@ -88,6 +88,11 @@ struct DenseArgs {
   cudaStream_t stream;
 };
 
+// bm25.cu: select the k best (float64 score, id) keys over n_lists sorted lists per query
+int launch_keyd_finalize(const KeyD* part, int n_lists, int n_queries, int kpl, long long row_offset, int k,
+                         double* out_scores, long long* out_ids, int* out_counts, int* out_flags,
+                         cudaStream_t st);
+
 // dense_mma.cu
 bool dense_mma_eligible(long long n_rows, int dim, int n_queries, int k, bool has_mask);
 size_t dense_mma_workspace_bytes(long long n_rows, int dim, int n_queries, int k);

@@ -32,7 +32,8 @@ def device_info() -> Tuple[int, int, int]:
     return a.value, b.value, c.value
 
 
-_DENSE_ALGO = {"auto": _lib.CMR_DENSE_AUTO, "scan": _lib.CMR_DENSE_SCAN, "mma": _lib.CMR_DENSE_MMA}
+_DENSE_ALGO = {"auto": _lib.CMR_DENSE_AUTO, "scan": _lib.CMR_DENSE_SCAN, "mma": _lib.CMR_DENSE_MMA,
+                "exact": _lib.CMR_DENSE_EXACT}
 
 
 def f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
@@ -70,7 +71,8 @@ def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Op
     """Exact top-k of queries (bf16 [B, D]) against emb (bf16 [N, D]).
 
     algo: "auto" | "scan" (HBM-streaming mma.sync scan) | "mma" (tcgen05/TMA GEMM
-    with the top-k epilogue); see cmr_dense_topk_ex in include/cmrag.h.
+    with the top-k epilogue) | "exact" (exhaustive float64 scan, the fallback for
+    flagged queries); see cmr_dense_topk_ex in include/cmrag.h.
 
     Returns (scores f64 [B,k], ids i64 [B,k], counts i32 [B], flags i32 [B]) on
     the device, enqueued on the current stream (no synchronisation)."""
@@ -323,3 +325,19 @@ def shard_merge(gathered: torch.Tensor, pool: int, kb: int, dim: int):
                                                d_c.data_ptr(), d_f.data_ptr(), _ptr(rows), _ptr(b_s), _ptr(b_i),
                                                _ptr(b_c), _stream()))
     return d_s, d_i, d_c, d_f, rows, b_s, b_i, b_c
+
+
+def dense_topk_certified(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Optional[torch.Tensor] = None,
+                         row_offset: int = 0, cert_eps: Optional[float] = None,
+                         workspace: Optional[DenseWorkspace] = None):
+    """dense_topk, then the queries whose result could not be certified are re-run on the
+    exhaustive float64 scan and patched in place.  Synchronises (it reads the flags)."""
+    scores, ids, counts, flags = dense_topk(emb, queries, k, row_mask=row_mask, row_offset=row_offset,
+                                            cert_eps=cert_eps, workspace=workspace)
+    bad = torch.nonzero(flags).flatten()
+    if bad.numel():
+        q = queries[None, :] if queries.dim() == 1 else queries
+        s2, i2, c2, f2 = dense_topk(emb, q[bad].contiguous(), k, row_mask=row_mask, row_offset=row_offset,
+                                    algo="exact")
+        scores[bad], ids[bad], counts[bad], flags[bad] = s2, i2, c2, f2
+    return scores, ids, counts, flags

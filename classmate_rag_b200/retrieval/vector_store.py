@@ -228,7 +228,8 @@ class ChromaVectorStore:
         k = min(int(top_k), ops_max_k())
         if k <= 0:
             raise ValueError("top_k must be positive")
-        out = ops.dense_topk(col.matrix(), q, k, row_mask=mask, workspace=col.workspace(q.shape[0], k))
+        # flagged (uncertifiable) queries are re-run on the exhaustive float64 scan
+        out = ops.dense_topk_certified(col.matrix(), q, k, row_mask=mask, workspace=col.workspace(q.shape[0], k))
         return col, out
 
     def query(self, *, query_embeddings: np.ndarray, where: Optional[Dict[str, Any]] = None, top_k: int = 8,

@@ -20,8 +20,8 @@
  *     (oracle/np_oracle.py): a fast fp32 pass over-selects candidates, an exact
  *     float64 pass in a pinned order rescores them.  out_flags bit 0
  *     (CMR_FLAG_UNCERTIFIED) is set when the fp32 error bound could not prove
- *     the over-selection sufficient; callers then retry with cmr_*_exhaustive
- *     or a larger k.
+ *     the over-selection sufficient; callers then re-run those queries with
+ *     cmr_dense_topk_ex(..., CMR_DENSE_EXACT).
  *   - Return value: 0 on success, negative cmr_status otherwise; the message
  *     is available from cmr_last_error() (thread-local).
  */
@@ -91,11 +91,16 @@ int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
  *                   bound of the k-th best score), so both passes are exact.
  *                   CMR_EUNSUPPORTED when the shape is outside that path (row_mask given,
  *                   dim < 64, fewer than 256 rows).
+ *   CMR_DENSE_EXACT exhaustive scan that ranks on the exact float64 dot of EVERY row (fp64 pipe
+ *                   bound, a few times slower): nothing to certify, out_flags is always 0.
+ *                   The fallback for queries the fast paths flag CMR_FLAG_UNCERTIFIED.
  *   CMR_DENSE_AUTO  SCAN for <= 8 queries or masked calls, MMA above.
- * Results are bit-identical between the two (ids, order and float64 scores). */
+ * Results are bit-identical between all of them (ids, order and float64 scores) whenever the
+ * fast paths certify theirs. */
 #define CMR_DENSE_AUTO 0
 #define CMR_DENSE_SCAN 1
 #define CMR_DENSE_MMA 2
+#define CMR_DENSE_EXACT 3
 int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim,
                       const uint16_t* queries, int n_queries, int k,
                       const uint8_t* row_mask, int64_t row_offset, double cert_eps,

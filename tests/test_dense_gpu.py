@@ -223,3 +223,45 @@ def test_dense_mma_unsupported_shapes_raise():
     s, i, c, f = ops.dense_topk(emb, q, 4, row_mask=torch.ones(1000, dtype=torch.uint8, device="cuda"))  # auto -> scan
     torch.cuda.synchronize()
     assert (c.cpu().numpy() == 4).all()
+
+
+# ---- exhaustive exact scan (CMR_DENSE_EXACT) and the certified wrapper ----
+
+@pytest.mark.parametrize("n,d,k,b", [(20000, 768, 10, 3), (3000, 384, 24, 2), (2500, 8, 3, 2), (700, 64, 100, 1), (5, 64, 10, 2)])
+def test_dense_exact_scan_matches_oracle(n, d, k, b):
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(n * 3 + d)
+    bits = _corpus(rng, n, d, dup_every=100 if n > 200 else 0)
+    qbits = _queries(rng, bits, b)
+    mask = (rng.random(n) < 0.5).astype(np.uint8) if n > 1000 else None
+    m = None if mask is None else torch.from_numpy(mask).cuda()
+    s, i, c, f = ops.dense_topk(_to_dev(bits), _to_dev(qbits), k, row_mask=m, row_offset=77, algo="exact")
+    torch.cuda.synchronize()
+    s, i, c, f = s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy(), f.cpu().numpy()
+    for bb in range(b):
+        want_ids, want_sc = o.dense_topk(qbits[bb], bits, k, mask=mask, row_offset=77)
+        nn = len(want_ids)
+        assert c[bb] == nn and f[bb] == 0
+        assert i[bb, :nn].tolist() == want_ids.tolist() and s[bb, :nn].tobytes() == want_sc.tobytes()
+        assert (i[bb, nn:] == -1).all()
+
+
+def test_certified_wrapper_resolves_flagged_queries():
+    """5000 identical rows: both fast paths must flag; the wrapper re-runs the query on the
+    exhaustive scan and returns the certified answer (ties in ascending row order)."""
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(3)
+    bits = np.repeat(_corpus(rng, 1, 128), 5000, axis=0)
+    other = _corpus(rng, 3000, 128)
+    allb = np.concatenate([other[:1500], bits, other[1500:]])
+    q = np.concatenate([bits[:1], _queries(rng, other, 2)])          # query 0 hits the duplicates
+    for nq in (3, 12):                                               # scan path / tcgen05 path
+        qq = np.concatenate([q] * (nq // 3))
+        s, i, c, f = ops.dense_topk_certified(_to_dev(allb), _to_dev(qq), 10)
+        torch.cuda.synchronize()
+        assert int(f.sum()) == 0
+        for bb in range(qq.shape[0]):
+            want_ids, want_sc = o.dense_topk(qq[bb], allb, 10)
+            assert i[bb].cpu().numpy().tolist() == want_ids.tolist()
+            assert s[bb].cpu().numpy().tobytes() == want_sc.tobytes()
+        assert i[0].cpu().numpy().tolist() == list(range(1500, 1510))
