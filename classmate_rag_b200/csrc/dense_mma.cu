@@ -385,6 +385,36 @@ dense_thresh_kernel(const float* __restrict__ gmax, int n_groups, int gstride, i
   if (tid == 0) thr[q] = orderable_f32(prefix);
 }
 
+// Same bound, one WARP per query (8 queries per CTA) for up to 4096 groups: the maxima are
+// staged in the warp's slice of shared memory (conflict-free lane-strided reads) and the 32
+// bisection rounds need no block barrier -- this sits on the critical path of every batch.
+constexpr int THR_WARPS = 8;
+constexpr int THR_WARP_MAX_GROUPS = 4096;
+
+__global__ void __launch_bounds__(THR_WARPS * 32)
+dense_thresh_warp_kernel(const float* __restrict__ gmax, int n_groups, int gstride, int kp, int n_queries,
+                         float* __restrict__ thr) {
+  extern __shared__ u32 s_vals[];  // [THR_WARPS][n_groups]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * THR_WARPS + warp;
+  if (q >= n_queries) return;
+  if (n_groups < kp) {
+    if (lane == 0) thr[q] = -INFINITY;
+    return;
+  }
+  u32* v = s_vals + (size_t)warp * n_groups;
+  for (int g = lane; g < n_groups; g += 32) v[g] = f32_orderable(gmax[(size_t)g * gstride + q]);
+  __syncwarp();
+  u32 prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const u32 c = prefix | (1u << bit);
+    int local = 0;
+    for (int g = lane; g < n_groups; g += 32) local += v[g] >= c;
+    if (__reduce_add_sync(0xFFFFFFFFu, local) >= kp) prefix = c;
+  }
+  if (lane == 0) thr[q] = orderable_f32(prefix);
+}
+
 // One CTA per query: collect the query's candidates from every CTA's private list, take the KP
 // best (unique keys, ranked by counting), then the shared exact rescoring tail.  A list or the
 // collection buffer that overflowed -> CMR_FLAG_UNCERTIFIED.
@@ -579,6 +609,9 @@ static int mma_opt_in() {
       e = cudaFuncSetAttribute(dense_mma_kernel<MM_NEARDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(dense_thresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_MAX_GROUPS * 4);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_thresh_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               THR_WARPS * THR_WARP_MAX_GROUPS * 4);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_mma)");
     attr_dev_mask |= (1 << dev);
   }
@@ -635,8 +668,12 @@ int dense_mma_topk(const DenseArgs& a) {
     kp.rows_evict_first = 0;
     dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, smem_bytes, a.stream>>>(tm_q, tm_rows, kp);
   }
-  dense_thresh_kernel<<<a.n_queries, 256, (size_t)(p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
-      gmax, p.n_groups, p.bpad, p.kp, thr);
+  if (p.n_groups <= THR_WARP_MAX_GROUPS)
+    dense_thresh_warp_kernel<<<(a.n_queries + THR_WARPS - 1) / THR_WARPS, THR_WARPS * 32,
+                               (size_t)THR_WARPS * (p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
+        gmax, p.n_groups, p.bpad, p.kp, a.n_queries, thr);
+  else
+    dense_thresh_kernel<<<a.n_queries, 256, (size_t)p.n_groups * 4, a.stream>>>(gmax, p.n_groups, p.bpad, p.kp, thr);
   {
     const int grid = p.n_lists;
     kp.n_outer = p.n_tiles;

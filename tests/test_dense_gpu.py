@@ -265,3 +265,22 @@ def test_certified_wrapper_resolves_flagged_queries():
             assert i[bb].cpu().numpy().tolist() == want_ids.tolist()
             assert s[bb].cpu().numpy().tobytes() == want_sc.tobytes()
         assert i[0].cpu().numpy().tolist() == list(range(1500, 1510))
+
+
+def test_dense_mma_many_groups_block_bound_kernel():
+    """k = 100 (KP = 128) over 2.5M rows: 610 sampled tiles x 8 groups = 4880 group maxima,
+    more than one warp stages -> the block-wide bound kernel.  Checked against the scan path
+    (and the oracle on one query)."""
+    from classmate_rag_b200 import ops
+    n, d, k, b = 2_500_000, 64, 100, 9
+    g = torch.Generator(device="cuda").manual_seed(11)
+    emb = torch.nn.functional.normalize(torch.randn((n, d), generator=g, device="cuda"), dim=1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(emb[:b].float() + 0.3 * torch.randn((b, d), generator=g, device="cuda") / d ** 0.5,
+                                      dim=1).to(torch.bfloat16)
+    s, i, c, f = [t.clone() for t in ops.dense_topk(emb, q, k, algo="mma")]
+    s2, i2, c2, f2 = ops.dense_topk(emb, q, k, algo="scan")
+    torch.cuda.synchronize()
+    assert int(f.sum()) == 0 and torch.equal(i, i2) and s.cpu().numpy().tobytes() == s2.cpu().numpy().tobytes()
+    bits = emb.view(torch.int16).cpu().numpy().view(np.uint16)
+    want_ids, want_sc = o.dense_topk(q[0].view(torch.int16).cpu().numpy().view(np.uint16), bits, k)
+    assert i[0].cpu().numpy().tolist() == want_ids.tolist() and s[0].cpu().numpy().tobytes() == want_sc.tobytes()
