@@ -129,6 +129,8 @@ __device__ __forceinline__ void block_merge_lists(const K* lists, int n_lists, s
   }
 }
 
+constexpr int SELECT_RANK_LISTS = 512;
+
 // Select the KP best keys out of n_lists sorted lists held in GLOBAL memory.
 //   s_heads [n_lists + 1] scratch   s_buf [CAP] scratch   s_cnt [1] scratch
 //   s_out   [KP] result, sorted best first, empties last
@@ -149,11 +151,15 @@ __device__ void block_select_from_lists(const K* __restrict__ lists, int n_lists
   }
   __syncthreads();
   if (n_lists > KP) {
-    for (int i = tid; i < n_lists; i += nthreads) {
+    // Ranking the heads against each other is quadratic: with very many lists only the first
+    // SELECT_RANK_LISTS heads are ranked.  Their KP-th best is still attained by KP distinct
+    // keys, so it is still a valid (slightly lower) bound.
+    const int n_rank = n_lists < SELECT_RANK_LISTS ? n_lists : SELECT_RANK_LISTS;
+    for (int i = tid; i < n_rank; i += nthreads) {
       const K h = s_heads[i];
       if (key_empty(h)) continue;
       int cnt = 0;
-      for (int j = 0; j < n_lists; ++j) cnt += key_gt(s_heads[j], h);
+      for (int j = 0; j < n_rank; ++j) cnt += key_gt(s_heads[j], h);
       if (cnt == KP - 1) s_heads[n_lists] = h;  // unique keys: exactly one writer
     }
     __syncthreads();

@@ -20,7 +20,7 @@ import torch
 BM25_K1 = 1.5
 BM25_B = 0.75
 BM25_EPS = 0.25
-DEFAULT_TILE_DOCS = 8192
+DEFAULT_TILE_DOCS = 2048   # 16 documents per thread of a 128-thread CTA (csrc/bm25.cu)
 DENSE_DENSITY = 0.125    # terms in at least this share of the documents get a factor column
 DENSE_MAX_TERMS = 64     # 8 B x n_docs each
 

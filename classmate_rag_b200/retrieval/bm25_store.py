@@ -60,7 +60,7 @@ class _DeviceIndex:
                 sub_tok = tokens[:0]
         n_docs = len(rows)
         tile = 512
-        while tile < 8192 and tile * 4 < n_docs:
+        while tile < 2048 and tile * 4 < n_docs:
             tile *= 2
         self.lex = lexical.build_lexical_index(sub_ptr, sub_tok, max(n_terms, 1), device=device, tile_docs=tile)
         self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}

@@ -8,7 +8,7 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 doc_ptr, tokens = synth.lexical_corpus(n, 30000, 64, "cuda")
 import os
-lex = lexical.build_lexical_index(doc_ptr, tokens, 30000, tile_docs=int(os.environ.get("TILE", "8192")))
+lex = lexical.build_lexical_index(doc_ptr, tokens, 30000, tile_docs=int(os.environ.get("TILE", str(lexical.DEFAULT_TILE_DOCS))))
 del doc_ptr, tokens
 terms = synth.lexical_queries(b, 30000)
 qt, qp = lexical.pack_queries(terms)
