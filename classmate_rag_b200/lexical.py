@@ -270,3 +270,57 @@ def pack_queries(queries: Sequence[Sequence[int]]):
     if flat.size == 0:
         flat = np.zeros(1, dtype=np.int32)  # keep a valid device pointer
     return torch.from_numpy(flat), torch.from_numpy(ptr)
+
+
+# --------------------------------------------------------------------------
+# N2: binary snapshot of a built index (replaces the per-ask JSONL re-parse +
+# BM25Okapi rebuild of the reference, rag/retrieval/bm25.py:220-248, rag/pipeline/rag.py:532)
+# --------------------------------------------------------------------------
+_SNAPSHOT_TENSORS = ("term_ptr", "tile_skip", "post_doc", "post_imp", "post_tf", "doc_len", "idf", "post_pack",
+                     "imp_table", "pair_tf", "pair_dl", "dense_imp", "dense_slot")
+_SNAPSHOT_VERSION = 1
+
+
+def save_lexical_index(ix: LexicalIndex, path) -> None:
+    """Write the index as one .npy file per array plus meta.json (loadable with mmap)."""
+    import json
+    from pathlib import Path
+    path = Path(path)
+    path.mkdir(parents=True, exist_ok=True)
+    present = []
+    for name in _SNAPSHOT_TENSORS:
+        t = getattr(ix, name)
+        if t is not None:
+            np.save(path / f"{name}.npy", t.detach().cpu().numpy())
+            present.append(name)
+    for name in ("idf_host", "df_host", "shard_df_host", "dense_terms"):
+        a = getattr(ix, name)
+        if a is not None:
+            np.save(path / f"{name}.npy", np.asarray(a))
+            present.append(name)
+    meta = {"version": _SNAPSHOT_VERSION, "n_docs": ix.n_docs, "n_terms": ix.n_terms, "tile_docs": ix.tile_docs,
+            "n_tiles": ix.n_tiles, "avgdl_hex": float(ix.avgdl).hex(), "k1_hex": float(ix.k1).hex(),
+            "b_hex": float(ix.b).hex(), "arrays": present}
+    (path / "meta.json").write_text(json.dumps(meta))
+
+
+def load_lexical_index(path, device) -> LexicalIndex:
+    """Inverse of save_lexical_index: arrays go straight to ``device`` (no rebuild)."""
+    import json
+    from pathlib import Path
+    path = Path(path)
+    meta = json.loads((path / "meta.json").read_text())
+    if meta.get("version") != _SNAPSHOT_VERSION:
+        raise ValueError(f"unsupported lexical snapshot version {meta.get('version')}")
+    kw = {}
+    for name in meta["arrays"]:
+        a = np.load(path / f"{name}.npy", mmap_mode="r")
+        if name in _SNAPSHOT_TENSORS:
+            kw[name] = torch.from_numpy(np.array(a)).to(device)
+        else:
+            kw[name] = np.array(a)
+    for name in _SNAPSHOT_TENSORS:
+        kw.setdefault(name, None)
+    return LexicalIndex(n_docs=int(meta["n_docs"]), n_terms=int(meta["n_terms"]), tile_docs=int(meta["tile_docs"]),
+                        n_tiles=int(meta["n_tiles"]), avgdl=float.fromhex(meta["avgdl_hex"]),
+                        k1=float.fromhex(meta["k1_hex"]), b=float.fromhex(meta["b_hex"]), **kw)

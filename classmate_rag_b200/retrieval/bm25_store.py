@@ -41,9 +41,13 @@ class _DeviceIndex:
     """Inverted index of a list of entries (the whole store or a filtered subset)."""
 
     def __init__(self, rows: Sequence[int], doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: int,
-                 all_doc_ptr_host: np.ndarray, device):
+                 all_doc_ptr_host: np.ndarray, device, lex: Optional["lexical.LexicalIndex"] = None):
         # rows: positions (in store order) of the documents this index covers
         self.rows = np.asarray(rows, dtype=np.int64)
+        self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
+        if lex is not None:     # loaded from a snapshot
+            self.lex = lex
+            return
         if len(rows) == all_doc_ptr_host.shape[0] - 1:
             sub_ptr, sub_tok = doc_ptr, tokens
         else:
@@ -63,7 +67,6 @@ class _DeviceIndex:
         while tile < 2048 and tile * 4 < n_docs:
             tile *= 2
         self.lex = lexical.build_lexical_index(sub_ptr, sub_tok, max(n_terms, 1), device=device, tile_docs=tile)
-        self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
 
 
 @dataclass
@@ -81,6 +84,9 @@ class BM25Store:
     _dirty: bool = field(default=True, repr=False)
     _dev_tokens: Optional[Tuple[torch.Tensor, torch.Tensor, np.ndarray]] = field(default=None, repr=False)
     _gids: Optional[torch.Tensor] = field(default=None, repr=False)
+    loaded_from_snapshot: bool = field(default=False, repr=False)
+    device_tokenize_from: int = 64          # batches of at least this many queries are tokenised on the device
+    _tokenizer: Any = field(default=None, repr=False)
 
     # ---------- core ops ----------
     def _rebuild(self) -> None:
@@ -90,6 +96,8 @@ class BM25Store:
         self._dirty = True
         self._full = None
         self._subsets.clear()
+        self.loaded_from_snapshot = False
+        self._tokenizer = None
 
     def _ensure_index(self) -> None:
         if not self._dirty and self._full is not None:
@@ -97,6 +105,8 @@ class BM25Store:
         if not torch.cuda.is_available():
             raise RuntimeError("BM25Store needs a CUDA device: classmate_rag_b200 has no CPU path")
         dev = torch.device(self.device)
+        if self._load_snapshot(dev):
+            return
         vocab = self._vocab
         lens = np.zeros(len(self._id_list), dtype=np.int64)
         flat: List[int] = []
@@ -188,8 +198,18 @@ class BM25Store:
         k = min(int(top_k), _lib.CMR_MAX_K)
         if k <= 0:
             raise ValueError("top_k must be positive")
-        qt, qp = lexical.pack_queries([self._query_terms(q) for q in queries])
         dev = torch.device(self.device)
+        if len(queries) >= self.device_tokenize_from:
+            # large batches: tokenise on the device (the language tag is still decided here)
+            if self._tokenizer is None:
+                from .device_tokenizer import DeviceTokenizer
+                self._tokenizer = DeviceTokenizer(self._vocab, dev)
+            longest = max(len(q.encode("utf-8")) for q in queries)
+            qt, qp, _ = self._tokenizer(queries, langs=[detect_lang_tag(q) for q in queries],
+                                        max_terms=max(8, (longest + 1) // 3 + 1))
+        else:
+            qt, qp = lexical.pack_queries([self._query_terms(q) for q in queries])
+            qt, qp = qt.to(dev), qp.to(dev)
         key = (len(queries), k)
         buf = ix.buffers.get(key)
         if buf is None:
@@ -200,7 +220,7 @@ class BM25Store:
             if nbytes == 0:
                 raise ValueError("unsupported bm25 shape: " + _lib.last_error())
             buf = ix.buffers[key] = ops.TopkBuffers(len(queries), k, nbytes, dev)
-        sc, docs, cnt, _ = ops.bm25_topk(ix.lex, qt.to(dev), qp.to(dev), k, buffers=buf)
+        sc, docs, cnt, _ = ops.bm25_topk(ix.lex, qt, qp, k, buffers=buf)
         return ix, sc, docs, cnt
 
     def search(self, *, query: str, where: Optional[Mapping[str, Any]] = None, top_k: int = 8) -> List[Dict[str, Any]]:
@@ -244,6 +264,58 @@ class BM25Store:
             for e in self._entries.values():
                 f.write(json.dumps({"id": e.id, "text": e.text, "tokens": e.tokens, "metadata": e.metadata},
                                    ensure_ascii=False) + "\n")
+        if self._entries and torch.cuda.is_available():
+            self._save_snapshot()
+
+    # Binary sidecar of the device index (N2): the next process loads the arrays instead of
+    # re-deriving them from the token lists.  Valid only for exactly this JSONL file.
+    @property
+    def snapshot_path(self) -> Path:
+        return Path(self.index_dir) / (self.index_file + ".cmrag")
+
+    def _jsonl_stamp(self):
+        st = self.index_path.stat()
+        return [int(st.st_size), int(st.st_mtime_ns)]
+
+    def _save_snapshot(self) -> None:
+        self._ensure_index()
+        snap = self.snapshot_path
+        lexical.save_lexical_index(self._full.lex, snap)
+        doc_ptr, tokens, _ = self._dev_tokens
+        np.save(snap / "corpus_doc_ptr.npy", doc_ptr.cpu().numpy())
+        np.save(snap / "corpus_tokens.npy", tokens.cpu().numpy())
+        words = [None] * len(self._vocab)
+        for w, n in self._vocab.items():
+            words[n] = w
+        (snap / "store.json").write_text(json.dumps({"jsonl": self._jsonl_stamp(), "n_entries": len(self._id_list),
+                                                     "vocab": words}, ensure_ascii=False), encoding="utf-8")
+
+    def _load_snapshot(self, dev) -> bool:
+        snap = self.snapshot_path
+        try:
+            if not (snap / "store.json").exists() or not self.index_path.exists():
+                return False
+            info = json.loads((snap / "store.json").read_text(encoding="utf-8"))
+            if info.get("jsonl") != self._jsonl_stamp() or info.get("n_entries") != len(self._id_list):
+                return False
+            lex = lexical.load_lexical_index(snap, dev)
+            if lex.n_docs != len(self._id_list):
+                return False
+            ptr = np.load(snap / "corpus_doc_ptr.npy")
+            tokens = torch.from_numpy(np.load(snap / "corpus_tokens.npy")).to(dev)
+        except Exception:
+            return False
+        self._vocab = {w: n for n, w in enumerate(info["vocab"])}
+        self._dev_tokens = (torch.from_numpy(ptr).to(dev), tokens, ptr)
+        self._columns = MetaColumns(dev)
+        self._columns.reset([self._entries[c].metadata for c in self._id_list])
+        self._gids = torch.tensor([REGISTRY.intern(c) for c in self._id_list], dtype=torch.int64, device=dev)
+        self._full = _DeviceIndex(range(len(self._id_list)), self._dev_tokens[0], tokens, len(self._vocab), ptr, dev,
+                                  lex=lex)
+        self._subsets.clear()
+        self._dirty = False
+        self.loaded_from_snapshot = True
+        return True
 
     def load(self) -> None:
         self._entries.clear()

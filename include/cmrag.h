@@ -257,6 +257,36 @@ int cmr_shard_merge(const void* gathered, int n_parts, int n_queries, int pool, 
                     cmr_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * N3  Query tokeniser on the device (rag/retrieval/bm25.py:34-70,194-195): letter runs of
+ *     [A-Za-z] + U+00C0..U+00FF (without U+00D7 / U+00F7), lower-cased, one-character tokens
+ *     and the stopwords of the query's language dropped, the rest mapped to term ids (-1 =
+ *     not in the vocabulary).  The dictionary is an open-addressing hash table (capacity a
+ *     power of two, 64-bit FNV-1a of the lower-cased UTF-8 bytes, slot = (fp ^ fp >> 32) &
+ *     (capacity - 1), linear probing, len < 0 = empty slot) over the vocabulary and both
+ *     stopword lists; hits are verified byte by byte against `pool`.
+ *       flags bit 0: English stopword, bit 1: Italian stopword; val: term id or -1.
+ *     text: the queries' UTF-8 bytes back to back, text_ptr int64 [n_queries + 1];
+ *     lang_it uint8 [n_queries] (1 = Italian stopword list) or NULL (all English);
+ *     out_terms int32 [n_queries, max_terms], padded with -1 (cmr_bm25_topk ignores -1, so
+ *     with q_ptr[b] = b * max_terms this is its q_terms input); out_counts int32 [n_queries]
+ *     = tokens found (> max_terms means the query was truncated).  All pointers device memory.
+ * ---------------------------------------------------------------------- */
+typedef struct cmr_token_table {
+  const uint64_t* fp;    /* [capacity] */
+  const int32_t* off;    /* [capacity] byte offset of the string in pool */
+  const int32_t* len;    /* [capacity] byte length, -1 = empty slot */
+  const int32_t* val;    /* [capacity] term id or -1 */
+  const uint8_t* flags;  /* [capacity] */
+  const uint8_t* pool;   /* lower-cased UTF-8 strings */
+  int32_t capacity;
+  int32_t reserved_;
+} cmr_token_table;
+
+int cmr_tokenize_queries(const uint8_t* text, const int64_t* text_ptr, const uint8_t* lang_it,
+                         int n_queries, const cmr_token_table* table, int max_terms,
+                         int32_t* out_terms, int32_t* out_counts, cmr_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * A9 / K6  Near-duplicate cosine filter over the embedding matrix (extension used by
  *     `rag rebuild`; greedy keep-first rule of rag/utils/dedup.py:40-55: row i is kept iff
  *     no previously KEPT row j < i has q.c >= threshold; hook rag/admin/backup.py:226-233).

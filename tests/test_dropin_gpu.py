@@ -160,3 +160,69 @@ def test_expand_uses_store_catalog(world, golden):
             assert [[x["id"], x["score"]] for x in out] == [[i, unhex(s)] for i, s in case["out"]]
     finally:
         ex.use_catalog(None)
+
+
+def test_bm25store_snapshot_reload_gives_identical_results(world, golden, tmp_path):
+    """N2: save() leaves a binary sidecar of the device index; a new process-like store loads it
+    (no rebuild) and answers exactly as before; a changed JSONL invalidates it."""
+    from classmate_rag_b200.retrieval import BM25Store
+    c = world[2]
+    a = BM25Store(index_dir=tmp_path / "bm25")
+    a.upsert_many(ids=c["ids"], texts=c["docs"], metadatas=c["metas"])
+    a.save()
+    assert (a.snapshot_path / "meta.json").exists()
+    b = BM25Store.load_or_create(tmp_path / "bm25")
+    cases = golden["bm25_search"][:40]
+    for case in cases:
+        res = b.search(query=case["query"], where=case["where"], top_k=case["top_k"])
+        assert [[x["id"], x["score"]] for x in res] == [[i, unhex(s)] for i, s in case["out"]]
+    assert b.loaded_from_snapshot
+    b.upsert_many(ids=["new"], texts=["gradient descent gradient"], metadatas=[{"language": "en"}])
+    assert not b.loaded_from_snapshot and b.search(query="gradient", top_k=100)[0]["id"] is not None
+    # a JSONL that no longer matches the sidecar: rebuilt from the token lists
+    with a.index_path.open("a", encoding="utf-8") as f:
+        f.write('{"id": "extra", "text": "kernel kernel", "tokens": ["kernel", "kernel"], "metadata": {"language": "en"}}\n')
+    d = BM25Store.load_or_create(tmp_path / "bm25")
+    assert d.count() == len(c["ids"]) + 1
+    assert d.search(query="kernel", top_k=3)[0]["id"] == "extra" and not d.loaded_from_snapshot
+
+
+def test_device_tokenizer_matches_host_tokenizer(golden):
+    """N3: cmr_tokenize_queries == tokenize() + vocabulary lookup, for both stopword lists,
+    accented letters, the two excluded signs, other scripts, empty and truncated queries."""
+    from classmate_rag_b200.retrieval.device_tokenizer import DeviceTokenizer
+    from classmate_rag_b200.retrieval.text import tokenize
+    texts = sorted({c["text"] for c in golden["tokenize"]}) + [
+        "ÀÉÎÕÜ Þorn ßtraße ÿes ×no÷ yes×no", "日本語 text mixed 한국어 and emoji 🙂 ok", "école école ÉCOLE",
+        "a b c I x", "come dove quando the of and perché PERCHÉ", "x" * 300 + " tail", "",
+        "gradient descent kernel memory bandwidth cache latency pipeline fusion retrieval ranking lexical dense"]
+    rng = np.random.default_rng(0)
+    alphabet = list("abcXYZ éÈñ×÷ß-_'1 ") + ["ÿ", "À", "Ā", "€"]
+    texts += ["".join(rng.choice(alphabet, size=int(rng.integers(0, 60)))) for _ in range(300)]
+    words = sorted({t for x in texts for t in tokenize(x, "en")} | {t for x in texts for t in tokenize(x, "it")})
+    vocab = {w: i for i, w in enumerate(words) if i % 3 != 0}          # a third of the words stays unknown
+    vocab["come"] = len(words) + 1                                     # a term that is an Italian stopword
+    tok = DeviceTokenizer(vocab, "cuda")
+    for lang in ("en", "it", None):
+        langs = None if lang is None else [lang] * len(texts)
+        q_terms, q_ptr, counts = tok(texts, langs=langs, max_terms=24)
+        q_terms, q_ptr, counts = q_terms.cpu().numpy(), q_ptr.cpu().numpy(), counts.cpu().numpy()
+        assert q_ptr.tolist() == [24 * i for i in range(len(texts) + 1)]
+        for i, x in enumerate(texts):
+            want = [vocab.get(t, -1) for t in tokenize(x, lang)]
+            assert counts[i] == len(want), (x, lang)
+            row = q_terms[24 * i: 24 * (i + 1)].tolist()
+            assert row[: min(len(want), 24)] == want[:24], (x, lang)
+            assert all(v == -1 for v in row[len(want):])
+
+
+def test_bm25store_batch_on_device_tokenizer_equals_host_path(world, golden):
+    store = world[0]
+    queries = [c["query"] for c in golden["bm25_search"]][:80] + ["Gradient DESCENT kernel", "memória ×bandwidth÷"]
+    want = [store.search(query=q, top_k=8) for q in queries]
+    store.device_tokenize_from = 1
+    try:
+        got = store.search_batch(queries=queries, top_k=8)
+    finally:
+        store.device_tokenize_from = 64
+    assert got == want

@@ -93,3 +93,22 @@ def test_dense_columns_hold_the_posting_factors():
     # algorithmic bytes: a dense token streams its 8-byte column, a sparse one its 4-byte postings
     t_dense, t_sparse = int(ix.dense_terms[0]), int(np.argmin(np.where(df > 0, df, 1 << 30)))
     assert ix.posting_bytes([t_dense, t_sparse, -1]) == 8 * 900 + 4 * int(df[t_sparse])
+
+
+def test_snapshot_round_trip(tmp_path):
+    """N2: save -> load gives the same arrays, scalars (bit for bit) and C struct."""
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=7, n_docs=1300, vocab=80, mean_len=10)
+    for kw in ({}, {"fmt": "wide", "dense_density": None}):
+        ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cpu", tile_docs=512, **kw)
+        lexical.save_lexical_index(ix, tmp_path / "snap")
+        back = lexical.load_lexical_index(tmp_path / "snap", "cpu")
+        assert (back.n_docs, back.n_terms, back.tile_docs, back.n_tiles) == (ix.n_docs, ix.n_terms, ix.tile_docs, ix.n_tiles)
+        assert back.avgdl == ix.avgdl and back.k1 == ix.k1 and back.b == ix.b
+        for name in lexical._SNAPSHOT_TENSORS:
+            a, b = getattr(ix, name), getattr(back, name)
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert a.dtype == b.dtype and torch.equal(a, b), name
+        assert np.array_equal(back.idf_host, ix.idf_host) and np.array_equal(back.shard_df_host, ix.shard_df_host)
+        assert back.struct().n_dense == ix.struct().n_dense and back.struct().n_codes == ix.struct().n_codes
+        assert back.posting_bytes([0, 1, 5]) == ix.posting_bytes([0, 1, 5])
