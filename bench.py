@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--cpu-sample-rows", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--latency-iters", type=int, default=200)
+    ap.add_argument("--latency-iters", type=int, default=1000)
+    ap.add_argument("--no-c2", action="store_true", help="skip the C2 side measurement (1M x 768 dense, B=1 / B=1024)")
     return ap.parse_args()
 
 
@@ -178,7 +179,7 @@ def main():
     import torch
     import torch.distributed as dist
     from classmate_rag_b200 import lexical, ops, sharding, synth
-    from classmate_rag_b200.engine import GraphedSearch, HybridEngine, SearchParams
+    from classmate_rag_b200.engine import GraphedSearch, HybridEngine, PipelinedSearch, SearchParams
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,19 +257,22 @@ def main():
     ms_per_step = total_ms / a.steps
     value = a.batch * a.steps / (total_ms * 1e-3)
 
-    # ---- per-stage device time (same steps again, events around the two scans) ---
+    # ---- per-stage device time: the same steps again, each stage back to back between two
+    # events (the queue stays full, so host launch latency is not part of the number) ----------
     pool = p.pool
-    for s in range(a.warmup, n_steps):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(stream)
-        eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool)
-        e[1].record(stream)
-        e[2].record(stream)
-        eng.lexical_topk(*dev_terms[s], p.k_bm25)
-        e[3].record(stream)
+
+    def stage_ms(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(a.warmup)                      # one untimed call: buffers of this shape exist
         torch.cuda.synchronize()
-        dense_ms.append(e[0].elapsed_time(e[1]))
-        lex_ms.append(e[2].elapsed_time(e[3]))
+        e0.record(stream)
+        for s in range(a.warmup, n_steps):
+            fn(s)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / a.steps
+    dense_ms = [stage_ms(lambda s: eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool))]
+    lex_ms = [stage_ms(lambda s: eng.lexical_topk(*dev_terms[s], p.k_bm25))]
     clock_info = clocks.stop()
     dense_avg = float(np.mean(dense_ms))
     lex_avg = float(np.mean(lex_ms))
@@ -305,40 +309,86 @@ def main():
 
     # ---- e2e: host buffers in, host results out, every step ---------------------
     q_host = q_f32.cpu().numpy()
-    gs = GraphedSearch(eng, p, a.batch, max_terms=16)
+    gs = PipelinedSearch(eng, p, a.batch, max_terms=16)
     for s in range(a.warmup):
-        gs(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+        gs.submit(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+    gs.drain()
     barrier()
     t0 = time.perf_counter()
     last = None
     for s in range(a.warmup, n_steps):
-        last = gs(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+        # every step: pinned host inputs -> H2D -> graph replay -> D2H; the host stages step s+1
+        # while the device runs step s (results of step s-1 are handed back by this call)
+        got = gs.submit(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
+        last = got if got is not None else last
+    last = gs.drain()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": a.batch * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": gs.h2d_bytes,
            "d2h_bytes_per_step": gs.d2h_bytes, "ms_per_step": e2e_s / a.steps * 1e3,
-           "path": "GraphedSearch: pinned host queries -> H2D -> CUDA-graph replay of the kernel sequence -> D2H results"}
+           "path": "PipelinedSearch: pinned host queries -> H2D -> CUDA-graph replay of the kernel sequence -> D2H "
+                   "results, every step; two graph slots so the host stages step s+1 while the device runs step s"}
     # sanity on the last batch: the planted row is the dense top-1 unless MMR/RRF reorder it out of the top-10
     ids_last = last[0]
     planted_last = planted[(n_steps - 1) * a.batch:].numpy()
     hit = float(np.mean([planted_last[i] in ids_last[i] for i in range(a.batch)]))
 
-    # ---- single-query latency (B=1), end to end ----------------------------------
+    # ---- single-query latency (B=1), end to end: host clock and CUDA events -----------------
     g1 = GraphedSearch(eng, p, 1, max_terms=16)
-    lat = []
-    for i in range(min(20, nq)):
-        g1(q_host[i:i + 1], [terms[i]])
+    lat, lat_dev = [], []
+    for i in range(min(50, max(nq, 1) * 4)):
+        g1(q_host[i % nq:i % nq + 1], [terms[i % nq]])
     barrier()
     for i in range(a.latency_iters):
         j = i % nq
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t1 = time.perf_counter()
-        g1(q_host[j:j + 1], [terms[j]])
+        g1.set_queries(q_host[j:j + 1], [terms[j]])
+        d0.record(g1.stream)
+        g1.launch()
+        d1.record(g1.stream)
+        g1.stream.synchronize()
         lat.append((time.perf_counter() - t1) * 1e3)
-    lat = np.array(lat)
+        lat_dev.append(d0.elapsed_time(d1))
+    lat, lat_dev = np.array(lat), np.array(lat_dev)
     latency = {"batch": 1, "iters": int(a.latency_iters), "p50_ms": float(np.percentile(lat, 50)),
                "p95_ms": float(np.percentile(lat, 95)), "p99_ms": float(np.percentile(lat, 99)),
+               "device_p50_ms": float(np.percentile(lat_dev, 50)), "device_p99_ms": float(np.percentile(lat_dev, 99)),
                "qps_serial": float(1e3 / np.mean(lat)),
                "hbm_frac_at_p50": (hi - lo) * a.dim * 2 / (float(np.percentile(lat, 50)) * 1e-3) / 1e9 / hbm_peak}
+
+    # ---- side measurement, BASELINE config C2: 1M x 768 exact dense top-10, batch 1 and 1024 ----
+    c2 = None
+    if world == 1 and not a.no_c2:
+        peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        n2, b2 = 1_000_000, 1024
+        emb2 = synth.dense_corpus(n2, a.dim, dev)
+        q2 = ops.f32_to_bf16(synth.dense_queries(n2, a.dim, b2, dev)[0])
+
+        def timed(qb, algo, iters=20):
+            ws = ops.DenseWorkspace(n2, a.dim, qb.shape[0], TOP_K, dev)
+            for _ in range(3):
+                ops.dense_topk(emb2, qb, TOP_K, workspace=ws, algo=algo)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            ev[0].record(stream)
+            for i in range(iters):
+                ops.dense_topk(emb2, qb, TOP_K, workspace=ws, algo=algo)
+                ev[i + 1].record(stream)
+            torch.cuda.synchronize()
+            return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]))
+        t_b1 = timed(q2[:1], "scan")
+        t_b1024 = timed(q2, "mma")
+        flops = 2.0 * b2 * n2 * a.dim
+        c2 = {"workload": f"1M x {a.dim} exact dense top-{TOP_K}",
+              "batch1": {"kernel": "dense_scan_kernel", "ms": t_b1, "qps": 1e3 / t_b1,
+                         "hbm_gbs": n2 * a.dim * 2 / (t_b1 * 1e-3) / 1e9, "hbm_frac": n2 * a.dim * 2 / (t_b1 * 1e-3) / 1e9 / hbm_peak},
+              "batch1024": {"kernel": "dense_mma_kernel (tcgen05/TMA; sample + bound + main + finalize)", "ms": t_b1024,
+                            "qps": b2 * 1e3 / t_b1024, "tflops": flops / (t_b1024 * 1e-3) / 1e12,
+                            "tensor_frac": flops / (t_b1024 * 1e-3) / 1e12 / tf_peak,
+                            "peak_tflops": tf_peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
+                            if peaks else "B200_PROFILING.md fallback (sustained)"}}
+        del emb2, q2
 
     # kernels per step (resident loop): dense = sample pass, bound, main pass, finalize (tcgen05 path)
     # or scan, finalize; then gather, mmr, bm25 tile, bm25 finalize, fuse; sharded: + 2 merges
@@ -352,7 +402,10 @@ def main():
                       "l2": "inputs larger than L2 (matrix %.1f GB per rank)" % (dense_bytes / 1e9),
                       "index_build_s": build_s},
            "roofline": roofline, "e2e": e2e, "latency": latency, "gpu_launches": launches_per_step * a.steps,
-           "clocks": clock_info, "planted_top1_in_top10": hit}
+           "clocks": clock_info, "planted_top1_in_top10": hit, "c2": c2,
+           "chroma_hnsw_recall_at_10": None,
+           "chroma_note": "chromadb/hnswlib are not installable offline: recall of the reference's ANN path vs exact "
+                          "search cannot be measured here; this implementation is exact (recall 1.0 by construction)"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a)
     elif rank == 0:

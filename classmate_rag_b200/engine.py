@@ -166,7 +166,7 @@ class GraphedSearch:
     This is the end-to-end call with HOST buffers that bench.py's ``e2e`` times."""
 
     def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64,
-                 graph_collectives: bool = True):
+                 graph_collectives: bool = True, stream: Optional[torch.cuda.Stream] = None):
         self.engine, self.p, self.b = engine, p, n_queries
         self.graph_collectives = graph_collectives
         dev = engine.device
@@ -181,7 +181,10 @@ class GraphedSearch:
         self.h_q = torch.zeros((n_queries, d), dtype=torch.float32).pin_memory()
         self.h_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32).pin_memory()
         self.h_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32).pin_memory()
-        self.stream = torch.cuda.Stream(device=dev)
+        # several GraphedSearch objects may share one stream (they share the engine's scratch
+        # buffers, so their device work must be serialised anyway): see PipelinedSearch
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
+        self.done = torch.cuda.Event()
         self.graph = None
         self._capture()
 
@@ -247,9 +250,52 @@ class GraphedSearch:
             self.h_vd.copy_(vd, non_blocking=True)
             self.h_bm.copy_(bm, non_blocking=True)
             self.h_cnt.copy_(cnt, non_blocking=True)
+            self.done.record(self.stream)
+
+    def result(self):
+        """Wait for the last launch() of THIS object and hand back its pinned result buffers."""
+        self.done.synchronize()
+        return self.h_ids.numpy(), self.h_fused.numpy(), self.h_vd.numpy(), self.h_bm.numpy(), self.h_cnt.numpy()
 
     def __call__(self, q_f32: np.ndarray, term_lists=None):
         self.set_queries(q_f32, term_lists)
         self.launch()
-        self.stream.synchronize()
-        return self.h_ids.numpy(), self.h_fused.numpy(), self.h_vd.numpy(), self.h_bm.numpy(), self.h_cnt.numpy()
+        return self.result()
+
+
+class PipelinedSearch:
+    """Throughput form of the host-buffer call: two GraphedSearch objects on one stream.
+    While the device works on batch i the host stages batch i+1 into the other object's
+    pinned buffers and enqueues it, so host staging never leaves the device idle.
+
+        ps = PipelinedSearch(engine, params, batch)
+        for q, terms in batches:
+            prev = ps.submit(q, terms)        # results of the batch submitted before (or None)
+        last = ps.drain()
+    """
+
+    def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64):
+        stream = torch.cuda.Stream(device=engine.device)
+        self.slots = [GraphedSearch(engine, p, n_queries, max_terms, stream=stream) for _ in range(2)]
+        self.turn = 0
+        self.pending: Optional[GraphedSearch] = None
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.slots[0].h2d_bytes
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.slots[0].d2h_bytes
+
+    def submit(self, q_f32: np.ndarray, term_lists=None):
+        g = self.slots[self.turn]
+        self.turn ^= 1
+        g.set_queries(q_f32, term_lists)   # g's previous results were handed out two submits ago
+        g.launch()
+        prev, self.pending = self.pending, g
+        return None if prev is None else tuple(a.copy() for a in prev.result())
+
+    def drain(self):
+        prev, self.pending = self.pending, None
+        return None if prev is None else tuple(a.copy() for a in prev.result())

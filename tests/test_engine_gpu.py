@@ -156,3 +156,25 @@ def test_single_exchange_shard_merge_equals_unsharded(small_world, n_shards, hyb
     assert int(d_f.sum()) == 0
     for a, b in zip(got, want):
         assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+
+
+def test_pipelined_search_returns_each_batch_in_order(small_world):
+    """PipelinedSearch (two graph slots on one stream) hands back, one submit late, exactly what
+    the single-slot GraphedSearch returns for the same batch."""
+    from classmate_rag_b200.engine import GraphedSearch, PipelinedSearch, SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    p = SearchParams(top_k=10)
+    qh = q.cpu().numpy()
+    one = GraphedSearch(eng, p, n_queries=2, max_terms=16)
+    want = [[x.copy() for x in one(qh[i:i + 2], terms[i:i + 2])] for i in (0, 2, 4, 0)]
+    ps = PipelinedSearch(eng, p, 2, max_terms=16)
+    got = []
+    for i in (0, 2, 4, 0):
+        r = ps.submit(qh[i:i + 2], terms[i:i + 2])
+        if r is not None:
+            got.append(r)
+    got.append(ps.drain())
+    assert ps.drain() is None and len(got) == 4
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert a.tobytes() == b.tobytes()
