@@ -552,8 +552,11 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, M
     // no bound (tiny matrix): every row of a CTA's tiles is a candidate
     p->cap = MM_R * ((p->n_tiles + p->n_lists - 1) / p->n_lists);
   } else {
-    // about MM_SAMPLE_STRIDE * KP candidates per query in all; 4x the even share + slack
-    p->cap = 4 * MM_SAMPLE_STRIDE * p->kp / p->n_lists + 32;
+    // About MM_SAMPLE_STRIDE * KP candidates per query in all.  An even spread would put only a
+    // few into each CTA's list, but neighbouring rows are often similar (chunks of one document)
+    // and land in the same tile, so lists are as deep as a 256 MB budget allows, 32..256 slots.
+    const long long budget = (256ll << 20) / ((long long)p->n_lists * n_queries * (long long)sizeof(u64));
+    p->cap = (int)(budget < 32 ? 32 : (budget > 256 ? 256 : budget));
   }
   if (p->cap > p->cap_total) p->cap = p->cap_total;
   size_t off = ((size_t)p->n_lists * n_queries * p->cap * sizeof(u64) + 15) / 16 * 16;

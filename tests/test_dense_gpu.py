@@ -284,3 +284,24 @@ def test_dense_mma_many_groups_block_bound_kernel():
     bits = emb.view(torch.int16).cpu().numpy().view(np.uint16)
     want_ids, want_sc = o.dense_topk(q[0].view(torch.int16).cpu().numpy().view(np.uint16), bits, k)
     assert i[0].cpu().numpy().tolist() == want_ids.tolist() and s[0].cpu().numpy().tobytes() == want_sc.tobytes()
+
+
+def test_dense_mma_clustered_rows_do_not_overflow_the_cta_lists():
+    """200 near-copies of the query's source row sit next to each other (chunks of one document):
+    they all land in one or two row tiles, i.e. in one or two CTAs' private lists."""
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(21)
+    n, d = 60_000, 128
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    base = x[31_000].copy()
+    for i in range(200):
+        v = base + 0.05 * rng.standard_normal(d).astype(np.float32) / np.sqrt(d) * (1 + i / 50)
+        x[31_000 + i] = v / np.linalg.norm(v)
+    bits = o.f32_to_bf16_bits(x)
+    qbits = np.repeat(o.f32_to_bf16_bits(base[None]), 9, axis=0)
+    s, i, c, f = ops.dense_topk(_to_dev(bits), _to_dev(qbits), 24, algo="mma")
+    torch.cuda.synchronize()
+    assert int(f.sum()) == 0
+    want_ids, want_sc = o.dense_topk(qbits[0], bits, 24)
+    assert i[0].cpu().numpy().tolist() == want_ids.tolist() and s[0].cpu().numpy().tobytes() == want_sc.tobytes()
