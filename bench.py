@@ -257,22 +257,33 @@ def main():
     ms_per_step = total_ms / a.steps
     value = a.batch * a.steps / (total_ms * 1e-3)
 
-    # ---- per-stage device time: the same steps again, each stage back to back between two
-    # events (the queue stays full, so host launch latency is not part of the number) ----------
+    # ---- per-stage device time.  Single shard: the same steps again with timing events at the
+    # stage boundaries INSIDE the step (a stage timed back to back on its own runs at other
+    # clocks: twenty BM25 launches in a row hit the power cap, inside a step they alternate
+    # with the memory-bound dense pass).  Sharded: each retriever back to back (its own exchange).
     pool = p.pool
-
-    def stage_ms(fn):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fn(a.warmup)                      # one untimed call: buffers of this shape exist
-        torch.cuda.synchronize()
-        e0.record(stream)
+    if world == 1:
+        marks = []
         for s in range(a.warmup, n_steps):
-            fn(s)
-        e1.record(stream)
+            ev = []
+            eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p, stage_events=ev)
+            marks.append(ev)
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / a.steps
-    dense_ms = [stage_ms(lambda s: eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool))]
-    lex_ms = [stage_ms(lambda s: eng.lexical_topk(*dev_terms[s], p.k_bm25))]
+        dense_ms = [m[0].elapsed_time(m[1]) for m in marks]
+        lex_ms = [m[2].elapsed_time(m[3]) for m in marks]
+    else:
+        def stage_ms(fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fn(a.warmup)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for s in range(a.warmup, n_steps):
+                fn(s)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / a.steps
+        dense_ms = [stage_ms(lambda s: eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool))]
+        lex_ms = [stage_ms(lambda s: eng.lexical_topk(*dev_terms[s], p.k_bm25))]
     clock_info = clocks.stop()
     dense_avg = float(np.mean(dense_ms))
     lex_avg = float(np.mean(lex_ms))

@@ -18,10 +18,10 @@
 //            query's candidate buffer (one global atomic each).
 //
 // The admission bound makes the single pass exact without keeping sorted lists on chip:
-// the same kernel first runs in SAMPLE mode over every 16th row tile and writes the maximum
+// the same kernel first runs in SAMPLE mode over every 16th (32nd from 2M rows on) row tile and writes the maximum
 // score of each sampled group of rows; the KP-th largest of those maxima is attained by at
 // least KP different rows, hence it is a lower bound of the KP-th best score of the query,
-// and every row of the true top-KP passes `score >= bound` in MAIN mode.  About 16*KP rows
+// and every row of the true top-KP passes `score >= bound` in MAIN mode.  About stride*KP rows
 // per query pass; dense_finalize_cand_kernel picks the KP best fp32 keys and hands them to
 // the shared exact float64 rescoring tail (dense_common.cuh), so ids, order and scores are
 // bit-identical to the scan path and to the oracle.
@@ -44,8 +44,10 @@ constexpr int MM_A_BYTES = MM_Q * MM_K * 2;  // 16 KiB
 constexpr int MM_B_BYTES = MM_R * MM_K * 2;  // 32 KiB
 constexpr int MM_THREADS = 192;
 constexpr int MM_SAMPLE = 0, MM_MAIN = 1, MM_NEARDUP = 2;
-constexpr int MM_CAP_PER_KP = 64;    // candidate slots per query = 64 * KP
-constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile
+constexpr int MM_CAP_PER_KP = 128;   // candidates finalize can collect per query = 128 * KP
+constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile ...
+constexpr int MM_SAMPLE_STRIDE_LARGE = 32;   // ... every 32nd from MM_LARGE_TILES tiles on (2M rows): the
+constexpr int MM_LARGE_TILES = 8192;         // bound is then still the KP-th of >= 256 tile maxima
 constexpr int MM_MAX_GROUPS = 49152; // threshold kernel keeps the group maxima in shared memory
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
@@ -317,7 +319,7 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tile_max = fmaxf(tile_max, m);
           }
         } else if (q_ok && m >= bound) {
-          // rare: about 16*KP rows per query over the whole scan (MAIN); near-duplicate pairs (NEARDUP)
+          // rare: about stride*KP rows per query over the whole scan (MAIN); near-duplicate pairs (NEARDUP)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (v[j] >= bound) {
@@ -536,9 +538,10 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, M
   p->bpad = (n_queries + 31) / 32 * 32;
   p->n_tiles = (int)((n_rows + MM_R - 1) / MM_R);
   const int full_tiles = (int)(n_rows / MM_R);
+  const int max_stride = full_tiles >= MM_LARGE_TILES ? MM_SAMPLE_STRIDE_LARGE : MM_SAMPLE_STRIDE;
   int stride = full_tiles / MM_SAMPLE_STRIDE;  // small matrices: sample (nearly) every tile
   if (stride < 1) stride = 1;
-  if (stride > MM_SAMPLE_STRIDE) stride = MM_SAMPLE_STRIDE;
+  if (stride > max_stride) stride = max_stride;
   for (;;) {
     p->sample_stride = stride;
     p->n_sample = full_tiles > 0 ? (full_tiles + stride - 1) / stride : 0;
@@ -552,7 +555,7 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, M
     // no bound (tiny matrix): every row of a CTA's tiles is a candidate
     p->cap = MM_R * ((p->n_tiles + p->n_lists - 1) / p->n_lists);
   } else {
-    // About MM_SAMPLE_STRIDE * KP candidates per query in all.  An even spread would put only a
+    // About stride * KP candidates per query in all.  An even spread would put only a
     // few into each CTA's list, but neighbouring rows are often similar (chunks of one document)
     // and land in the same tile, so lists are as deep as a 256 MB budget allows, 32..256 slots.
     const long long budget = (256ll << 20) / ((long long)p->n_lists * n_queries * (long long)sizeof(u64));

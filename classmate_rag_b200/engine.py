@@ -105,10 +105,16 @@ class HybridEngine:
     # -- the hot path --------------------------------------------------------
     def search(self, q_bf16: torch.Tensor, q_terms: Optional[torch.Tensor], q_ptr: Optional[torch.Tensor],
                p: SearchParams, *, dense_mask: Optional[torch.Tensor] = None,
-               lex_mask: Optional[torch.Tensor] = None):
+               lex_mask: Optional[torch.Tensor] = None, stage_events: Optional[list] = None):
         """Returns device tensors (ids i64 [B,top_k], fused f64, vector_distance f64
         (NaN = None), bm25_score f64 (NaN = None), counts i32 [B]); nothing is
-        synchronised."""
+        synchronised.  ``stage_events``: a list that receives timing events at the stage
+        boundaries (start, dense done, MMR done, BM25 done, fused) -- single-shard path only."""
+        def mark():
+            if stage_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                stage_events.append(e)
         if q_bf16.dim() == 1:
             q_bf16 = q_bf16[None]
         hybrid = p.hybrid and self.lex is not None and q_terms is not None
@@ -117,19 +123,25 @@ class HybridEngine:
         pool = min(pool, 64) if p.use_mmr else pool
         if self.comm is not None:
             return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
+        mark()
         scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
         self.last_dense_flags = flags
+        mark()
         if p.use_mmr:
             rows = self.pool_rows(ids)
             v_ids, v_sims, v_cnt = ops.mmr_select(rows, scores, ids, counts, min(k_vec, pool), p.mmr_lambda)
         else:
             v_ids, v_sims, v_cnt = ids, scores, counts
+        mark()
         bm = None
         if hybrid:
             b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
             bm = (b_ids, b_sc, b_cnt)
-        return ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
-                               w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+        mark()
+        out = ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
+                              w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+        mark()
+        return out
 
 
     def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask):
