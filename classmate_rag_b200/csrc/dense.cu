@@ -515,7 +515,7 @@ extern "C" int cmr_dense_topk_ex(const uint16_t* emb, int64_t n_rows, int dim, c
     return CMR_EUNSUPPORTED;
   }
   // auto: a single scan pass serves up to 8 queries at the HBM rate; above that the
-  // tensor-core GEMM reads the matrix once for up to 128 queries.
+  // tensor-core GEMM reads the matrix once for up to 128 queries (with or without a mask).
   const bool use_mma = algo == CMR_DENSE_MMA || (algo == CMR_DENSE_AUTO && can_mma && n_queries > 8);
   return use_mma ? dense_mma_topk(a) : dense_scan_topk(a);
 }

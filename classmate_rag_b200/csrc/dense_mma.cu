@@ -160,6 +160,7 @@ struct MmParams {
   u64* cand;           // [n_ctas][n_left][cap]: every CTA keeps private lists, so no atomics
   int* cnt;            // [n_ctas][n_left] entries appended (may exceed cap: the excess was dropped)
   int cap;             // slots per (CTA, query)
+  const u32* mask_bits;  // SAMPLE / MAIN: bit r % 32 of word r / 32 = row r may be returned; NULL = all
   // NEARDUP
   float nd_bound;      // emit pairs with fp32 score >= nd_bound (= threshold - error bound)
   u64* edges;          // (i << 32) | j
@@ -309,6 +310,12 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         __syncwarp();
         float v[32];
         tmem_ld32(taddr + c * 32, v);
+        if (MODE != MM_NEARDUP && p.mask_bits != nullptr) {
+          // `where` filter / tombstones: one broadcast word covers the 32 rows of this load
+          const u32 bits = p.mask_bits[(row0 + c * 32) >> 5];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : -INFINITY;
+        }
         float m = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
@@ -353,6 +360,27 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+// uint8 row mask -> one bit per row, zero padded to whole 256-row tiles (so rows past the end
+// of the matrix are filtered too)
+__global__ void mask_to_bits_kernel(const uint8_t* __restrict__ mask, long long n_rows, long long n_words,
+                                    u32* __restrict__ bits) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  u32 out = 0;
+  const long long r0 = w * 32;
+  if (r0 + 32 <= n_rows && (reinterpret_cast<uintptr_t>(mask + r0) & 15) == 0) {
+    const uint4 a = *reinterpret_cast<const uint4*>(mask + r0), b = *reinterpret_cast<const uint4*>(mask + r0 + 16);
+    const u32 words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out |= (((words[i] >> (8 * j)) & 0xFFu) ? 1u : 0u) << (4 * i + j);
+  } else {
+    for (int j = 0; j < 32 && r0 + j < n_rows; ++j) out |= (mask[r0 + j] ? 1u : 0u) << j;
+  }
+  bits[w] = out;
 }
 
 // One CTA per query: bound = the kp-th largest of the G sampled group maxima (bit-wise
@@ -524,7 +552,7 @@ struct MmaPlan {
   int n_lists;    // CTAs of the MAIN pass
   int n_mb, n_chunks, q_box_rows, bpad;
   int n_tiles, n_sample, sample_stride, gpt, n_groups;
-  size_t off_cnt, off_thr, off_gmax, total;
+  size_t off_cnt, off_thr, off_gmax, off_bits, total;
 };
 
 static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, MmaPlan* p) {
@@ -568,12 +596,15 @@ static void mma_plan(long long n_rows, int dim, int n_queries, int k, int sms, M
   p->off_thr = off;
   off += ((size_t)p->bpad * 4 + 15) / 16 * 16;
   p->off_gmax = off;
-  off += (size_t)(p->n_groups > 0 ? p->n_groups : 1) * p->bpad * 4;
+  off += ((size_t)(p->n_groups > 0 ? p->n_groups : 1) * p->bpad * 4 + 15) / 16 * 16;
+  p->off_bits = off;
+  off += (size_t)p->n_tiles * (MM_R / 32) * 4;   // row-mask bits (used when the call has a mask)
   p->total = off;
 }
 
 bool dense_mma_eligible(long long n_rows, int dim, int n_queries, int k, bool has_mask) {
-  return !has_mask && dim >= MM_K && n_rows >= MM_R && n_rows < 0x7FFFFF00ll && n_queries >= 1 &&
+  (void)has_mask;  // filters are applied in the epilogue from a bitmask
+  return dim >= MM_K && n_rows >= MM_R && n_rows < 0x7FFFFF00ll && n_queries >= 1 &&
          n_queries <= MM_MAX_QUERIES && k >= 1 && k <= CMR_MAX_K;
 }
 
@@ -667,6 +698,13 @@ int dense_mma_topk(const DenseArgs& a) {
   kp.cand = cand;
   kp.cnt = cnt;
   kp.cap = p.cap;
+  kp.mask_bits = nullptr;
+  if (a.row_mask != nullptr) {
+    u32* bits = (u32*)(ws + p.off_bits);
+    const long long n_words = (long long)p.n_tiles * (MM_R / 32);
+    mask_to_bits_kernel<<<(int)((n_words + 255) / 256), 256, 0, a.stream>>>(a.row_mask, a.n_rows, n_words, bits);
+    kp.mask_bits = bits;
+  }
   if (p.n_sample > 0) {
     const int grid = p.n_sample < sms ? p.n_sample : sms;
     kp.n_outer = p.n_sample;

@@ -329,11 +329,11 @@ def shard_merge(gathered: torch.Tensor, pool: int, kb: int, dim: int):
 
 def dense_topk_certified(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Optional[torch.Tensor] = None,
                          row_offset: int = 0, cert_eps: Optional[float] = None,
-                         workspace: Optional[DenseWorkspace] = None):
+                         workspace: Optional[DenseWorkspace] = None, algo: str = "auto"):
     """dense_topk, then the queries whose result could not be certified are re-run on the
     exhaustive float64 scan and patched in place.  Synchronises (it reads the flags)."""
     scores, ids, counts, flags = dense_topk(emb, queries, k, row_mask=row_mask, row_offset=row_offset,
-                                            cert_eps=cert_eps, workspace=workspace)
+                                            cert_eps=cert_eps, workspace=workspace, algo=algo)
     bad = torch.nonzero(flags).flatten()
     if bad.numel():
         q = queries[None, :] if queries.dim() == 1 else queries

@@ -88,8 +88,9 @@ class HybridRetriever:
         if col.n_rows == 0:
             return empty
         q = ops.f32_to_bf16(torch.from_numpy(np.ascontiguousarray(q_vec, dtype=np.float32)[None]).to(dev))
-        scores, rows, counts, _ = ops.dense_topk_certified(col.matrix(), q, pool, row_mask=col.mask(where),
-                                                           workspace=col.workspace(1, pool))
+        mask = col.mask(where)
+        scores, rows, counts, _ = ops.dense_topk_certified(col.matrix(), q, pool, row_mask=mask,
+                                                           workspace=col.workspace(1, pool), algo=col.algo_for(mask))
         if self.use_mmr:
             cand = ops.gather_rows(col.matrix(), rows)
             rows, scores, counts = ops.mmr_select(cand, scores, rows, counts, min(k, pool), self.mmr_lambda)

@@ -129,11 +129,19 @@ class _Collection:
 
     def mask(self, where: Optional[Mapping[str, Any]]) -> Optional[torch.Tensor]:
         """Device row mask of a query: None when every row qualifies (no filter, no
-        tombstones), which lets the batched tcgen05 path run."""
+        tombstones)."""
         clauses = chroma_clauses(where)
         if not clauses and self.n_dead == 0:
             return None
         return self.columns.mask(clauses, alive=self.alive[: self.n_rows])
+
+    def algo_for(self, mask: Optional[torch.Tensor]) -> str:
+        """A very selective filter is served best by the exhaustive float64 scan, which only
+        reads the allowed rows; otherwise the library picks scan / tcgen05 by batch size."""
+        if mask is None:
+            return "auto"
+        allowed = int(mask.sum())
+        return "exact" if allowed * 16 <= self.n_rows else "auto"
 
 
 @dataclass
@@ -229,7 +237,8 @@ class ChromaVectorStore:
         if k <= 0:
             raise ValueError("top_k must be positive")
         # flagged (uncertifiable) queries are re-run on the exhaustive float64 scan
-        out = ops.dense_topk_certified(col.matrix(), q, k, row_mask=mask, workspace=col.workspace(q.shape[0], k))
+        out = ops.dense_topk_certified(col.matrix(), q, k, row_mask=mask, workspace=col.workspace(q.shape[0], k),
+                                       algo=col.algo_for(mask))
         return col, out
 
     def query(self, *, query_embeddings: np.ndarray, where: Optional[Dict[str, Any]] = None, top_k: int = 8,

@@ -79,7 +79,7 @@ int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
 /* Same call with an explicit choice of kernel (tests, benchmarks).
  *   CMR_DENSE_SCAN  HBM-streaming scan: coalesced 16-byte loads feed mma.sync tiles, up to
  *                   32 queries per pass over the matrix; warp-private top-k lists.  The
- *                   single-query (GEMV-shaped) path; the only one that takes a row_mask.
+ *                   single-query (GEMV-shaped) path.
  *   CMR_DENSE_MMA   batched q.C^T on the tcgen05 tensor cores: TMA stages 128-byte-swizzled
  *                   tiles of queries and rows in shared memory, one thread issues
  *                   tcgen05.mma (M = 128 queries, N = 256 rows, K = 16) into double-buffered
@@ -89,12 +89,14 @@ int cmr_dense_topk(const uint16_t* emb, int64_t n_rows, int dim,
  *                   128 queries.  The bound comes from a first pass of the same kernel over
  *                   1/16 of the row tiles (k-th largest of the tile maxima: a valid lower
  *                   bound of the k-th best score), so both passes are exact.
- *                   CMR_EUNSUPPORTED when the shape is outside that path (row_mask given,
- *                   dim < 64, fewer than 256 rows).
+ *                   A row_mask is turned into one bit per row and applied in the epilogue.
+ *                   CMR_EUNSUPPORTED when the shape is outside that path (dim < 64, fewer
+ *                   than 256 rows, more than 8192 queries).
  *   CMR_DENSE_EXACT exhaustive scan that ranks on the exact float64 dot of EVERY row (fp64 pipe
  *                   bound, a few times slower): nothing to certify, out_flags is always 0.
  *                   The fallback for queries the fast paths flag CMR_FLAG_UNCERTIFIED.
- *   CMR_DENSE_AUTO  SCAN for <= 8 queries or masked calls, MMA above.
+ *   CMR_DENSE_AUTO  SCAN for <= 8 queries, MMA above (when the shape allows).  For a very
+ *                   selective mask CMR_DENSE_EXACT is the cheapest: it reads allowed rows only.
  * Results are bit-identical between all of them (ids, order and float64 scores) whenever the
  * fast paths certify theirs. */
 #define CMR_DENSE_AUTO 0

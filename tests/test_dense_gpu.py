@@ -217,12 +217,46 @@ def test_dense_mma_unsupported_shapes_raise():
     q = torch.zeros((9, 64), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError):
         ops.dense_topk(emb, q, 4, algo="mma")          # fewer than 256 rows
-    emb = torch.zeros((1000, 64), dtype=torch.bfloat16, device="cuda")
+    emb = torch.zeros((1000, 32), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError):
-        ops.dense_topk(emb, q, 4, algo="mma", row_mask=torch.ones(1000, dtype=torch.uint8, device="cuda"))
-    s, i, c, f = ops.dense_topk(emb, q, 4, row_mask=torch.ones(1000, dtype=torch.uint8, device="cuda"))  # auto -> scan
+        ops.dense_topk(emb, torch.zeros((9, 32), dtype=torch.bfloat16, device="cuda"), 4, algo="mma")   # dim < 64
+    s, i, c, f = ops.dense_topk(emb, torch.zeros((9, 32), dtype=torch.bfloat16, device="cuda"), 4)      # auto -> scan
     torch.cuda.synchronize()
     assert (c.cpu().numpy() == 4).all()
+
+
+@pytest.mark.parametrize("n,d,b,keep", [(9000, 256, 12, 0.3), (20000, 768, 32, 0.9), (5000, 64, 130, 0.02), (70000, 64, 9, 0.5)])
+def test_dense_mma_row_mask(n, d, b, keep):
+    """`where` filter / tombstones on the tcgen05 path: the mask becomes one bit per row and is
+    applied in the epilogue (sample pass included, so the bound only sees allowed rows)."""
+    from classmate_rag_b200 import ops
+    rng = np.random.default_rng(n + b)
+    bits = _corpus(rng, n, d, dup_every=64)
+    qbits = _queries(rng, bits, b)
+    mask = (rng.random(n) < keep).astype(np.uint8)
+    mask[-7:] = 1
+    emb, q, m = _to_dev(bits), _to_dev(qbits), torch.from_numpy(mask).cuda()
+    s, i, c, f = [t.clone() for t in ops.dense_topk(emb, q, 10, row_mask=m, row_offset=1000, algo="mma")]
+    s2, i2, c2, f2 = ops.dense_topk(emb, q, 10, row_mask=m, row_offset=1000, algo="scan")
+    torch.cuda.synchronize()
+    ok = f.cpu().numpy() == 0          # a very selective mask may overflow a list: flagged, never wrong
+    assert ok.sum() >= b // 2
+    assert torch.equal(i[ok], i2[ok]) and s[ok].cpu().numpy().tobytes() == s2[ok].cpu().numpy().tobytes()
+    for bb in range(min(b, 3)):
+        want_ids, want_sc = o.dense_topk(qbits[bb], bits, 10, mask=mask, row_offset=1000)
+        if ok[bb]:
+            assert i[bb, :len(want_ids)].cpu().numpy().tolist() == want_ids.tolist()
+            assert s[bb, :len(want_ids)].cpu().numpy().tobytes() == want_sc.tobytes()
+    # the certified wrapper always ends exact
+    s3, i3, c3, f3 = ops.dense_topk_certified(emb, q, 10, row_mask=m, row_offset=1000)
+    torch.cuda.synchronize()
+    assert int(f3.sum()) == 0 and torch.equal(i3, i2)
+    # an unaligned mask view works too
+    big = torch.zeros(n + 3, dtype=torch.uint8, device="cuda")
+    big[3:] = m
+    s4, i4, c4, f4 = ops.dense_topk(emb, q, 10, row_mask=big[3:], row_offset=1000, algo="mma")
+    torch.cuda.synchronize()
+    assert torch.equal(i4[ok], i2[ok])
 
 
 # ---- exhaustive exact scan (CMR_DENSE_EXACT) and the certified wrapper ----
