@@ -133,6 +133,36 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   // Query tokens are processed in chunks of BM_MAXQ (one chunk for any normal query).
   // With more than one chunk the accumulators must persist across chunks, so the tile
   // loop is the outer loop and chunks the inner one.
+  //
+  // Single-chunk queries (the normal case) keep a token's constants -- posting base, idf,
+  // dense column -- in the registers of thread `tid` (< 64) for the whole kernel; per tile
+  // only the two skip-table entries of SPARSE tokens are needed, and those of the next tile
+  // are loaded while this tile is processed, so staging adds no dependent load to the
+  // per-tile chain.
+  const bool one_chunk = (qhi - qlo) <= BM_MAXQ;
+  long long tk_base = 0;
+  const uint32_t* tk_skip = nullptr;
+  u32 pre0 = 0, pre1 = 0;  // skip entries of the tile about to be processed
+  if (one_chunk && tid < qhi - qlo) {
+    const int t = q_terms[qlo + tid];
+    double w = 0.0;
+    int slot = -1;
+    if (t >= 0 && t < ix.n_terms) {
+      tk_base = ix.term_ptr[t];
+      w = ix.idf[t];
+      if (ix.dense_slot != nullptr) slot = ix.dense_slot[t];
+      if (slot < 0) {
+        tk_skip = ix.tile_skip + (size_t)t * (ix.n_tiles + 1);
+        if (first_tile < ix.n_tiles) {
+          pre0 = tk_skip[first_tile];
+          pre1 = tk_skip[first_tile + 1];
+        }
+      }
+    }
+    s_w[tid] = w;
+    s_slot[tid] = slot;
+  }
+
   for (int tile = first_tile; tile < ix.n_tiles; tile += gridDim.y) {
     const long long tile_lo = (long long)tile * ix.tile_docs;
     const long long rem = ix.n_docs - tile_lo;
@@ -144,7 +174,17 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
     for (int c0 = qlo; c0 < qhi; c0 += BM_MAXQ) {
       const int m = (qhi - c0) < BM_MAXQ ? (qhi - c0) : BM_MAXQ;
       __syncthreads();  // previous users of the staging arrays and of the accumulators are done
-      if (tid < m) {
+      if (one_chunk) {
+        if (tid < m) {
+          s_lo[tid] = tk_base + pre0;   // dense / unknown tokens: an empty slice (0, 0)
+          s_hi[tid] = tk_base + pre1;
+          const int next = tile + (int)gridDim.y;
+          if (tk_skip != nullptr && next < ix.n_tiles) {  // in flight during this tile's passes
+            pre0 = tk_skip[next];
+            pre1 = tk_skip[next + 1];
+          }
+        }
+      } else if (tid < m) {
         const int t = q_terms[c0 + tid];
         long long lo = 0, hi = 0;
         double w = 0.0;
