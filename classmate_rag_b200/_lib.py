@@ -50,6 +50,10 @@ _SIGNATURES = {
     "cmr_shard_merge": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp]),
     "cmr_tokenize_queries": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "cmr_shard_exchange_pack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
+                                          _i64, C.c_int, _vp, _vp]),
+    "cmr_shard_exchange_merge": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "cmr_topk_merge": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "cmr_bm25_workspace_bytes": (_sz, [_vp, C.c_int, C.c_int]),
     "cmr_bm25_topk": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _i64,

@@ -275,34 +275,71 @@ __host__ __device__ inline size_t shard_msg_bytes(int pool, int kb, int dim) {
 
 constexpr int SHARD_THREADS = 256;
 
+// Peer-memory form of the exchange (ShardP2P below): instead of one local message that NCCL
+// then all-gathers, the kernel stores every element straight into the receive buffer of EVERY
+// rank (its own included) over NVLink -- peer pointers from a symmetric-memory rendezvous --
+// and the last CTA to finish publishes an epoch flag on every rank (release, system scope).
+// shard_merge_kernel on each rank waits for all flags of the epoch (acquire) and merges.  No
+// collective launch; the transfer overlaps the packing query by query.
+struct ShardP2P {
+  const unsigned long long* peer_recv;   // device array [n_parts]: base of every rank's receive buffer
+  const unsigned long long* peer_flags;  // device array [n_parts]: base of every rank's flag words (u32)
+  unsigned int* state;                   // local: [0] epoch of the last completed pack, [1] CTAs done
+  int n_parts, my_rank;
+  unsigned long long slot_stride;        // bytes between the slots of two source ranks
+  unsigned long long parity_stride;      // bytes between the two buffers used on alternating steps
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool P2P>
 __global__ void __launch_bounds__(SHARD_THREADS)
 shard_pack_kernel(const double* __restrict__ d_scores, const long long* __restrict__ d_ids,
                   const int* __restrict__ d_counts, const int* __restrict__ d_flags, int pool,
                   const double* __restrict__ b_scores, const long long* __restrict__ b_ids,
                   const int* __restrict__ b_counts, int kb, const uint4* __restrict__ emb, long long n_rows,
-                  int dim, long long row_offset, unsigned char* __restrict__ msg) {
+                  int dim, long long row_offset, unsigned char* __restrict__ msg, ShardP2P x) {
   const int qi = blockIdx.x, tid = threadIdx.x;
   const size_t mb = shard_msg_bytes(pool, kb, dim);
-  unsigned char* m = msg + (size_t)qi * mb;
-  double* ms = reinterpret_cast<double*>(m);
-  long long* mi = reinterpret_cast<long long*>(m + (size_t)8 * pool);
-  double* bs = reinterpret_cast<double*>(m + (size_t)16 * pool);
-  long long* bi = reinterpret_cast<long long*>(m + (size_t)16 * pool + (size_t)8 * kb);
-  int* hdr = reinterpret_cast<int*>(m + (size_t)16 * pool + (size_t)16 * kb);
-  uint4* rows = reinterpret_cast<uint4*>(m + (size_t)16 * pool + (size_t)16 * kb + 16);
+  const size_t o_ids = (size_t)8 * pool, o_bs = (size_t)16 * pool, o_bi = o_bs + (size_t)8 * kb,
+               o_hdr = o_bs + (size_t)16 * kb, o_rows = o_hdr + 16;
+  const int n_dst = P2P ? x.n_parts : 1;
+  unsigned int epoch = 0;
+  if (P2P) epoch = x.state[0] + 1u;
+  // destination g of this query's message
+  auto dst = [&](int g) -> unsigned char* {
+    if (!P2P) return msg + (size_t)qi * mb;
+    return reinterpret_cast<unsigned char*>(x.peer_recv[g]) + (size_t)(epoch & 1u) * x.parity_stride +
+           (size_t)x.my_rank * x.slot_stride + (size_t)qi * mb;
+  };
   for (int i = tid; i < pool; i += SHARD_THREADS) {
-    ms[i] = d_scores[(size_t)qi * pool + i];
-    mi[i] = d_ids[(size_t)qi * pool + i];
+    const double sv = d_scores[(size_t)qi * pool + i];
+    const long long iv = d_ids[(size_t)qi * pool + i];
+    for (int g = 0; g < n_dst; ++g) {
+      unsigned char* m = dst(g);
+      reinterpret_cast<double*>(m)[i] = sv;
+      reinterpret_cast<long long*>(m + o_ids)[i] = iv;
+    }
   }
   for (int i = tid; i < kb; i += SHARD_THREADS) {
-    bs[i] = b_scores[(size_t)qi * kb + i];
-    bi[i] = b_ids[(size_t)qi * kb + i];
+    const double sv = b_scores[(size_t)qi * kb + i];
+    const long long iv = b_ids[(size_t)qi * kb + i];
+    for (int g = 0; g < n_dst; ++g) {
+      unsigned char* m = dst(g);
+      reinterpret_cast<double*>(m + o_bs)[i] = sv;
+      reinterpret_cast<long long*>(m + o_bi)[i] = iv;
+    }
   }
   if (tid == 0) {
-    hdr[0] = d_counts[qi];
-    hdr[1] = d_flags != nullptr ? d_flags[qi] : 0;
-    hdr[2] = kb > 0 ? b_counts[qi] : 0;
-    hdr[3] = 0;
+    const int4 hdr = make_int4(d_counts[qi], d_flags != nullptr ? d_flags[qi] : 0, kb > 0 ? b_counts[qi] : 0, 0);
+    for (int g = 0; g < n_dst; ++g) *reinterpret_cast<int4*>(dst(g) + o_hdr) = hdr;
   }
   if (dim > 0) {
     const int dim_vec = dim / 8;
@@ -314,7 +351,26 @@ shard_pack_kernel(const double* __restrict__ d_scores, const long long* __restri
         const long long local = d_ids[(size_t)qi * pool + r] - row_offset;
         if (local >= 0 && local < n_rows) val = emb[(size_t)local * dim_vec + v];
       }
-      rows[e] = val;
+      for (int g = 0; g < n_dst; ++g) reinterpret_cast<uint4*>(dst(g) + o_rows)[e] = val;
+    }
+  }
+  if (P2P) {
+    // publish: every thread's peer stores are ordered before the CTA's arrival; the last CTA
+    // raises the epoch flag of this (source rank, parity) on every rank
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int arrived = atomicAdd(&x.state[1], 1u);
+      if (arrived == gridDim.x - 1) {
+        __threadfence_system();
+        for (int g = 0; g < x.n_parts; ++g) {
+          unsigned int* f = reinterpret_cast<unsigned int*>(x.peer_flags[g]) + (epoch & 1u) * x.n_parts + x.my_rank;
+          st_release_sys_u32(f, epoch);
+        }
+        x.state[1] = 0u;
+        __threadfence();
+        x.state[0] = epoch;   // the merge kernel (next in the stream) reads the epoch from here
+      }
     }
   }
 }
@@ -322,7 +378,10 @@ shard_pack_kernel(const double* __restrict__ d_scores, const long long* __restri
 // One CTA per query over the gathered messages [G][B][msg].  Ranking by counting over the
 // G*pool (G*kb) entries with the total order (score desc, id asc): identical for any G.
 __global__ void __launch_bounds__(SHARD_THREADS)
-shard_merge_kernel(const unsigned char* __restrict__ gathered, int n_parts, int n_queries, int pool, int kb,
+shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t slot_stride,
+                   const unsigned int* __restrict__ wait_flags, const unsigned int* __restrict__ wait_state,
+                   unsigned long long parity_stride, int* __restrict__ timeout_flag,
+                   int n_parts, int n_queries, int pool, int kb,
                    int dim, double* __restrict__ d_scores, long long* __restrict__ d_ids,
                    int* __restrict__ d_counts, int* __restrict__ d_flags, uint4* __restrict__ d_rows,
                    double* __restrict__ b_scores, long long* __restrict__ b_ids, int* __restrict__ b_counts) {
@@ -334,7 +393,23 @@ shard_merge_kernel(const unsigned char* __restrict__ gathered, int n_parts, int 
   __shared__ int s_total, s_flag;
   const int qi = blockIdx.x, tid = threadIdx.x;
   const size_t mb = shard_msg_bytes(pool, kb, dim);
-  auto msg_of = [&](int g) { return gathered + ((size_t)g * n_queries + qi) * mb; };
+  if (wait_flags != nullptr) {
+    // peer-memory exchange: wait until every rank has published this step's message
+    const unsigned int epoch = wait_state[0];
+    gathered += (size_t)(epoch & 1u) * parity_stride;
+    if (tid < n_parts) {
+      const unsigned int* f = wait_flags + (epoch & 1u) * n_parts + tid;
+      const long long t0 = clock64();
+      while (ld_acquire_sys_u32(f) != epoch) {
+        if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank died; fail loudly instead of hanging
+          *timeout_flag = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  auto msg_of = [&](int g) { return gathered + (size_t)g * slot_stride + (size_t)qi * mb; };
 
   for (int pass = 0; pass < 2; ++pass) {
     const int k = pass == 0 ? pool : kb;
@@ -599,9 +674,29 @@ extern "C" int cmr_shard_pack(const double* dense_scores, const int64_t* dense_i
   CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 list");
   CMR_CHECK_ARG(dim == 0 || n_rows == 0 || emb, "null embedding matrix");
   CMR_CHECK_ARG(((uintptr_t)msg % 16) == 0, "message buffer must be 16-byte aligned");
-  shard_pack_kernel<<<n_queries, SHARD_THREADS, 0, (cudaStream_t)stream>>>(
+  shard_pack_kernel<false><<<n_queries, SHARD_THREADS, 0, (cudaStream_t)stream>>>(
       dense_scores, (const long long*)dense_ids, dense_counts, dense_flags, pool, bm_scores, (const long long*)bm_ids,
-      bm_counts, kb, reinterpret_cast<const uint4*>(emb), n_rows, dim, row_offset, (unsigned char*)msg);
+      bm_counts, kb, reinterpret_cast<const uint4*>(emb), n_rows, dim, row_offset, (unsigned char*)msg, ShardP2P{});
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+static int launch_shard_merge(const void* gathered, size_t slot_stride, const unsigned int* wait_flags,
+                              const unsigned int* wait_state, unsigned long long parity_stride, int* timeout_flag,
+                              int n_parts, int n_queries, int pool, int kb, int dim, double* dense_scores,
+                              int64_t* dense_ids, int32_t* dense_counts, int32_t* dense_flags, uint16_t* dense_rows,
+                              double* bm_scores, int64_t* bm_ids, int32_t* bm_counts, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_parts >= 1 && n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
+  CMR_CHECK_ARG(gathered && dense_scores && dense_ids && dense_counts && dense_flags, "null pointer argument");
+  CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 output");
+  CMR_CHECK_ARG(n_parts <= SHARD_THREADS, "too many shards");
+  const int n = n_parts * (pool > kb ? pool : kb);
+  const size_t smem = (size_t)n * 16 + (size_t)pool * 4 + 16;
+  CMR_CHECK_ARG(smem <= 48 * 1024, "too many shards x list entries for one merge (%d)", n);
+  shard_merge_kernel<<<n_queries, SHARD_THREADS, smem, (cudaStream_t)stream>>>(
+      (const unsigned char*)gathered, slot_stride, wait_flags, wait_state, parity_stride, timeout_flag, n_parts,
+      n_queries, pool, kb, dim, dense_scores, (long long*)dense_ids, dense_counts, dense_flags,
+      reinterpret_cast<uint4*>(dense_rows), bm_scores, (long long*)bm_ids, bm_counts);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }
@@ -610,15 +705,45 @@ extern "C" int cmr_shard_merge(const void* gathered, int n_parts, int n_queries,
                                double* dense_scores, int64_t* dense_ids, int32_t* dense_counts, int32_t* dense_flags,
                                uint16_t* dense_rows, double* bm_scores, int64_t* bm_ids, int32_t* bm_counts,
                                cmr_stream_t stream) {
-  CMR_CHECK_ARG(n_parts >= 1 && n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
-  CMR_CHECK_ARG(gathered && dense_scores && dense_ids && dense_counts && dense_flags, "null pointer argument");
-  CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 output");
-  const int n = n_parts * (pool > kb ? pool : kb);
-  const size_t smem = (size_t)n * 16 + (size_t)pool * 4 + 16;
-  CMR_CHECK_ARG(smem <= 48 * 1024, "too many shards x list entries for one merge (%d)", n);
-  shard_merge_kernel<<<n_queries, SHARD_THREADS, smem, (cudaStream_t)stream>>>(
-      (const unsigned char*)gathered, n_parts, n_queries, pool, kb, dim, dense_scores, (long long*)dense_ids,
-      dense_counts, dense_flags, reinterpret_cast<uint4*>(dense_rows), bm_scores, (long long*)bm_ids, bm_counts);
+  if (pool < 0 || kb < 0 || dim < 0 || dim % 8 != 0 || n_queries <= 0) {
+    set_error("bad shard message shape");
+    return CMR_EINVAL;
+  }
+  return launch_shard_merge(gathered, (size_t)n_queries * shard_msg_bytes(pool, kb, dim), nullptr, nullptr, 0, nullptr,
+                            n_parts, n_queries, pool, kb, dim, dense_scores, dense_ids, dense_counts, dense_flags,
+                            dense_rows, bm_scores, bm_ids, bm_counts, stream);
+}
+
+extern "C" int cmr_shard_exchange_pack(const double* dense_scores, const int64_t* dense_ids,
+                                       const int32_t* dense_counts, const int32_t* dense_flags, int pool,
+                                       const double* bm_scores, const int64_t* bm_ids, const int32_t* bm_counts,
+                                       int kb, const uint16_t* emb, int64_t n_rows, int dim, int64_t row_offset,
+                                       int n_queries, const cmr_shard_p2p* x, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
+  CMR_CHECK_ARG(dense_scores && dense_ids && dense_counts && x, "null pointer argument");
+  CMR_CHECK_ARG(kb == 0 || (bm_scores && bm_ids && bm_counts), "null BM25 list");
+  CMR_CHECK_ARG(dim == 0 || n_rows == 0 || emb, "null embedding matrix");
+  CMR_CHECK_ARG(x->peer_recv && x->peer_flags && x->state && x->n_parts >= 1 && x->my_rank >= 0 &&
+                    x->my_rank < x->n_parts, "incomplete peer-exchange descriptor");
+  CMR_CHECK_ARG((size_t)n_queries * shard_msg_bytes(pool, kb, dim) <= x->slot_stride && x->slot_stride % 16 == 0 &&
+                    x->parity_stride >= x->slot_stride * (size_t)x->n_parts && x->parity_stride % 16 == 0,
+                "peer receive buffer too small for this message");
+  ShardP2P p{(const unsigned long long*)x->peer_recv, (const unsigned long long*)x->peer_flags, (unsigned int*)x->state,
+             x->n_parts, x->my_rank, x->slot_stride, x->parity_stride};
+  shard_pack_kernel<true><<<n_queries, SHARD_THREADS, 0, (cudaStream_t)stream>>>(
+      dense_scores, (const long long*)dense_ids, dense_counts, dense_flags, pool, bm_scores, (const long long*)bm_ids,
+      bm_counts, kb, reinterpret_cast<const uint4*>(emb), n_rows, dim, row_offset, nullptr, p);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
+}
+
+extern "C" int cmr_shard_exchange_merge(const void* local_recv, const uint32_t* local_flags, const cmr_shard_p2p* x,
+                                        int32_t* timeout_flag, int n_queries, int pool, int kb, int dim,
+                                        double* dense_scores, int64_t* dense_ids, int32_t* dense_counts,
+                                        int32_t* dense_flags, uint16_t* dense_rows, double* bm_scores,
+                                        int64_t* bm_ids, int32_t* bm_counts, cmr_stream_t stream) {
+  CMR_CHECK_ARG(local_recv && local_flags && x && x->state && timeout_flag, "null pointer argument");
+  return launch_shard_merge(local_recv, (size_t)x->slot_stride, local_flags, (const unsigned int*)x->state,
+                            x->parity_stride, timeout_flag, x->n_parts, n_queries, pool, kb, dim, dense_scores,
+                            dense_ids, dense_counts, dense_flags, dense_rows, bm_scores, bm_ids, bm_counts, stream);
 }

@@ -157,9 +157,19 @@ class HybridEngine:
         finally:
             self.comm = comm
         dim = self.emb.shape[1] if p.use_mmr else 0
-        msg = ops.shard_pack(dense, bm_local, self.emb if p.use_mmr else None, row_offset=self.row_offset)
-        gathered = comm.all_gather_bytes(msg)
-        d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_merge(gathered, pool, p.k_bm25 if hybrid else 0, dim)
+        kb = p.k_bm25 if hybrid else 0
+        b = q_bf16.shape[0]
+        peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim))
+        if peer is not None:
+            # stores into every rank's receive buffer over NVLink + flags: no collective launch
+            ops.shard_exchange_pack(dense, bm_local, self.emb if p.use_mmr else None, peer.struct,
+                                    row_offset=self.row_offset)
+            d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_exchange_merge(
+                peer.recv, peer.flags, peer.struct, peer.timeout, b, pool, kb, dim)
+        else:
+            msg = ops.shard_pack(dense, bm_local, self.emb if p.use_mmr else None, row_offset=self.row_offset)
+            gathered = comm.all_gather_bytes(msg)
+            d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_merge(gathered, pool, kb, dim)
         self.last_dense_flags = d_f
         if p.use_mmr:
             v_ids, v_sims, v_cnt = ops.mmr_select(rows, d_s, d_i, d_c, min(k_vec, pool), p.mmr_lambda)

@@ -341,3 +341,49 @@ def dense_topk_certified(emb: torch.Tensor, queries: torch.Tensor, k: int, *, ro
                                     algo="exact")
         scores[bad], ids[bad], counts[bad], flags[bad] = s2, i2, c2, f2
     return scores, ids, counts, flags
+
+
+class ShardP2PStruct(__import__("ctypes").Structure):
+    """Mirror of ``cmr_shard_p2p`` (include/cmrag.h)."""
+    import ctypes as _C
+    _fields_ = [("peer_recv", _C.c_void_p), ("peer_flags", _C.c_void_p), ("state", _C.c_void_p),
+                ("n_parts", _C.c_int32), ("my_rank", _C.c_int32), ("slot_stride", _C.c_uint64),
+                ("parity_stride", _C.c_uint64)]
+
+
+def shard_exchange_pack(dense, bm, emb: Optional[torch.Tensor], x: "ShardP2PStruct", *, row_offset: int = 0) -> None:
+    """cmr_shard_exchange_pack: like shard_pack, but the message is stored directly into every
+    rank's receive buffer over NVLink and the epoch flags are raised (no collective)."""
+    import ctypes as C
+    d_s, d_i, d_c, d_f = dense
+    b, pool = d_s.shape
+    kb = 0 if bm is None else bm[0].shape[1]
+    dim = 0 if emb is None else emb.shape[1]
+    bp = (None, None, None) if bm is None else (bm[0].data_ptr(), bm[1].data_ptr(), bm[2].data_ptr())
+    with torch.cuda.device(d_s.device):
+        _lib.check(_lib.load().cmr_shard_exchange_pack(d_s.data_ptr(), d_i.data_ptr(), d_c.data_ptr(), _ptr(d_f), pool,
+                                                       *bp, kb, _ptr(emb), 0 if emb is None else emb.shape[0], dim,
+                                                       row_offset, b, C.byref(x), _stream()))
+
+
+def shard_exchange_merge(local_recv: torch.Tensor, local_flags: torch.Tensor, x: "ShardP2PStruct",
+                         timeout_flag: torch.Tensor, n_queries: int, pool: int, kb: int, dim: int):
+    """cmr_shard_exchange_merge: wait for every rank's flag of this epoch, then merge.  Same
+    outputs as shard_merge."""
+    import ctypes as C
+    dev = local_recv.device
+    b = n_queries
+    d_s = torch.empty((b, pool), dtype=torch.float64, device=dev)
+    d_i = torch.empty((b, pool), dtype=torch.int64, device=dev)
+    d_c = torch.empty((b,), dtype=torch.int32, device=dev)
+    d_f = torch.empty((b,), dtype=torch.int32, device=dev)
+    rows = torch.empty((b, pool, dim), dtype=torch.bfloat16, device=dev) if dim else None
+    b_s = torch.empty((b, kb), dtype=torch.float64, device=dev) if kb else None
+    b_i = torch.empty((b, kb), dtype=torch.int64, device=dev) if kb else None
+    b_c = torch.empty((b,), dtype=torch.int32, device=dev) if kb else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_shard_exchange_merge(local_recv.data_ptr(), local_flags.data_ptr(), C.byref(x),
+                                                        timeout_flag.data_ptr(), b, pool, kb, dim, d_s.data_ptr(),
+                                                        d_i.data_ptr(), d_c.data_ptr(), d_f.data_ptr(), _ptr(rows),
+                                                        _ptr(b_s), _ptr(b_i), _ptr(b_c), _stream()))
+    return d_s, d_i, d_c, d_f, rows, b_s, b_i, b_c

@@ -32,14 +32,64 @@ def shard_range(n: int, rank: int, world: int, align: int = 16) -> Tuple[int, in
     return lo, min(n, lo + per)
 
 
-class ShardComm:
-    """The two exchanges of the sharded hot path."""
+class PeerExchange:
+    """Receive buffers + flag words of the peer-memory exchange (cmr_shard_exchange_*), mapped
+    into every rank of the box through torch's symmetric memory (cudaMalloc'ed buffers whose
+    handles are exchanged once; afterwards the kernels store into peers over NVLink)."""
 
-    def __init__(self, group=None, merge_fn: Optional[Callable] = None):
+    def __init__(self, group, device, slot_bytes: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.slot = (int(slot_bytes) + 255) // 256 * 256
+        self.parity = self.slot * world
+        with torch.cuda.device(device):
+            self.recv = symm_mem.empty(2 * self.parity, dtype=torch.uint8, device=device)
+            self.flags = symm_mem.empty(max(2 * world, 64), dtype=torch.int32, device=device)
+            self.recv.zero_()
+            self.flags.zero_()
+            h_recv = symm_mem.rendezvous(self.recv, self.group)
+            h_flags = symm_mem.rendezvous(self.flags, self.group)
+        self._handles = (h_recv, h_flags)
+        self.peer_recv = torch.tensor([int(p) for p in h_recv.buffer_ptrs], dtype=torch.int64, device=device)
+        self.peer_flags = torch.tensor([int(p) for p in h_flags.buffer_ptrs], dtype=torch.int64, device=device)
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=device)
+        self.struct = ops.ShardP2PStruct(self.peer_recv.data_ptr(), self.peer_flags.data_ptr(), self.state.data_ptr(),
+                                         world, rank, self.slot, self.parity)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)     # every rank's buffers are zeroed before anyone stores into them
+
+
+class ShardComm:
+    """The exchanges of the sharded hot path."""
+
+    def __init__(self, group=None, merge_fn: Optional[Callable] = None, peer_memory: Optional[bool] = None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._merge_fn = merge_fn  # injectable for the CPU (gloo) tests
+        # peer-memory exchange: on by default with NCCL (CMRAG_P2P=0 turns it off); any failure
+        # to set it up falls back to the NCCL all-gather of the same messages
+        if peer_memory is None:
+            import os
+            peer_memory = os.environ.get("CMRAG_P2P", "1") != "0" and dist.get_backend(group) == "nccl"
+        self.peer_memory = bool(peer_memory)
+        self.peer: Optional[PeerExchange] = None
+        self.peer_error: Optional[str] = None
+
+    def peer_exchange(self, device, slot_bytes: int) -> Optional[PeerExchange]:
+        """The PeerExchange big enough for ``slot_bytes`` per rank (collective on first use /
+        growth: every rank calls it with the same size), or None when unavailable."""
+        if not self.peer_memory:
+            return None
+        if self.peer is None or self.peer.slot < slot_bytes:
+            try:
+                self.peer = PeerExchange(self.group, device, slot_bytes)
+            except Exception as exc:  # no symmetric memory on this build / topology
+                self.peer_memory, self.peer, self.peer_error = False, None, repr(exc)
+        return self.peer
 
     def _merge(self, scores, ids, counts):
         if self._merge_fn is not None:

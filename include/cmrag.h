@@ -258,6 +258,38 @@ int cmr_shard_merge(const void* gathered, int n_parts, int n_queries, int pool, 
                     uint16_t* dense_rows, double* bm_scores, int64_t* bm_ids, int32_t* bm_counts,
                     cmr_stream_t stream);
 
+/* K7 over peer memory (no collective launch).  Every rank owns a receive buffer and a few flag
+ * words in memory that all ranks of the box have mapped (e.g. a torch symmetric-memory
+ * rendezvous: cudaMalloc + IPC / fabric handles over NVLink).  cmr_shard_exchange_pack is
+ * cmr_shard_pack with the stores going straight into EVERY rank's receive buffer
+ * (slot my_rank of the buffer selected by the step's parity); when its last CTA has finished it
+ * raises flag [parity][my_rank] = epoch on every rank (st.release.sys).
+ * cmr_shard_exchange_merge waits (ld.acquire.sys) until all n_parts flags of the epoch are
+ * up, then merges like cmr_shard_merge.  `state` (two uint32, zero-initialised, rank-local)
+ * carries the epoch from step to step, so the pair can be captured in a CUDA graph.  Two
+ * buffers alternate (parity): a rank can be at most one step ahead of its slowest peer.
+ * A rank that never arrives makes the merge give up after ~10 s and set *timeout_flag. */
+typedef struct cmr_shard_p2p {
+  const uint64_t* peer_recv;   /* device array [n_parts]: address of every rank's receive buffer   */
+  const uint64_t* peer_flags;  /* device array [n_parts]: address of every rank's flag words (u32,
+                                  at least 2 * n_parts, zero-initialised)                         */
+  uint32_t* state;             /* device, rank-local, 2 x uint32, zero-initialised                */
+  int32_t n_parts, my_rank;
+  uint64_t slot_stride;        /* bytes reserved per source rank  (>= n_queries * msg bytes)      */
+  uint64_t parity_stride;      /* bytes between the two alternating buffers (>= n_parts * slot)   */
+} cmr_shard_p2p;
+
+int cmr_shard_exchange_pack(const double* dense_scores, const int64_t* dense_ids, const int32_t* dense_counts,
+                            const int32_t* dense_flags, int pool, const double* bm_scores,
+                            const int64_t* bm_ids, const int32_t* bm_counts, int kb, const uint16_t* emb,
+                            int64_t n_rows, int dim, int64_t row_offset, int n_queries,
+                            const cmr_shard_p2p* x, cmr_stream_t stream);
+int cmr_shard_exchange_merge(const void* local_recv, const uint32_t* local_flags, const cmr_shard_p2p* x,
+                             int32_t* timeout_flag, int n_queries, int pool, int kb, int dim,
+                             double* dense_scores, int64_t* dense_ids, int32_t* dense_counts,
+                             int32_t* dense_flags, uint16_t* dense_rows, double* bm_scores, int64_t* bm_ids,
+                             int32_t* bm_counts, cmr_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * N3  Query tokeniser on the device (rag/retrieval/bm25.py:34-70,194-195): letter runs of
  *     [A-Za-z] + U+00C0..U+00FF (without U+00D7 / U+00F7), lower-cased, one-character tokens

@@ -178,3 +178,20 @@ def test_pipelined_search_returns_each_batch_in_order(small_world):
     for g, w in zip(got, want):
         for a, b in zip(g, w):
             assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.timeout(300)
+def test_multi_gpu_sharded_search_peer_memory_and_nccl():
+    """Needs >= 2 GPUs on the box (skipped otherwise): tools/shard_check.py under torchrun --
+    peer-memory exchange, NCCL exchange and the unsharded engine agree bit for bit."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    n_gpu = torch.cuda.device_count()
+    if n_gpu < 2:
+        pytest.skip("one GPU only")
+    root = Path(__file__).resolve().parents[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n_gpu, 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29577", str(root / "tools" / "shard_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "shard_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
