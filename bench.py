@@ -239,23 +239,31 @@ def main():
         return float(t.item())
 
     # ---- value: device-resident inputs, CUDA events, max over ranks -------------
+    # The step is replayed from its CUDA graph (one launch per step); the queries of every
+    # step already live in HBM and are copied device-to-device into the graph's input buffers.
     clocks = ClockSampler(local)
-    stream = torch.cuda.current_stream()
+    q_res = q_f32.contiguous()
+    gv = GraphedSearch(eng, p, a.batch, max_terms=16)
+    stream = gv.stream
+
+    def resident_step(s):
+        gv.launch_resident(q_res[s * a.batch:(s + 1) * a.batch], *dev_terms[s])
     dense_ms, lex_ms = [], []
     for s in range(a.warmup):
-        eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p)
+        resident_step(s)
     clocks.start()
     barrier()
     clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for s in range(a.warmup, n_steps):
-        eng.search(q_bf16[s * a.batch:(s + 1) * a.batch], *dev_terms[s], p)
+        resident_step(s)
     ev1.record(stream)
     barrier()
     total_ms = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = total_ms / a.steps
     value = a.batch * a.steps / (total_ms * 1e-3)
+    stream = torch.cuda.current_stream()
 
     # ---- per-stage device time.  Single shard: the same steps again with timing events at the
     # stage boundaries INSIDE the step (a stage timed back to back on its own runs at other
@@ -403,7 +411,7 @@ def main():
 
     # kernels per step (resident loop): dense = sample pass, bound, main pass, finalize (tcgen05 path)
     # or scan, finalize; then gather, mmr, bm25 tile, bm25 finalize, fuse; sharded: + 2 merges
-    launches_per_step = (4 if a.batch > 8 else 2) + 5 + (2 if world > 1 else 0)
+    launches_per_step = 1 + (4 if a.batch > 8 else 2) + 5 + (2 if world > 1 else 0)   # +1: f32 -> bf16 of the queries
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic",
@@ -429,7 +437,7 @@ def main():
         # The captured CUDA graphs hold NCCL kernels of this communicator; tearing the
         # process group down under them can block forever.  Drop the graphs, drain the
         # device, and leave without destroy_process_group (exit code 0 on every rank).
-        del gs, g1
+        del gs, g1, gv
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()

@@ -274,6 +274,26 @@ class GraphedSearch:
             self.h_cnt.copy_(cnt, non_blocking=True)
             self.done.record(self.stream)
 
+    def launch_resident(self, q_f32: torch.Tensor, q_terms: Optional[torch.Tensor] = None,
+                        q_ptr: Optional[torch.Tensor] = None):
+        """Replay with inputs that already live in HBM (device tensors of the captured shapes:
+        q_f32 [B, dim] float32, q_terms int32 (at most B * max_terms), q_ptr int32 [B + 1]).
+        Results stay on the device (``self.out``); nothing is copied to the host."""
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            self.q_f32.copy_(q_f32, non_blocking=True)
+            if self.hybrid:
+                n = q_terms.numel()
+                if n > self.q_terms.numel():
+                    raise ValueError("too many query tokens for this graph (raise max_terms)")
+                self.q_terms[:n].copy_(q_terms, non_blocking=True)
+                self.q_ptr.copy_(q_ptr, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.out = self._run()
+            self.done.record(self.stream)
+        return self.out
+
     def result(self):
         """Wait for the last launch() of THIS object and hand back its pinned result buffers."""
         self.done.synchronize()
