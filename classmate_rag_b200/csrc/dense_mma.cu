@@ -47,7 +47,10 @@ constexpr int MM_SAMPLE = 0, MM_MAIN = 1, MM_NEARDUP = 2;
 constexpr int MM_CAP_PER_KP = 128;   // candidates finalize can collect per query = 128 * KP
 constexpr int MM_SAMPLE_STRIDE = 16; // SAMPLE mode visits every 16th full tile ...
 constexpr int MM_SAMPLE_STRIDE_LARGE = 32;   // ... every 32nd from MM_LARGE_TILES tiles on (2M rows): the
-constexpr int MM_LARGE_TILES = 8192;         // bound is then still the KP-th of >= 256 tile maxima
+#ifndef CMR_MM_LARGE_TILES
+#define CMR_MM_LARGE_TILES 8192
+#endif
+constexpr int MM_LARGE_TILES = CMR_MM_LARGE_TILES;   // bound is then still the KP-th of >= 256 tile maxima
 constexpr int MM_MAX_GROUPS = 49152; // threshold kernel keeps the group maxima in shared memory
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
@@ -433,7 +436,19 @@ dense_thresh_warp_kernel(const float* __restrict__ gmax, int n_groups, int gstri
     return;
   }
   u32* v = s_vals + (size_t)warp * n_groups;
-  for (int g = lane; g < n_groups; g += 32) v[g] = f32_orderable(gmax[(size_t)g * gstride + q]);
+  for (int g0 = lane; g0 < n_groups; g0 += 32 * 8) {  // 8 independent loads in flight per lane
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + 32 * u;
+      if (g < n_groups) x[u] = gmax[(size_t)g * gstride + q];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + 32 * u;
+      if (g < n_groups) v[g] = f32_orderable(x[u]);
+    }
+  }
   __syncwarp();
   u32 prefix = 0;
   for (int bit = 31; bit >= 0; --bit) {
@@ -487,11 +502,53 @@ dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__
   }
   __syncthreads();
   const int m = s_total < cap_total ? s_total : cap_total;
+  // Ranking m keys against each other is quadratic, and only the KP best matter: find the
+  // KP-th largest score word by bisection (32 rounds of counting), then rank just the keys
+  // that reach it (the KP best plus ties of the last one).
+  u32 floor_word = 0;
+  if (m > 4 * KP) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const u32 c = floor_word | (1u << bit);
+      int local = 0;
+      for (int e = tid; e < m; e += FIN_THREADS) local += (u32)(s_keys[e] >> 32) >= c;
+      local = __reduce_add_sync(0xFFFFFFFFu, local);
+      if (tid == 0) s_total = 0;
+      __syncthreads();
+      if (lane == 0 && local) atomicAdd(&s_total, local);
+      __syncthreads();
+      if (s_total >= KP) floor_word = c;
+      __syncthreads();
+    }
+  }
+  // survivors (score word >= floor) are compacted and ranked among themselves; with more than
+  // 4*KP of them (a crowd of ties at the boundary) every key is ranked against all m instead
+  u64* s_surv = reinterpret_cast<u64*>(s_score + KP);   // [4 * KP]
+  if (tid == 0) s_total = 0;
+  __syncthreads();
   for (int e = tid; e < m; e += FIN_THREADS) {
     const u64 key = s_keys[e];
-    int rank = 0;
-    for (int j = 0; j < m; ++j) rank += s_keys[j] > key;
-    if (rank < KP) s_out[rank] = key;
+    if ((u32)(key >> 32) >= floor_word) {
+      const int slot = atomicAdd(&s_total, 1);
+      if (slot < 4 * KP) s_surv[slot] = key;
+    }
+  }
+  __syncthreads();
+  const int n_surv = s_total;
+  if (n_surv <= 4 * KP) {
+    for (int e = tid; e < n_surv; e += FIN_THREADS) {
+      const u64 key = s_surv[e];
+      int rank = 0;
+      for (int j = 0; j < n_surv; ++j) rank += s_surv[j] > key;
+      if (rank < KP) s_out[rank] = key;
+    }
+  } else {
+    for (int e = tid; e < m; e += FIN_THREADS) {
+      const u64 key = s_keys[e];
+      if ((u32)(key >> 32) < floor_word) continue;
+      int rank = 0;
+      for (int j = 0; j < m && rank < KP; ++j) rank += s_keys[j] > key;
+      if (rank < KP) s_out[rank] = key;
+    }
   }
   __syncthreads();
   dense_finalize_tail<KP>(s_out, s_score, emb, dim, queries + (size_t)qi * dim, row_offset, k, cert_eps,
@@ -617,13 +674,13 @@ size_t dense_mma_workspace_bytes(long long n_rows, int dim, int n_queries, int k
 
 template <int KPL>
 static int launch_finalize_cand(const DenseArgs& a, const MmaPlan& p, const u64* cand, const int* cnt) {
-  const size_t smem = (size_t)p.cap_total * 8 + (size_t)p.kp * 16 + 16;
+  const size_t smem = (size_t)p.cap_total * 8 + (size_t)p.kp * 16 + (size_t)4 * p.kp * 8 + 16;
   static int attr_dev_mask = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_dev_mask & (1 << dev))) {
     cudaError_t e = cudaFuncSetAttribute(dense_finalize_cand_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         MM_CAP_PER_KP * 32 * KPL * 8 + 32 * KPL * 16 + 16);
+                                         MM_CAP_PER_KP * 32 * KPL * 8 + 32 * KPL * 16 + 4 * 32 * KPL * 8 + 16);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense_finalize_cand)");
     attr_dev_mask |= (1 << dev);
   }

@@ -226,3 +226,31 @@ def test_bm25store_batch_on_device_tokenizer_equals_host_path(world, golden):
     finally:
         store.device_tokenize_from = 64
     assert got == want
+
+
+def test_dropin_edge_cases(tmp_path, golden):
+    """Empty stores, non-hybrid, no MMR, top_k beyond the corpus, filters that match nothing."""
+    from classmate_rag_b200.retrieval import BM25Store, ChromaVectorStore, HybridRetriever
+    c = golden["corpus"]
+    emb_f32 = o.bf16_bits_to_f32(bits_from_hex(c["emb_bits"], (c["n"], c["d"])))
+    emb = _Emb()
+    emb.vec = emb_f32[3]
+    vs = ChromaVectorStore(persist_dir=tmp_path / "chroma", collection_name="edge")
+    bm = BM25Store(index_dir=tmp_path / "bm25")
+    hr = HybridRetriever(vector_store=vs, bm25_store=bm, embedder=emb)
+    assert hr.retrieve(question="gradient", top_k=8) == []                      # both stores empty
+    assert vs.query(query_embeddings=emb_f32[0], top_k=3) == [] and vs.count() == 0
+    bm.upsert_many(ids=c["ids"][:10], texts=c["docs"][:10], metadatas=c["metas"][:10])
+    only_bm = hr.retrieve(question="gradient descent kernel", top_k=8)          # vector store still empty
+    assert only_bm and all(x["scores"]["vector_distance"] is None for x in only_bm)
+    assert [x["id"] for x in only_bm] == [x["id"] for x in bm.search(query="gradient descent kernel", top_k=8)]
+    vs.upsert(ids=c["ids"][:10], documents=c["docs"][:10], metadatas=c["metas"][:10], embeddings=emb_f32[:10])
+    out = hr.retrieve(question="gradient descent kernel", top_k=50)             # top_k beyond what exists
+    assert 0 < len(out) <= 16 and out[0]["scores"]["fused"] >= out[-1]["scores"]["fused"]
+    dense_only = HybridRetriever(vector_store=vs, bm25_store=bm, embedder=emb, use_mmr=False).retrieve(
+        question="anything", top_k=4, hybrid=False)
+    assert [x["id"] for x in dense_only] == [x["id"] for x in vs.query(query_embeddings=emb.vec, top_k=8)][:4]
+    assert dense_only[0]["id"] == c["ids"][3] and all(x["scores"]["bm25_score"] is None for x in dense_only)
+    assert hr.retrieve(question="gradient", filters={"course": "NoSuchCourse"}, top_k=8) == []
+    with pytest.raises(ValueError):
+        vs.query(query_embeddings=np.zeros(c["d"] * 2, dtype=np.float32), top_k=3)   # wrong dimension
