@@ -2,6 +2,7 @@
 memory, streams.  All compute is in the CUDA library."""
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -343,12 +344,11 @@ def dense_topk_certified(emb: torch.Tensor, queries: torch.Tensor, k: int, *, ro
     return scores, ids, counts, flags
 
 
-class ShardP2PStruct(__import__("ctypes").Structure):
+class ShardP2PStruct(ctypes.Structure):
     """Mirror of ``cmr_shard_p2p`` (include/cmrag.h)."""
-    import ctypes as _C
-    _fields_ = [("peer_recv", _C.c_void_p), ("peer_flags", _C.c_void_p), ("state", _C.c_void_p),
-                ("n_parts", _C.c_int32), ("my_rank", _C.c_int32), ("slot_stride", _C.c_uint64),
-                ("parity_stride", _C.c_uint64)]
+    _fields_ = [("peer_recv", ctypes.c_void_p), ("peer_flags", ctypes.c_void_p), ("state", ctypes.c_void_p),
+                ("n_parts", ctypes.c_int32), ("my_rank", ctypes.c_int32), ("slot_stride", ctypes.c_uint64),
+                ("parity_stride", ctypes.c_uint64)]
 
 
 def shard_exchange_pack(dense, bm, emb: Optional[torch.Tensor], x: "ShardP2PStruct", *, row_offset: int = 0) -> None:

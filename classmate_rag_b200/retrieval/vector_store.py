@@ -220,6 +220,22 @@ class ChromaVectorStore:
     def compact(self) -> None:
         self._ensure_collection().compact()
 
+    def dedupe(self, threshold: float = 0.95) -> List[str]:
+        """Near-duplicate filter over the stored embeddings (the `rag rebuild` hook,
+        rag/admin/backup.py:226-233; keep-first rule of rag/utils/dedup.py:40-55 on cosine):
+        a row is dropped iff an earlier KEPT row has q.c >= threshold.  Runs on the tensor
+        cores (classmate_rag_b200.neardup).  Returns the ids removed, in insertion order."""
+        from .. import neardup
+        col = self._ensure_collection()
+        col.compact()
+        if col.n_rows < 2:
+            return []
+        keep = neardup.neardup_keep_mask(col.matrix().contiguous(), threshold).bool().cpu().numpy()
+        dropped = [cid for cid, k in zip(col.ids, keep) if not k]
+        col.delete(dropped)
+        col.compact()
+        return dropped
+
     def count(self) -> int:
         col = self._ensure_collection()
         return col.n_rows - col.n_dead

@@ -254,3 +254,25 @@ def test_dropin_edge_cases(tmp_path, golden):
     assert hr.retrieve(question="gradient", filters={"course": "NoSuchCourse"}, top_k=8) == []
     with pytest.raises(ValueError):
         vs.query(query_embeddings=np.zeros(c["d"] * 2, dtype=np.float32), top_k=3)   # wrong dimension
+
+
+def test_vector_store_dedupe_hook(tmp_path):
+    """`rag rebuild` hook: near-duplicate rows (cos >= 0.95 to an earlier kept row) are removed."""
+    from classmate_rag_b200.retrieval import ChromaVectorStore
+    rng = np.random.default_rng(4)
+    n, d = 600, 64
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    dup_of = {50: 10, 51: 50, 300: 299, 599: 0}
+    for i, j in dup_of.items():
+        v = x[j] + 0.02 * rng.standard_normal(d).astype(np.float32) / np.sqrt(d)
+        x[i] = v / np.linalg.norm(v)
+    x = o.bf16_bits_to_f32(o.f32_to_bf16_bits(x))
+    ids = [f"c{i}" for i in range(n)]
+    vs = ChromaVectorStore(persist_dir=tmp_path / "chroma", collection_name="dd")
+    vs.upsert(ids=ids, documents=ids, metadatas=[{} for _ in ids], embeddings=x)
+    want_keep = o.neardup_keep_mask(o.f32_to_bf16_bits(x), 0.95)
+    dropped = vs.dedupe(0.95)
+    assert dropped == [ids[i] for i in range(n) if not want_keep[i]] == ["c50", "c51", "c300", "c599"]
+    assert vs.count() == n - 4 and vs.dedupe(0.95) == []
+    assert vs.query(query_embeddings=x[50], top_k=1)[0]["id"] == "c10"
