@@ -227,6 +227,7 @@ class GraphedSearch:
                 with torch.cuda.graph(g, stream=self.stream):
                     self.out = self._run()
                 self.graph = g
+                self._peer_generation = getattr(self.engine.comm, "peer_generation", 0)
             ids, fused, vd, bm, cnt = self.out
             self.h_ids = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
             self.h_fused = torch.empty(fused.shape, dtype=fused.dtype).pin_memory()
@@ -255,8 +256,14 @@ class GraphedSearch:
             self.h_terms[: int(ptr[-1])].copy_(flat[: int(ptr[-1])])
             self.h_ptr.copy_(ptr)
 
+    def _check_graph(self):
+        if self.graph is not None and getattr(self.engine.comm, "peer_generation", 0) != getattr(self, "_peer_generation", 0):
+            raise RuntimeError("the peer-exchange buffers were re-allocated after this graph was captured; "
+                               "build a new GraphedSearch")
+
     def launch(self):
         """H2D copies + graph replay + D2H copies on the engine's stream (asynchronous)."""
+        self._check_graph()
         with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
             self.q_f32.copy_(self.h_q, non_blocking=True)
             if self.hybrid:
@@ -279,6 +286,7 @@ class GraphedSearch:
         """Replay with inputs that already live in HBM (device tensors of the captured shapes:
         q_f32 [B, dim] float32, q_terms int32 (at most B * max_terms), q_ptr int32 [B + 1]).
         Results stay on the device (``self.out``); nothing is copied to the host."""
+        self._check_graph()
         with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
             self.q_f32.copy_(q_f32, non_blocking=True)
             if self.hybrid:

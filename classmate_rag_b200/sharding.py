@@ -78,6 +78,8 @@ class ShardComm:
         self.peer_memory = bool(peer_memory)
         self.peer: Optional[PeerExchange] = None
         self.peer_error: Optional[str] = None
+        self.peer_generation = 0
+        self.min_slot_bytes = 16 << 20
 
     def peer_exchange(self, device, slot_bytes: int) -> Optional[PeerExchange]:
         """The PeerExchange big enough for ``slot_bytes`` per rank (collective on first use /
@@ -86,7 +88,10 @@ class ShardComm:
             return None
         if self.peer is None or self.peer.slot < slot_bytes:
             try:
-                self.peer = PeerExchange(self.group, device, slot_bytes)
+                # generous first allocation: a later, larger message would need new buffers, and
+                # CUDA graphs captured before hold the old addresses (see GraphedSearch.launch)
+                self.peer = PeerExchange(self.group, device, max(int(slot_bytes), self.min_slot_bytes))
+                self.peer_generation += 1
             except Exception as exc:  # no symmetric memory on this build / topology
                 self.peer_memory, self.peer, self.peer_error = False, None, repr(exc)
         return self.peer

@@ -56,6 +56,14 @@ def main():
             out = gs(qh, terms)
         for a, b in zip(out, want):
             assert a.tobytes() == b.cpu().numpy().tobytes(), name + " graph"
+        # the other message shapes: no lexical list (non-hybrid), no rows (MMR off)
+        for hyb, mmr in ((False, True), (True, False), (False, False)):
+            p2 = SearchParams(top_k=10, hybrid=hyb, use_mmr=mmr)
+            w2 = [t.clone() for t in full.search(qb, qt, qp, p2)]
+            g2 = [t.clone() for t in eng.search(qb, qt, qp, p2)]
+            torch.cuda.synchronize()
+            for a, b in zip(g2, w2):
+                assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes(), (name, hyb, mmr)
         results[name] = True
         del gs, eng
         torch.cuda.synchronize()
