@@ -133,6 +133,19 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// v[j] for a run-time j: registers cannot be indexed, a dense switch becomes one indirect branch
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  switch (j) {
+#define CMR_PICK(i) case i: return v[i];
+    CMR_PICK(0) CMR_PICK(1) CMR_PICK(2) CMR_PICK(3) CMR_PICK(4) CMR_PICK(5) CMR_PICK(6) CMR_PICK(7)
+    CMR_PICK(8) CMR_PICK(9) CMR_PICK(10) CMR_PICK(11) CMR_PICK(12) CMR_PICK(13) CMR_PICK(14) CMR_PICK(15)
+    CMR_PICK(16) CMR_PICK(17) CMR_PICK(18) CMR_PICK(19) CMR_PICK(20) CMR_PICK(21) CMR_PICK(22) CMR_PICK(23)
+    CMR_PICK(24) CMR_PICK(25) CMR_PICK(26) CMR_PICK(27) CMR_PICK(28) CMR_PICK(29) CMR_PICK(30)
+#undef CMR_PICK
+    default: return v[31];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Work enumeration shared by the three warp roles.  An item is one (A block of 128 rows of
 // the left operand, B tile of 256 rows of the right operand) pair = one TMEM accumulator.
@@ -329,21 +342,27 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tile_max = fmaxf(tile_max, m);
           }
         } else if (q_ok && m >= bound) {
-          // rare: about stride*KP rows per query over the whole scan (MAIN); near-duplicate pairs (NEARDUP)
+          // Rare per thread (about stride*KP rows per query over the whole scan; near-duplicate
+          // pairs in NEARDUP) but at 1024 queries ~40 % of the warp-chunks have a lane in here,
+          // and an epilogue warp has no other warp to hide behind: keep it short.  One branch-free
+          // pass builds the hit mask, then only the set bits are visited (jump-table pick).
+          u32 hits = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (v[j] >= bound) {
-              const long long row = row0 + c * 32 + j;
-              if (MODE == MM_MAIN) {
-                if (row < p.n_rows) {
-                  const int slot = s_cnt[qi]++;   // only this thread touches query qi in this CTA
-                  if (slot < p.cap)
-                    p.cand[((size_t)blockIdx.x * p.n_left + qi) * p.cap + slot] = make_key(v[j], (u32)row);
-                }
-              } else if (row < (long long)qi) {
-                const unsigned long long slot = atomicAdd(p.edge_count, 1ull);
-                if (slot < p.edge_cap) p.edges[slot] = ((u64)(u32)qi << 32) | (u64)(u32)row;
+          for (int j = 0; j < 32; ++j) hits |= (v[j] >= bound ? 1u : 0u) << j;
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const float sv = pick32(v, j);
+            const long long row = row0 + c * 32 + j;
+            if (MODE == MM_MAIN) {
+              if (row < p.n_rows) {
+                const int slot = s_cnt[qi]++;   // only this thread touches query qi in this CTA
+                if (slot < p.cap)
+                  p.cand[((size_t)blockIdx.x * p.n_left + qi) * p.cap + slot] = make_key(sv, (u32)row);
               }
+            } else if (row < (long long)qi) {
+              const unsigned long long slot = atomicAdd(p.edge_count, 1ull);
+              if (slot < p.edge_cap) p.edges[slot] = ((u64)(u32)qi << 32) | (u64)(u32)row;
             }
           }
         }
