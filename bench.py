@@ -279,6 +279,7 @@ def main():
         torch.cuda.synchronize()
         dense_ms = [m[0].elapsed_time(m[1]) for m in marks]
         lex_ms = [m[2].elapsed_time(m[3]) for m in marks]
+        stage_step_ms = float(np.mean([m[0].elapsed_time(m[4]) for m in marks]))   # this (eager) loop's own step
     else:
         def stage_ms(fn):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,6 +293,7 @@ def main():
             return e0.elapsed_time(e1) / a.steps
         dense_ms = [stage_ms(lambda s: eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool))]
         lex_ms = [stage_ms(lambda s: eng.lexical_topk(*dev_terms[s], p.k_bm25))]
+        stage_step_ms = ms_per_step
     clock_info = clocks.stop()
     dense_avg = float(np.mean(dense_ms))
     lex_avg = float(np.mean(lex_ms))
@@ -305,8 +307,8 @@ def main():
     dense_bytes = (hi - lo) * a.dim * 2
     passes = (a.batch + 127) // 128 if a.batch > 8 else 1
     achieved = dense_bytes * passes / (dense_avg * 1e-3) / 1e9
-    dense_kernel = ("dense_mma_kernel<MAIN> (tcgen05/TMA; events bracket cmr_dense_topk = 1/16 sample pass + bound + "
-                    "main pass + finalize)" if a.batch > 8 else
+    dense_kernel = ("dense_mma_kernel<MAIN> (tcgen05/TMA; events bracket cmr_dense_topk = sample pass over every 16th/32nd "
+                    "tile + bound + main pass + finalize)" if a.batch > 8 else
                     "dense_scan_kernel (events bracket cmr_dense_topk = scan + finalize)")
     traffic = None
     tpath = ROOT / "profiles" / "traffic.json"
@@ -321,10 +323,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dense_kernel,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dense_bytes,
-                "avg_launch_ms": dense_avg, "share_of_step": dense_avg / ms_per_step,
+                "avg_launch_ms": dense_avg, "share_of_step": dense_avg / stage_step_ms,
                 "bm25": {"kernel": "bm25_tile_kernel (+finalize)", "algorithmic_bytes_per_step": lex_bytes,
                          "avg_ms_per_step": lex_avg, "achieved": lex_bytes / (lex_avg * 1e-3) / 1e9, "unit": "GB/s",
-                         "frac": lex_bytes / (lex_avg * 1e-3) / 1e9 / hbm_peak, "share_of_step": lex_avg / ms_per_step}}
+                         "frac": lex_bytes / (lex_avg * 1e-3) / 1e9 / hbm_peak, "share_of_step": lex_avg / stage_step_ms}}
 
     # ---- e2e: host buffers in, host results out, every step ---------------------
     q_host = q_f32.cpu().numpy()
