@@ -34,7 +34,7 @@
 
 namespace cmr {
 
-typedef void (*tile_fn_t)(cmr_lex_index, const int*, const int*, const uint8_t*, KeyD*);
+typedef void (*tile_fn_t)(cmr_lex_index, const int*, const int*, const uint8_t*, KeyD*, int);
 #ifndef CMR_BM_THREADS
 #define CMR_BM_THREADS 128
 #endif
@@ -106,7 +106,7 @@ __device__ __forceinline__ void bm25_sweep_full(double* __restrict__ acc, int ti
 template <int KPL, bool PACKED>
 __global__ void __launch_bounds__(BM_THREADS, CMR_BM_MINCTAS)
 bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr,
-                 const uint8_t* __restrict__ row_mask, KeyD* __restrict__ part) {
+                 const uint8_t* __restrict__ row_mask, KeyD* __restrict__ part, int min_tokens) {
   constexpr int KP = 32 * KPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);             // [tile_docs]
@@ -126,6 +126,7 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   for (int i = tid; i < BM_WARPS * KP; i += BM_THREADS) key_clear(s_lists[i]);
   if (tid < BM_WARPS) s_thr[tid] = -INFINITY;
   const int qlo = q_ptr[b], qhi = q_ptr[b + 1];
+  if (qhi - qlo <= min_tokens) return;  // the batch kernel has served this query (CTA-uniform exit)
   KeyD* w_list = s_lists + warp * KP;
   volatile double* w_thr = s_thr + warp;
   const int first_tile = blockIdx.y;
@@ -434,13 +435,530 @@ bm25_finalize_kernel(const KeyD* __restrict__ part, int n_lists, long long row_o
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// bm25_batch_kernel -- the batched form (>= BB_MIN_QUERIES queries, k <= 32, packed postings).
+//
+// The tile kernel above re-reads a dense term's factor column from L2 once per query that
+// contains the term: 32 queries x ~3 dense tokens x 80 MB at 10M documents = 8.8 GB of
+// L2->SM traffic for 2.9 GB of distinct column data, and every token pass ends in a CTA
+// barrier.  Here a CTA owns document tiles and ALL queries of a chunk (<= 32) visit a
+// tile while it is on chip:
+//   * producer warp: one bulk copy (cp.async.bulk + mbarrier complete_tx) per distinct dense
+//     column used by the chunk stages a 256-document slice (2 KB) of it in shared memory,
+//     double buffered -- every column byte leaves HBM/L2 once per chunk, not once per query;
+//   * 16 consumer warps, each owning 2 queries of the chunk (paired heavy + light by an
+//     estimate of their per-slice cost): lane l keeps the float64 accumulators of documents
+//     l, l+32, ... (8 per lane) in REGISTERS and walks the query's tokens in order.  A dense
+//     token is 8 conflict-free LDS.64 + DMUL + DADD; no barrier, no shared-memory
+//     read-modify-write.  A sparse token with postings in the slice spills the 8 accumulators
+//     to a warp-private 2 KB strip, scatters the postings into it (__syncwarp only), and the
+//     next dense token reloads.  Token constants live in the registers of lane j (token j)
+//     and are broadcast with shuffles;
+//   * the postings a query needs for a 2048-document tile (~150) are copied into a
+//     warp-private arena with cp.async one tile ahead (skip-table entries two tiles ahead),
+//     so the token loop never waits for a posting to arrive from HBM;
+//   * the scores are compared with the query's admission threshold straight from registers;
+//     hits go to the (CTA, query) sorted list in shared memory.  Additions happen in query
+//     token order for every document, so the float64 scores equal the tile kernel's bit for bit.
+// Queries longer than BB_MAXT tokens are left to the tile kernel (launched afterwards in
+// its "long queries only" mode).
+// ---------------------------------------------------------------------------------------
+constexpr int BB_SUB = 256;                 // documents per staged slice
+constexpr int BB_R = BB_SUB / 32;           // accumulators per lane
+constexpr int BB_STAGES = 2;
+#ifndef CMR_BB_NC
+#define CMR_BB_NC 24
+#endif
+constexpr int BB_NC = CMR_BB_NC;            // dense columns staged per slice (others are read from L2)
+constexpr int BB_CWARPS = 16;               // consumer warps
+constexpr int BB_QW = 2;                    // queries per consumer warp
+constexpr int BB_QB = BB_CWARPS * BB_QW;    // queries per chunk
+constexpr int BB_THREADS = (BB_CWARPS + 1) * 32;
+constexpr int BB_MAXT = 16;                 // tokens per query served here (one per lane, 16-byte program entry each)
+constexpr int BB_KP = 32;
+constexpr int BB_ARENA = 256;               // postings staged per (query, tile); the rest is read from global
+constexpr int BB_MAX_DENSE = 2048;          // columns the slot -> staged-column map can hold
+constexpr int BB_MIN_QUERIES = 8;
+
+__device__ __forceinline__ u32 bb_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bb_mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bb_mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bb_mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bb_mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BB_DONE;\n"
+      "bra BB_WAIT;\n"
+      "BB_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bb_bulk_load(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bb_cp_async4(u32 dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct __align__(16) BbOp {  // one real token of a query's program (unknown tokens are dropped)
+  double w;         // idf
+  u32 arg;          // BB_OP_COL: byte offset of the staged column inside a stage; BB_OP_GLOBAL: dense slot;
+                    // BB_OP_SPARSE: the lane that holds the token's posting cursor
+  u32 op;
+};
+constexpr u32 BB_OP_COL = 0, BB_OP_GLOBAL = 1, BB_OP_SPARSE = 2;
+
+struct BbTok {      // token j of a query, held by lane j
+  int kind;         // 0 nothing, 1 dense column staged in shared memory, 2 dense column read from global, 3 sparse
+  int arg;          // staged column index / dense slot
+  double w;         // idf
+  const u32* post;  // post_pack + term_ptr[t]
+  const u32* skip;  // tile_skip row of the term
+  const u32* src;   // the current tile's slice: in the warp's arena, or in global memory when it did not fit
+  u32 cur, end;     // unconsumed part of that slice (offsets into src)
+  u32 n0, n1;       // slice bounds (offsets into post) of this CTA's next tile ...
+  u32 m0, m1;       // ... and of the one after
+};
+
+__device__ __forceinline__ double bb_below(double v) {  // largest double strictly below a finite v
+  const long long bits = __double_as_longlong(v);
+  if (v > 0.0) return __longlong_as_double(bits - 1);
+  if (v < 0.0) return __longlong_as_double(bits + 1);
+  return -4.9406564584124654e-324;
+}
+
+// Copy the slices [n0, n1) of the query's sparse tokens into `arena` (asynchronously) and
+// return, per lane, where token `lane`'s slice will be (nullptr: it did not fit).
+__device__ __forceinline__ const u32* bb_stage_slices(const BbTok& tk, u32* arena, int lane) {
+  const u32 len = tk.kind == 3 ? tk.n1 - tk.n0 : 0u;
+  u32 off = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(0xFFFFFFFFu, off, d);
+    if (lane >= d) off += o;
+  }
+  off -= len;  // exclusive prefix
+  const bool fits = len > 0 && off + len <= (u32)BB_ARENA;
+  unsigned todo = __ballot_sync(0xFFFFFFFFu, fits);
+  while (todo) {
+    const int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const u32 l = __shfl_sync(0xFFFFFFFFu, len, j);
+    const u32 o = __shfl_sync(0xFFFFFFFFu, off, j);
+    const u32* g = reinterpret_cast<const u32*>(
+                       __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tk.post), j)) +
+                   __shfl_sync(0xFFFFFFFFu, tk.n0, j);
+    const u32 dst = bb_smem_u32(arena + o);
+    for (u32 i = lane; i < l; i += 32) bb_cp_async4(dst + 4u * i, g + i);
+  }
+  return fits ? arena + off : nullptr;
+}
+
+__global__ void __launch_bounds__(BB_THREADS, 1)
+bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr,
+                  const uint8_t* __restrict__ row_mask, KeyD* __restrict__ part, int n_queries, int chunk_q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_cols = reinterpret_cast<double*>(smem_raw);                      // [STAGES][NC][SUB]
+  double* s_acc = s_cols + (size_t)BB_STAGES * BB_NC * BB_SUB;               // [CWARPS][SUB]
+  KeyD* s_lists = reinterpret_cast<KeyD*>(s_acc + BB_CWARPS * BB_SUB);       // [QB][KP]
+  u32* s_arena = reinterpret_cast<u32*>(s_lists + BB_QB * BB_KP);            // [CWARPS][QW][2][ARENA]
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_arena + (size_t)BB_CWARPS * BB_QW * 2 * BB_ARENA);
+  int* s_colslot = reinterpret_cast<int*>(s_bar + 2 * BB_STAGES);            // [NC] dense slot of staged column c
+  int* s_ncols = s_colslot + BB_NC;                                          // [1] (+3 pad)
+  int* s_cost = s_ncols + 4;                                                 // [QB] estimated per-slice cost of a query
+  int* s_order = s_cost + BB_QB;                                             // [QB] chunk-local query, heaviest first
+  BbOp* s_prog = reinterpret_cast<BbOp*>(s_order + BB_QB);                   // [QB][MAXT] token programs
+  short* s_colmap = reinterpret_cast<short*>(s_prog + BB_QB * BB_MAXT);      // [n_dense] staged index, -1 unused, -2 not staged
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.y * chunk_q;
+  const int q1 = (q0 + chunk_q) < n_queries ? (q0 + chunk_q) : n_queries;
+  const u32 bar_full = bb_smem_u32(s_bar), bar_empty = bb_smem_u32(s_bar + BB_STAGES);
+
+  // ---- set-up: lists, barriers, the chunk's distinct dense columns, query -> warp pairing ----
+  for (int i = tid; i < BB_QB * BB_KP; i += BB_THREADS) key_clear(s_lists[i]);
+  for (int i = tid; i < ix.n_dense; i += BB_THREADS) s_colmap[i] = -1;
+  if (tid == 0) {
+    for (int s = 0; s < BB_STAGES; ++s) {
+      bb_mbar_init(bar_full + 8 * s, 1);
+      bb_mbar_init(bar_empty + 8 * s, BB_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (ix.n_dense > 0) {
+    const int t_lo = q_ptr[q0], t_hi = q_ptr[q1];
+    for (int i = t_lo + tid; i < t_hi; i += BB_THREADS) {
+      const int t = q_terms[i];
+      if (t >= 0 && t < ix.n_terms) {
+        const int slot = ix.dense_slot[t];
+        if (slot >= 0) s_colmap[slot] = 0;  // benign race: every writer stores 0
+      }
+    }
+  }
+  if (tid < BB_QB) {
+    // cost of one 256-document slice of this query: a dense token ~1 unit, a sparse token whose
+    // list reaches most slices ~6 units (spill, scatter, reload), a rare one ~1
+    int cost = -1;
+    const int q = q0 + tid;
+    if (q < q1) {
+      cost = 0;
+      const int lo = q_ptr[q], hi = q_ptr[q + 1];
+      if (hi - lo <= BB_MAXT) {
+        for (int i = lo; i < hi; ++i) {
+          const int t = q_terms[i];
+          if (t < 0 || t >= ix.n_terms) continue;
+          if (ix.dense_slot != nullptr && ix.dense_slot[t] >= 0) { cost += 1; continue; }
+          const long long df = ix.term_ptr[t + 1] - ix.term_ptr[t];
+          cost += (df * BB_SUB >= ix.n_docs / 2) ? 6 : 1;
+        }
+      }
+    }
+    s_cost[tid] = cost;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int n = 0;
+    for (int base = 0; base < ix.n_dense; base += 32) {
+      const int i = base + lane;
+      const bool used = i < ix.n_dense && s_colmap[i] == 0;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, used);
+      if (used) {
+        const int idx = n + __popc(bal & ((1u << lane) - 1u));
+        if (idx < BB_NC) {
+          s_colmap[i] = (short)idx;
+          s_colslot[idx] = i;
+        } else {
+          s_colmap[i] = -2;
+        }
+      }
+      n += __popc(bal);
+    }
+    if (lane == 0) s_ncols[0] = n < BB_NC ? n : BB_NC;
+  } else if (warp == 1) {
+    const int mine = s_cost[lane];
+    int rank = 0;
+    for (int o = 0; o < BB_QB; ++o) {
+      const int c = s_cost[o];
+      rank += (c > mine) || (c == mine && o < lane);
+    }
+    s_order[rank] = lane;  // a permutation of 0..31; absent queries (cost -1) come last
+  }
+  __syncthreads();
+  const int ncols = s_ncols[0];
+  const int subs = ix.tile_docs / BB_SUB;
+
+  if (warp == BB_CWARPS) {
+    // ---- producer: stage the next slice of every column the chunk uses ---------------------
+    u32 it = 0;
+    for (int tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
+      const long long tile_lo = (long long)tile * ix.tile_docs;
+      for (int s = 0; s < subs; ++s, ++it) {
+        const long long doc0 = tile_lo + (long long)s * BB_SUB;
+        if (doc0 >= ix.n_docs) break;
+        const long long rem = ix.n_docs - doc0;
+        const u32 n_here = rem < BB_SUB ? (u32)rem : (u32)BB_SUB;
+        const u32 st = it % BB_STAGES, ph = (it / BB_STAGES) & 1u;
+        bb_mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+        if (lane == 0) bb_mbar_expect_tx(bar_full + 8 * st, (u32)ncols * n_here * 8u);
+        __syncwarp();
+        for (int c = lane; c < ncols; c += 32)
+          bb_bulk_load(bb_smem_u32(s_cols + ((size_t)st * BB_NC + c) * BB_SUB),
+                       ix.dense_imp + (size_t)s_colslot[c] * ix.n_docs + doc0, n_here * 8u, bar_full + 8 * st);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ---------------------------------------------------------------------------
+  // warp w serves the w-th heaviest and the w-th lightest query of the chunk
+  BbTok tk[BB_QW];
+  int ntok[BB_QW], qid[BB_QW];
+  double thr[BB_QW];
+  bool seeded[BB_QW];
+  const int G = (int)gridDim.x;
+#pragma unroll
+  for (int qi = 0; qi < BB_QW; ++qi) {
+    const int ql = s_order[qi == 0 ? warp : BB_QB - 1 - warp];
+    const int q = q0 + ql;
+    qid[qi] = q;
+    ntok[qi] = -1;  // not served here
+    thr[qi] = -INFINITY;
+    seeded[qi] = false;
+    tk[qi].kind = 0; tk[qi].arg = 0; tk[qi].w = 0.0; tk[qi].post = nullptr; tk[qi].skip = nullptr;
+    tk[qi].src = nullptr; tk[qi].cur = tk[qi].end = 0;
+    tk[qi].n0 = tk[qi].n1 = tk[qi].m0 = tk[qi].m1 = 0;
+    if (q < q1) {
+      const int qlo = q_ptr[q], m = q_ptr[q + 1] - qlo;
+      if (m <= BB_MAXT) {
+        ntok[qi] = m;
+        if (lane < m) {
+          const int t = q_terms[qlo + lane];
+          if (t >= 0 && t < ix.n_terms) {
+            tk[qi].w = ix.idf[t];
+            const int slot = ix.dense_slot != nullptr ? ix.dense_slot[t] : -1;
+            if (slot >= 0) {
+              const int cm = s_colmap[slot];
+              tk[qi].kind = cm >= 0 ? 1 : 2;
+              tk[qi].arg = cm >= 0 ? cm : slot;
+            } else {
+              tk[qi].kind = 3;
+              tk[qi].post = ix.post_pack + ix.term_ptr[t];
+              tk[qi].skip = ix.tile_skip + (size_t)t * (ix.n_tiles + 1);
+              const int first = blockIdx.x;  // < n_tiles (grid is clamped)
+              tk[qi].n0 = tk[qi].skip[first];
+              tk[qi].n1 = tk[qi].skip[first + 1];
+              if (first + G < ix.n_tiles) {
+                tk[qi].m0 = tk[qi].skip[first + G];
+                tk[qi].m1 = tk[qi].skip[first + G + 1];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // the query's program: its real tokens in order, 16 bytes each, read back with one broadcast LDS.128
+  int nprog[BB_QW];
+#pragma unroll
+  for (int qi = 0; qi < BB_QW; ++qi) {
+    BbOp* prog = s_prog + (size_t)(warp + qi * BB_CWARPS) * BB_MAXT;
+    const bool real = tk[qi].kind != 0;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, real);
+    nprog[qi] = ntok[qi] < 0 ? 0 : __popc(bal);
+    if (real && ntok[qi] >= 0) {
+      BbOp o;
+      o.w = tk[qi].w;
+      o.op = tk[qi].kind == 1 ? BB_OP_COL : (tk[qi].kind == 2 ? BB_OP_GLOBAL : BB_OP_SPARSE);
+      o.arg = tk[qi].kind == 1 ? (u32)tk[qi].arg * (u32)(BB_SUB * 8) : (tk[qi].kind == 2 ? (u32)tk[qi].arg : (u32)lane);
+      prog[__popc(bal & ((1u << lane) - 1u))] = o;
+    }
+  }
+  __syncwarp();
+  double* w_acc = s_acc + warp * BB_SUB;
+  u32* w_arena = s_arena + (size_t)warp * BB_QW * 2 * BB_ARENA;
+  const u32* staged[BB_QW];
+#pragma unroll
+  for (int qi = 0; qi < BB_QW; ++qi)  // the first tile's postings
+    staged[qi] = ntok[qi] >= 0 ? bb_stage_slices(tk[qi], w_arena + (qi * 2 + 0) * BB_ARENA, lane) : nullptr;
+
+  u32 it = 0;
+  u32 par = 0;  // arena buffer of the current tile
+  for (int tile = blockIdx.x; tile < ix.n_tiles; tile += G, par ^= 1u) {
+    const long long tile_lo = (long long)tile * ix.tile_docs;
+    bb_cp_async_wait_all();
+    __syncwarp();
+    // this tile's slices become current; the next tile's postings and the skip entries of the
+    // tile after that are requested now
+#pragma unroll
+    for (int qi = 0; qi < BB_QW; ++qi) {
+      if (ntok[qi] < 0) continue;
+      tk[qi].cur = 0;
+      tk[qi].end = tk[qi].kind == 3 ? tk[qi].n1 - tk[qi].n0 : 0u;
+      tk[qi].src = staged[qi] != nullptr ? staged[qi] : tk[qi].post + tk[qi].n0;
+      tk[qi].n0 = tk[qi].m0;
+      tk[qi].n1 = tk[qi].m1;
+      tk[qi].m0 = tk[qi].m1 = 0;
+      if (tile + G < ix.n_tiles) {
+        staged[qi] = bb_stage_slices(tk[qi], w_arena + (qi * 2 + (par ^ 1u)) * BB_ARENA, lane);
+        if (tk[qi].kind == 3 && tile + 2 * G < ix.n_tiles) {
+          tk[qi].m0 = tk[qi].skip[tile + 2 * G];
+          tk[qi].m1 = tk[qi].skip[tile + 2 * G + 1];
+        }
+      }
+    }
+    for (int s = 0; s < subs; ++s, ++it) {
+      const long long doc0 = tile_lo + (long long)s * BB_SUB;
+      if (doc0 >= ix.n_docs) break;
+      const long long rem = ix.n_docs - doc0;
+      const int n_here = rem < BB_SUB ? (int)rem : BB_SUB;
+      const u32 st = it % BB_STAGES, ph = (it / BB_STAGES) & 1u;
+      const u32 loc_lo = (u32)(s * BB_SUB), loc_hi = loc_lo + BB_SUB;
+      bb_mbar_wait(bar_full + 8 * st, ph);
+      const double* cols = s_cols + (size_t)st * BB_NC * BB_SUB;
+#pragma unroll
+      for (int qi = 0; qi < BB_QW; ++qi) {
+        const int m = ntok[qi];
+        if (m < 0) continue;  // warp-uniform
+        double a[BB_R];
+#pragma unroll
+        for (int r = 0; r < BB_R; ++r) a[r] = 0.0;
+        bool spilled = false;  // the warp's strip in shared memory, not a[], holds the accumulators
+        const BbOp* prog = s_prog + (size_t)(warp + qi * BB_CWARPS) * BB_MAXT;
+        const unsigned char* cols_b = reinterpret_cast<const unsigned char*>(cols) + lane * 8;
+        const int np = nprog[qi];
+        for (int t = 0; t < np; ++t) {
+          const BbOp o = prog[t];  // broadcast LDS.128
+          const double w = o.w;
+          if (o.op != BB_OP_SPARSE) {
+            if (spilled) {
+              __syncwarp();
+#pragma unroll
+              for (int r = 0; r < BB_R; ++r) a[r] = w_acc[r * 32 + lane];
+              spilled = false;
+            }
+            if (o.op == BB_OP_COL) {
+              const double* cp = reinterpret_cast<const double*>(cols_b + o.arg);
+#pragma unroll
+              for (int r = 0; r < BB_R; ++r) a[r] = __dadd_rn(a[r], __dmul_rn(w, cp[r * 32]));  // no fma (rank_bm25 rounds the product)
+            } else {
+              const double* gp = ix.dense_imp + (size_t)o.arg * ix.n_docs + doc0 + lane;
+#pragma unroll
+              for (int r = 0; r < BB_R; ++r) {
+                const double f = (r * 32 + lane < n_here) ? ldg_stream_f64(gp + r * 32) : 0.0;
+                a[r] = __dadd_rn(a[r], __dmul_rn(w, f));
+              }
+            }
+            continue;
+          }
+          // sparse token: anything of its slice inside these 256 documents?
+          const int j = (int)o.arg;
+          u32 c = __shfl_sync(0xFFFFFFFFu, tk[qi].cur, j);
+          const u32 e = __shfl_sync(0xFFFFFFFFu, tk[qi].end, j);
+          if (c >= e) continue;
+          const u32* src = reinterpret_cast<const u32*>(
+              __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tk[qi].src), j));
+          u32 pk = c + lane < e ? src[c + lane] : 0xFFFFFFFFu;
+          if ((__shfl_sync(0xFFFFFFFFu, pk, 0) & 0xFFFFu) >= loc_hi) continue;  // sorted by document
+          if (!spilled) {
+#pragma unroll
+            for (int r = 0; r < BB_R; ++r) w_acc[r * 32 + lane] = a[r];
+            spilled = true;
+          }
+          __syncwarp();  // the strip is complete (spill or the previous token's scatter)
+          for (;;) {
+            const bool in = c + lane < e && (pk & 0xFFFFu) < loc_hi;  // a prefix of the lanes
+            if (in) {
+              const double imp = __ldg(ix.imp_table + (pk >> 16));
+              double* p = w_acc + ((pk & 0xFFFFu) - loc_lo);
+              *p = __dadd_rn(*p, __dmul_rn(w, imp));  // documents are unique within a list
+            }
+            const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, in));
+            c += (u32)cnt;
+            if (cnt < 32) break;
+            pk = c + lane < e ? src[c + lane] : 0xFFFFFFFFu;
+          }
+          if (lane == j) tk[qi].cur = c;
+        }
+        if (spilled) {
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < BB_R; ++r) a[r] = w_acc[r * 32 + lane];
+          __syncwarp();  // the strip may be rewritten by the next query
+        }
+
+        // ---- selection straight from the registers ------------------------------------------
+        KeyD* list = s_lists + (size_t)(warp + qi * BB_CWARPS) * BB_KP;
+        if (!seeded[qi]) {
+          // first slice of this CTA: each lane's best score is reached by a distinct document,
+          // so the smallest of the 32 lane maxima is a lower bound of the CTA's 32nd best score
+          seeded[qi] = true;
+          double mx = -INFINITY;
+#pragma unroll
+          for (int r = 0; r < BB_R; ++r) {
+            const int i = r * 32 + lane;
+            bool ok = i < n_here;
+            if (ok && row_mask != nullptr) ok = row_mask[doc0 + i] != 0;
+            if (ok) mx = fmax(mx, a[r]);
+          }
+          double mn = mx;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
+          if (mn > -INFINITY) thr[qi] = bb_below(mn);
+        }
+        {
+          // Fast reject: for a threshold >= +0.0, x > thr needs x > 0 and then the bit patterns
+          // compare like signed integers, so "no high word reaches the threshold's" proves no hit.
+          const double t0 = thr[qi];
+          const int t_hi = __double2hiint(t0);
+          bool any_hit;
+          if (t_hi >= 0) {
+            int mx = __double2hiint(a[0]);
+#pragma unroll
+            for (int r = 1; r < BB_R; ++r) mx = max(mx, __double2hiint(a[r]));
+            any_hit = mx >= t_hi;
+          } else {
+            any_hit = false;
+#pragma unroll
+            for (int r = 0; r < BB_R; ++r) any_hit |= a[r] > t0;
+          }
+          if (__any_sync(0xFFFFFFFFu, any_hit)) {
+#pragma unroll
+            for (int r = 0; r < BB_R; ++r) {
+              const int i = r * 32 + lane;
+              bool ok = (i < n_here) && (a[r] > thr[qi]);
+              if (ok && row_mask != nullptr) ok = row_mask[doc0 + i] != 0;
+              unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+              while (bal) {
+                const int src_lane = __ffs(bal) - 1;
+                bal &= bal - 1;
+                KeyD key;
+                key.s = __shfl_sync(0xFFFFFFFFu, a[r], src_lane);
+                key.id = (u32)(doc0 + r * 32 + src_lane);
+                key.pad = 0;
+                if (key.s > thr[qi]) {
+                  KeyD new_last;
+                  key_clear(new_last);
+                  if (warp_list_insert<BB_KP, KeyD>(list, key, lane, new_last) && !key_empty(new_last)) thr[qi] = new_last.s;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) bb_mbar_arrive(bar_empty + 8 * st);
+    }
+  }
+
+#pragma unroll
+  for (int qi = 0; qi < BB_QW; ++qi) {
+    if (ntok[qi] < 0) continue;
+    const KeyD* list = s_lists + (size_t)(warp + qi * BB_CWARPS) * BB_KP;
+    KeyD* dst = part + ((size_t)qid[qi] * gridDim.x + blockIdx.x) * BB_KP;
+    dst[lane] = list[lane];
+  }
+}
+
+static inline size_t bb_smem_bytes(int n_dense) {
+  return (size_t)BB_STAGES * BB_NC * BB_SUB * 8 + (size_t)BB_CWARPS * BB_SUB * 8 + (size_t)BB_QB * BB_KP * sizeof(KeyD) +
+         (size_t)BB_CWARPS * BB_QW * 2 * BB_ARENA * 4 + 2 * BB_STAGES * 8 + BB_NC * 4 + 16 + 2 * BB_QB * 4 +
+         (size_t)BB_QB * BB_MAXT * sizeof(BbOp) +
+         (size_t)((n_dense + 7) / 8 * 8) * 2 + 128;
+}
+
 struct Bm25Plan {
   bool packed;
   tile_fn_t fn;
   int kpl;
   int grid_y;  // tile groups (lists per query)
   size_t smem_tile, smem_fin;
+  bool batch;          // bm25_batch_kernel serves the queries of up to BB_MAXT tokens
+  int bb_chunks, bb_chunk_q;
+  size_t smem_bb;
 };
+
+static bool batch_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CMR_BM25_BATCH");
+    on = (e && e[0] == '1') ? 1 : 0;  // opt-in: see the note above bm25_batch_kernel
+  }
+  return on != 0;
+}
 
 static int check_index(const cmr_lex_index* ix) {
   CMR_CHECK_ARG(ix != nullptr, "null index");
@@ -491,6 +1009,13 @@ static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p)
     }
     if (n_cache < 32) cache[n_cache++] = Occ{fn, p->smem_tile, dev, per_sm};
   }
+  // CMR_BM25_CTAS_PER_SM: plan the single wave for fewer CTAs per SM than the kernel could hold
+  // alone -- set when the kernel shares the SMs with the dense scan (engine overlap)
+  {
+    const char* e = getenv("CMR_BM25_CTAS_PER_SM");  // read per call: cheap, and a process may change it
+    const int cap_per_sm = e ? atoi(e) : 0;
+    if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
+  }
   const long long resident = (long long)sms * per_sm;
   long long gy = resident / n_queries;  // one wave: every CTA resident
   if (gy < 1) gy = 1;
@@ -506,6 +1031,19 @@ static int make_plan(const cmr_lex_index& ix, int n_queries, int k, Bm25Plan* p)
   if (gy > max_gy) gy = max_gy;
   if (gy > 65535) gy = 65535;
   p->grid_y = (int)gy;
+  // batched form: one persistent CTA per SM, the lists of a query are the CTAs
+  p->batch = batch_enabled() && n_queries >= BB_MIN_QUERIES && p->kpl == 1 && p->packed && ix.n_terms > 0 &&
+             ix.n_dense <= BB_MAX_DENSE && ix.tile_docs % BB_SUB == 0 &&
+             (ix.n_dense == 0 || (ix.n_docs % 2 == 0 && ((uintptr_t)ix.dense_imp % 16) == 0));
+  p->bb_chunks = p->bb_chunk_q = 0;
+  p->smem_bb = 0;
+  if (p->batch) {
+    p->bb_chunks = (n_queries + BB_QB - 1) / BB_QB;
+    p->bb_chunk_q = (n_queries + p->bb_chunks - 1) / p->bb_chunks;
+    p->smem_bb = bb_smem_bytes(ix.n_dense);
+    p->grid_y = sms < ix.n_tiles ? sms : ix.n_tiles;
+    if (p->bb_chunks > 65535) p->batch = false;
+  }
   const int cap = kp * kp < 4096 ? kp * kp : 4096;
   p->smem_fin = (size_t)(p->grid_y + 1) * 16 + (size_t)cap * 16 + (size_t)kp * 16 + 16;
   if (p->smem_fin > 220 * 1024) {
@@ -529,7 +1067,19 @@ static int launch_bm25(const cmr_lex_index& ix, const Bm25Plan& p, const int* q_
     attr_dev_mask |= (1 << dev);
   }
   dim3 grid(n_queries, p.grid_y);
-  p.fn<<<grid, BM_THREADS, p.smem_tile, st>>>(ix, q_terms, q_ptr, row_mask, part);
+  int min_tokens = -1;
+  if (p.batch) {
+    static int bb_attr_mask = 0;
+    if (!(bb_attr_mask & (1 << dev))) {
+      cudaError_t e = cudaFuncSetAttribute(bm25_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(bm25_batch)");
+      bb_attr_mask |= (1 << dev);
+    }
+    bm25_batch_kernel<<<dim3(p.grid_y, p.bb_chunks), BB_THREADS, p.smem_bb, st>>>(ix, q_terms, q_ptr, row_mask, part,
+                                                                                 n_queries, p.bb_chunk_q);
+    min_tokens = BB_MAXT;  // the tile kernel only serves longer queries (its CTAs leave at once otherwise)
+  }
+  p.fn<<<grid, BM_THREADS, p.smem_tile, st>>>(ix, q_terms, q_ptr, row_mask, part, min_tokens);
   bm25_finalize_kernel<KPL><<<n_queries, BMF_THREADS, p.smem_fin, st>>>(part, p.grid_y, row_offset, k, out_scores,
                                                                        out_ids, out_counts, out_flags);
   return CMR_OK;

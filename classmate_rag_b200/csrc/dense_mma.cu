@@ -31,6 +31,7 @@
 // HBM once and re-read from L2.  Algorithmic bytes per launch: n_rows * dim * 2 (+1/16 for
 // the sample pass); flops 2 * n_queries * n_rows * dim.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "dense_common.cuh"
 
@@ -39,7 +40,7 @@ namespace cmr {
 constexpr int MM_Q = 128;     // queries per MMA tile (UMMA M, TMEM lanes)
 constexpr int MM_R = 256;     // rows per MMA tile (UMMA N, TMEM columns)
 constexpr int MM_K = 64;      // bf16 per K chunk: one 128-byte swizzle span
-constexpr int MM_STAGES = 4;
+constexpr int MM_STAGES = 4;   // ring slots (at most; MmParams::n_stages of them are used)
 constexpr int MM_A_BYTES = MM_Q * MM_K * 2;  // 16 KiB
 constexpr int MM_B_BYTES = MM_R * MM_K * 2;  // 32 KiB
 constexpr int MM_THREADS = 192;
@@ -160,6 +161,7 @@ struct MmParams {
   int n_left;          // rows of the left operand (queries; NEARDUP: matrix rows)
   long long n_rows;    // rows of the right operand
   int n_chunks;        // K chunks of 64 columns
+  int n_stages;        // ring slots in use (2..MM_STAGES): fewer leave shared memory to a co-resident kernel
   int n_outer;         // outer items in total
   int n_inner;         // SAMPLE/MAIN: query blocks
   int stride;          // SAMPLE: tile stride; NEARDUP: block step of this rank
@@ -228,7 +230,7 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const u32 raw = smem_u32(smem_raw);
   const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const u32 stage_bytes = p.a_bytes + MM_B_BYTES;
-  const u32 bars = base + MM_STAGES * stage_bytes;
+  const u32 bars = base + (u32)p.n_stages * stage_bytes;
   // barrier slots: full[s] at +8s, empty[s] at +32+8s, tmem_full[b] at +64+8b, tmem_empty[b] at +80+8b
   volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(smem_raw + (bars - raw) + 96);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + (bars - raw) + 128);  // MAIN: [n_inner * 128] list lengths
@@ -239,7 +241,7 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
-    for (int s = 0; s < MM_STAGES; ++s) {
+    for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 32 + 8 * s, 1);
     }
@@ -264,17 +266,17 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ===== TMA producer =====
       const unsigned long long hint_rows = p.rows_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
       const unsigned long long hint_left = MODE == MM_NEARDUP ? TMA_EVICT_NORMAL : TMA_EVICT_LAST;
-      u32 it = 0;
+      u32 s = 0, ph = 0;  // ring slot and its phase
       for (MmIter<MODE> w(p); w.valid(); w.advance()) {
         const int a0 = w.a_row0(), b0 = w.b_row0();
-        for (int kc = 0; kc < p.n_chunks; ++kc, ++it) {
-          const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+        for (int kc = 0; kc < p.n_chunks; ++kc) {
           mbar_wait(bars + 32 + 8 * s, ph ^ 1u);
           const u32 full = bars + 8 * s;
           mbar_expect_tx(full, p.tx_bytes);
           const u32 sa = base + s * stage_bytes;
           tma_load_2d(sa, &tm_q, full, kc * MM_K, a0, hint_left);
           tma_load_2d(sa + p.a_bytes, &tm_rows, full, kc * MM_K, b0, hint_rows);
+          if (++s == (u32)p.n_stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -282,14 +284,13 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      u32 it = 0, ai = 0;
+      u32 s = 0, ph = 0, ai = 0;
       for (MmIter<MODE> w(p); w.valid(); w.advance(), ++ai) {
         const u32 ab = ai & 1u, aph = (ai >> 1) & 1u;
         mbar_wait(bars + 80 + 8 * ab, aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const u32 d_tmem = tmem_base + ab * MM_R;
-        for (int kc = 0; kc < p.n_chunks; ++kc, ++it) {
-          const u32 s = it % MM_STAGES, ph = (it / MM_STAGES) & 1u;
+        for (int kc = 0; kc < p.n_chunks; ++kc) {
           mbar_wait(bars + 8 * s, ph);  // TMA bytes have landed
           tc_fence_after();
           const u32 sa = base + s * stage_bytes;
@@ -299,6 +300,7 @@ dense_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int k = 0; k < MM_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
             tc_mma_bf16(d_tmem, da + 2ull * k, db + 2ull * k, MM_IDESC, (kc | k) != 0);
           tc_commit(bars + 32 + 8 * s);  // frees the ring slot when these MMAs retire
+          if (++s == (u32)p.n_stages) { s = 0; ph ^= 1u; }
         }
         tc_commit(bars + 64 + 8 * ab);   // accumulator complete
       }
@@ -616,8 +618,18 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int di
 constexpr int MM_SMEM_MAX = 227 * 1024;
 constexpr int MM_MAX_QUERIES = 8192;  // list counters of all query blocks must fit in shared memory
 
+// Ring depth: MM_STAGES unless CMR_MM_STAGES (2..MM_STAGES) says otherwise.  The HBM-bound shapes
+// (<= 128 queries) keep the memory system busy with 3 slots (96 KB of rows in flight per SM); the
+// shared memory saved lets the BM25 tile kernel run beside the scan (engine.HybridEngine overlap).
+static int mma_stages() {
+  const char* e = getenv("CMR_MM_STAGES");  // read per call: cheap, and a process may change it
+  int n = e ? atoi(e) : MM_STAGES;
+  if (n < 2 || n > MM_STAGES) n = MM_STAGES;
+  return n;
+}
+
 static inline size_t mma_smem_bytes(u32 a_bytes, int n_inner) {
-  return (size_t)MM_STAGES * (a_bytes + MM_B_BYTES) + 1024 /* alignment slack */ + 128 /* barriers */ +
+  return (size_t)mma_stages() * (a_bytes + MM_B_BYTES) + 1024 /* alignment slack */ + 128 /* barriers */ +
          (size_t)n_inner * MM_Q * 4 /* MAIN: list counters */;
 }
 
@@ -759,6 +771,7 @@ int dense_mma_topk(const DenseArgs& a) {
   kp.n_left = a.n_queries;
   kp.n_rows = a.n_rows;
   kp.n_chunks = p.n_chunks;
+  kp.n_stages = mma_stages();
   kp.n_inner = p.n_mb;
   kp.tx_bytes = tx_bytes;
   kp.a_bytes = (u32)(p.q_box_rows * MM_K * 2 + 1023) / 1024 * 1024;
@@ -901,6 +914,7 @@ extern "C" int cmr_neardup_edges(const uint16_t* emb, int64_t n_rows, int dim, f
   kp.n_left = (int)n_rows;
   kp.n_rows = n_rows;
   kp.n_chunks = (dim + MM_K - 1) / MM_K;
+  kp.n_stages = mma_stages();
   kp.n_outer = mine;
   kp.n_inner = 0;
   kp.stride = block_step;

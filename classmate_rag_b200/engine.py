@@ -13,6 +13,7 @@ cmr_topk_merge (classmate_rag_b200.sharding).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -46,7 +47,7 @@ class HybridEngine:
     """One shard (or the whole corpus) resident on one GPU."""
 
     def __init__(self, emb: torch.Tensor, lex: Optional[LexicalIndex], *, row_offset: int = 0,
-                 max_row_norm: float = 1.0, comm=None):
+                 max_row_norm: float = 1.0, comm=None, overlap: Optional[bool] = None):
         if not emb.is_cuda or emb.dtype != torch.bfloat16:
             raise RuntimeError("emb must be a CUDA bfloat16 matrix (no CPU path)")
         self.emb = emb
@@ -57,6 +58,26 @@ class HybridEngine:
         self.device = emb.device
         self._dense_ws = {}
         self._bm_buf = {}
+        # overlap: the BM25 kernels run on a side stream next to the dense scan.  The scan is
+        # HBM-bound and leaves most issue slots idle, BM25 is latency-bound and moves few bytes,
+        # so together they take little longer than the scan alone (CMRAG_OVERLAP=0 serialises).
+        if overlap is None:
+            overlap = os.environ.get("CMRAG_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
+        self._side = None
+
+    def _fork_lexical(self, q_terms, q_ptr, k, lex_mask):
+        """BM25 top-k on the side stream, forked from the current stream; returns (result, join)
+        where join() makes the current stream wait for it.  Works eagerly and under CUDA-graph
+        capture (the fork/join become graph edges)."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = self.lexical_topk(q_terms, q_ptr, k, lex_mask)
+        return out, (lambda: cur.wait_stream(side))
 
     # -- stage helpers -------------------------------------------------------
     def _cert_eps(self, dim: int) -> float:
@@ -124,6 +145,9 @@ class HybridEngine:
         if self.comm is not None:
             return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
         mark()
+        join = None
+        if hybrid and self.overlap:
+            (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
         scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
         self.last_dense_flags = flags
         mark()
@@ -135,7 +159,10 @@ class HybridEngine:
         mark()
         bm = None
         if hybrid:
-            b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+            if join is not None:
+                join()
+            else:
+                b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
             bm = (b_ids, b_sc, b_cnt)
         mark()
         out = ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
@@ -149,10 +176,16 @@ class HybridEngine:
         cmr_shard_pack -> all-gather -> cmr_shard_merge -> MMR -> fuse."""
         comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
         try:
+            join = None
+            if hybrid and self.overlap:
+                (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
             dense = self.dense_pool(q_bf16, pool, dense_mask)
             bm_local = None
             if hybrid:
-                b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+                if join is not None:
+                    join()
+                else:
+                    b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
                 bm_local = (b_sc, b_ids, b_cnt)
         finally:
             self.comm = comm
