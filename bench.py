@@ -270,6 +270,8 @@ def main():
     # clocks: twenty BM25 launches in a row hit the power cap, inside a step they alternate
     # with the memory-bound dense pass).  Sharded: each retriever back to back (its own exchange).
     pool = p.pool
+    overlap_on = eng.overlap
+    eng.overlap = False   # stage times are those of each retriever running alone inside a (serial) step
     if world == 1:
         marks = []
         for s in range(a.warmup, n_steps):
@@ -294,6 +296,7 @@ def main():
         dense_ms = [stage_ms(lambda s: eng.dense_pool(q_bf16[s * a.batch:(s + 1) * a.batch], pool))]
         lex_ms = [stage_ms(lambda s: eng.lexical_topk(*dev_terms[s], p.k_bm25))]
         stage_step_ms = ms_per_step
+    eng.overlap = overlap_on
     clock_info = clocks.stop()
     dense_avg = float(np.mean(dense_ms))
     lex_avg = float(np.mean(lex_ms))
@@ -421,7 +424,10 @@ def main():
                       "vocab": VOCAB, "postings_this_rank": lex.n_postings, "rows_this_rank": hi - lo,
                       "parallelism": f"row-shard x{world}", "sm_count": sm, "cc": f"{cc_major}.{cc_minor}",
                       "l2": "inputs larger than L2 (matrix %.1f GB per rank)" % (dense_bytes / 1e9),
-                      "index_build_s": build_s},
+                      "index_build_s": build_s,
+                      "overlap": ("BM25 kernels on a side stream beside the dense scan inside the step's CUDA graph"
+                                  if overlap_on else "off (CMRAG_OVERLAP=0): the retrievers run one after the other"),
+                      "stage_times": "roofline.avg_launch_ms / bm25.avg_ms_per_step: each retriever alone, in a serial step"},
            "roofline": roofline, "e2e": e2e, "latency": latency, "gpu_launches": launches_per_step * a.steps,
            "clocks": clock_info, "planted_top1_in_top10": hit, "c2": c2,
            "chroma_hnsw_recall_at_10": None,

@@ -477,8 +477,8 @@ constexpr int BB_QB = BB_CWARPS * BB_QW;    // queries per chunk
 constexpr int BB_THREADS = (BB_CWARPS + 1) * 32;
 constexpr int BB_MAXT = 16;                 // tokens per query served here (one per lane, 16-byte program entry each)
 constexpr int BB_KP = 32;
-constexpr int BB_ARENA = 256;               // postings staged per (query, tile); the rest is read from global
-constexpr int BB_MAX_DENSE = 2048;          // columns the slot -> staged-column map can hold
+constexpr int BB_ARENA = 192;               // postings staged per (query, tile); the rest is read from global
+constexpr int BB_MAX_DENSE = 512;           // columns the slot -> staged-column map can hold
 constexpr int BB_MIN_QUERIES = 8;
 
 __device__ __forceinline__ u32 bb_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -516,21 +516,20 @@ __device__ __forceinline__ void bb_cp_async_wait_all() { asm volatile("cp.async.
 struct __align__(16) BbOp {  // one real token of a query's program (unknown tokens are dropped)
   double w;         // idf
   u32 arg;          // BB_OP_COL: byte offset of the staged column inside a stage; BB_OP_GLOBAL: dense slot;
-                    // BB_OP_SPARSE: the lane that holds the token's posting cursor
+                    // BB_OP_SPARSE: index of the token's BbCur / BbTile entry
   u32 op;
 };
 constexpr u32 BB_OP_COL = 0, BB_OP_GLOBAL = 1, BB_OP_SPARSE = 2;
 
-struct BbTok {      // token j of a query, held by lane j
-  int kind;         // 0 nothing, 1 dense column staged in shared memory, 2 dense column read from global, 3 sparse
-  int arg;          // staged column index / dense slot
-  double w;         // idf
-  const u32* post;  // post_pack + term_ptr[t]
-  const u32* skip;  // tile_skip row of the term
-  const u32* src;   // the current tile's slice: in the warp's arena, or in global memory when it did not fit
-  u32 cur, end;     // unconsumed part of that slice (offsets into src)
-  u32 n0, n1;       // slice bounds (offsets into post) of this CTA's next tile ...
-  u32 m0, m1;       // ... and of the one after
+struct __align__(16) BbCur {   // a sparse token's slice of the CURRENT tile (per query, in shared memory)
+  u32 cur, end;                // unconsumed part: offsets into src
+  const u32* src;              // in the query's arena, or in global memory when the slice did not fit
+};
+struct __align__(16) BbTile {  // a sparse token's tile-level state
+  const u32* post;             // post_pack + term_ptr[t]; nullptr = not a sparse token
+  const u32* skip;             // tile_skip row of the term
+  u32 n0, n1;                  // slice bounds (offsets into post) of this CTA's next tile ...
+  u32 m0, m1;                  // ... and of the one after (written by cp.async)
 };
 
 __device__ __forceinline__ double bb_below(double v) {  // largest double strictly below a finite v
@@ -540,31 +539,18 @@ __device__ __forceinline__ double bb_below(double v) {  // largest double strict
   return -4.9406564584124654e-324;
 }
 
-// Copy the slices [n0, n1) of the query's sparse tokens into `arena` (asynchronously) and
-// return, per lane, where token `lane`'s slice will be (nullptr: it did not fit).
-__device__ __forceinline__ const u32* bb_stage_slices(const BbTok& tk, u32* arena, int lane) {
-  const u32 len = tk.kind == 3 ? tk.n1 - tk.n0 : 0u;
+// Arena layout of one (query, tile): the slices [lo, hi) of the sparse tokens (lane = token)
+// packed in token order; a slice that does not fit stays in global memory.  Returns the
+// slice's offset in the arena or -1.
+__device__ __forceinline__ int bb_arena_offset(u32 len, int lane) {
   u32 off = len;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < BB_MAXT; d <<= 1) {
     const u32 o = __shfl_up_sync(0xFFFFFFFFu, off, d);
     if (lane >= d) off += o;
   }
   off -= len;  // exclusive prefix
-  const bool fits = len > 0 && off + len <= (u32)BB_ARENA;
-  unsigned todo = __ballot_sync(0xFFFFFFFFu, fits);
-  while (todo) {
-    const int j = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const u32 l = __shfl_sync(0xFFFFFFFFu, len, j);
-    const u32 o = __shfl_sync(0xFFFFFFFFu, off, j);
-    const u32* g = reinterpret_cast<const u32*>(
-                       __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tk.post), j)) +
-                   __shfl_sync(0xFFFFFFFFu, tk.n0, j);
-    const u32 dst = bb_smem_u32(arena + o);
-    for (u32 i = lane; i < l; i += 32) bb_cp_async4(dst + 4u * i, g + i);
-  }
-  return fits ? arena + off : nullptr;
+  return (len > 0 && off + len <= (u32)BB_ARENA) ? (int)off : -1;
 }
 
 __global__ void __launch_bounds__(BB_THREADS, 1)
@@ -574,19 +560,25 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
   double* s_cols = reinterpret_cast<double*>(smem_raw);                      // [STAGES][NC][SUB]
   double* s_acc = s_cols + (size_t)BB_STAGES * BB_NC * BB_SUB;               // [CWARPS][SUB]
   KeyD* s_lists = reinterpret_cast<KeyD*>(s_acc + BB_CWARPS * BB_SUB);       // [QB][KP]
-  u32* s_arena = reinterpret_cast<u32*>(s_lists + BB_QB * BB_KP);            // [CWARPS][QW][2][ARENA]
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_arena + (size_t)BB_CWARPS * BB_QW * 2 * BB_ARENA);
+  BbOp* s_prog = reinterpret_cast<BbOp*>(s_lists + BB_QB * BB_KP);           // [QB][MAXT] token programs
+  BbCur* s_cur = reinterpret_cast<BbCur*>(s_prog + BB_QB * BB_MAXT);         // [QB][MAXT]
+  BbTile* s_tile = reinterpret_cast<BbTile*>(s_cur + BB_QB * BB_MAXT);       // [QB][MAXT]
+  u32* s_arena = reinterpret_cast<u32*>(s_tile + BB_QB * BB_MAXT);           // [QB][2][ARENA]
+  double* s_thr = reinterpret_cast<double*>(s_arena + (size_t)BB_QB * 2 * BB_ARENA);  // [QB] admission thresholds
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_thr + BB_QB);   // full[STAGES], empty[STAGES]
   int* s_colslot = reinterpret_cast<int*>(s_bar + 2 * BB_STAGES);            // [NC] dense slot of staged column c
   int* s_ncols = s_colslot + BB_NC;                                          // [1] (+3 pad)
   int* s_cost = s_ncols + 4;                                                 // [QB] estimated per-slice cost of a query
   int* s_order = s_cost + BB_QB;                                             // [QB] chunk-local query, heaviest first
-  BbOp* s_prog = reinterpret_cast<BbOp*>(s_order + BB_QB);                   // [QB][MAXT] token programs
-  short* s_colmap = reinterpret_cast<short*>(s_prog + BB_QB * BB_MAXT);      // [n_dense] staged index, -1 unused, -2 not staged
+  int* s_np = s_order + BB_QB;                                               // [QB] program length, -1 = not served here
+  int* s_qid = s_np + BB_QB;                                                 // [QB] query of the slot
+  short* s_colmap = reinterpret_cast<short*>(s_qid + BB_QB);                 // [n_dense] staged index, -1 unused, -2 not staged
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q0 = blockIdx.y * chunk_q;
   const int q1 = (q0 + chunk_q) < n_queries ? (q0 + chunk_q) : n_queries;
   const u32 bar_full = bb_smem_u32(s_bar), bar_empty = bb_smem_u32(s_bar + BB_STAGES);
+  const int G = (int)gridDim.x;
 
   // ---- set-up: lists, barriers, the chunk's distinct dense columns, query -> warp pairing ----
   for (int i = tid; i < BB_QB * BB_KP; i += BB_THREADS) key_clear(s_lists[i]);
@@ -664,7 +656,7 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
   if (warp == BB_CWARPS) {
     // ---- producer: stage the next slice of every column the chunk uses ---------------------
     u32 it = 0;
-    for (int tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < ix.n_tiles; tile += G) {
       const long long tile_lo = (long long)tile * ix.tile_docs;
       for (int s = 0; s < subs; ++s, ++it) {
         const long long doc0 = tile_lo + (long long)s * BB_SUB;
@@ -684,76 +676,77 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
   }
 
   // ---- consumers ---------------------------------------------------------------------------
-  // warp w serves the w-th heaviest and the w-th lightest query of the chunk
-  BbTok tk[BB_QW];
-  int ntok[BB_QW], qid[BB_QW];
-  double thr[BB_QW];
-  bool seeded[BB_QW];
-  const int G = (int)gridDim.x;
-#pragma unroll
+  // Warp w serves the w-th heaviest and the w-th lightest query of the chunk: slots w and
+  // w + CWARPS.  Everything a query carries from slice to slice lives in shared memory, so the
+  // slice loop below needs few registers and its eight loads per dense token issue back to back.
   for (int qi = 0; qi < BB_QW; ++qi) {
-    const int ql = s_order[qi == 0 ? warp : BB_QB - 1 - warp];
-    const int q = q0 + ql;
-    qid[qi] = q;
-    ntok[qi] = -1;  // not served here
-    thr[qi] = -INFINITY;
-    seeded[qi] = false;
-    tk[qi].kind = 0; tk[qi].arg = 0; tk[qi].w = 0.0; tk[qi].post = nullptr; tk[qi].skip = nullptr;
-    tk[qi].src = nullptr; tk[qi].cur = tk[qi].end = 0;
-    tk[qi].n0 = tk[qi].n1 = tk[qi].m0 = tk[qi].m1 = 0;
+    const int ls = warp + qi * BB_CWARPS;
+    const int q = q0 + s_order[qi == 0 ? warp : BB_QB - 1 - warp];
+    int np = -1;
+    BbTile tt;
+    tt.post = nullptr; tt.skip = nullptr; tt.n0 = tt.n1 = tt.m0 = tt.m1 = 0;
     if (q < q1) {
       const int qlo = q_ptr[q], m = q_ptr[q + 1] - qlo;
       if (m <= BB_MAXT) {
-        ntok[qi] = m;
+        int kind = 0, arg = 0;  // 0 nothing, 1 staged dense column, 2 dense column in global memory, 3 sparse
+        double w = 0.0;
         if (lane < m) {
           const int t = q_terms[qlo + lane];
           if (t >= 0 && t < ix.n_terms) {
-            tk[qi].w = ix.idf[t];
+            w = ix.idf[t];
             const int slot = ix.dense_slot != nullptr ? ix.dense_slot[t] : -1;
             if (slot >= 0) {
               const int cm = s_colmap[slot];
-              tk[qi].kind = cm >= 0 ? 1 : 2;
-              tk[qi].arg = cm >= 0 ? cm : slot;
+              kind = cm >= 0 ? 1 : 2;
+              arg = cm >= 0 ? cm : slot;
             } else {
-              tk[qi].kind = 3;
-              tk[qi].post = ix.post_pack + ix.term_ptr[t];
-              tk[qi].skip = ix.tile_skip + (size_t)t * (ix.n_tiles + 1);
-              const int first = blockIdx.x;  // < n_tiles (grid is clamped)
-              tk[qi].n0 = tk[qi].skip[first];
-              tk[qi].n1 = tk[qi].skip[first + 1];
+              kind = 3;
+              tt.post = ix.post_pack + ix.term_ptr[t];
+              tt.skip = ix.tile_skip + (size_t)t * (ix.n_tiles + 1);
+              const int first = blockIdx.x;  // < n_tiles (the grid is clamped)
+              tt.n0 = tt.skip[first];
+              tt.n1 = tt.skip[first + 1];
               if (first + G < ix.n_tiles) {
-                tk[qi].m0 = tk[qi].skip[first + G];
-                tk[qi].m1 = tk[qi].skip[first + G + 1];
+                tt.m0 = tt.skip[first + G];
+                tt.m1 = tt.skip[first + G + 1];
               }
             }
           }
         }
+        // the query's program: its real tokens in order, read back with one broadcast LDS.128 each
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, kind != 0);
+        np = __popc(bal);
+        if (kind != 0) {
+          BbOp o;
+          o.w = w;
+          o.op = kind == 1 ? BB_OP_COL : (kind == 2 ? BB_OP_GLOBAL : BB_OP_SPARSE);
+          o.arg = kind == 1 ? (u32)arg * (u32)(BB_SUB * 8) : (kind == 2 ? (u32)arg : (u32)lane);
+          s_prog[ls * BB_MAXT + __popc(bal & ((1u << lane) - 1u))] = o;
+        }
+        // the first tile's postings
+        const int off = bb_arena_offset(tt.post != nullptr ? tt.n1 - tt.n0 : 0u, lane);
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, off >= 0);
+        u32* arena = s_arena + (size_t)(ls * 2 + 0) * BB_ARENA;
+        while (todo) {
+          const int j = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const u32 l = __shfl_sync(0xFFFFFFFFu, tt.n1 - tt.n0, j);
+          const u32* g = reinterpret_cast<const u32*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tt.post + tt.n0), j));
+          const u32 dst = bb_smem_u32(arena + __shfl_sync(0xFFFFFFFFu, off, j));
+          for (u32 i = lane; i < l; i += 32) bb_cp_async4(dst + 4u * i, g + i);
+        }
       }
     }
-  }
-  // the query's program: its real tokens in order, 16 bytes each, read back with one broadcast LDS.128
-  int nprog[BB_QW];
-#pragma unroll
-  for (int qi = 0; qi < BB_QW; ++qi) {
-    BbOp* prog = s_prog + (size_t)(warp + qi * BB_CWARPS) * BB_MAXT;
-    const bool real = tk[qi].kind != 0;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, real);
-    nprog[qi] = ntok[qi] < 0 ? 0 : __popc(bal);
-    if (real && ntok[qi] >= 0) {
-      BbOp o;
-      o.w = tk[qi].w;
-      o.op = tk[qi].kind == 1 ? BB_OP_COL : (tk[qi].kind == 2 ? BB_OP_GLOBAL : BB_OP_SPARSE);
-      o.arg = tk[qi].kind == 1 ? (u32)tk[qi].arg * (u32)(BB_SUB * 8) : (tk[qi].kind == 2 ? (u32)tk[qi].arg : (u32)lane);
-      prog[__popc(bal & ((1u << lane) - 1u))] = o;
+    if (lane < BB_MAXT) s_tile[ls * BB_MAXT + lane] = tt;
+    if (lane == 0) {
+      s_np[ls] = np;
+      s_qid[ls] = q;
+      s_thr[ls] = -INFINITY;
     }
   }
   __syncwarp();
   double* w_acc = s_acc + warp * BB_SUB;
-  u32* w_arena = s_arena + (size_t)warp * BB_QW * 2 * BB_ARENA;
-  const u32* staged[BB_QW];
-#pragma unroll
-  for (int qi = 0; qi < BB_QW; ++qi)  // the first tile's postings
-    staged[qi] = ntok[qi] >= 0 ? bb_stage_slices(tk[qi], w_arena + (qi * 2 + 0) * BB_ARENA, lane) : nullptr;
+  bool first_slice = true;
 
   u32 it = 0;
   u32 par = 0;  // arena buffer of the current tile
@@ -761,25 +754,53 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
     const long long tile_lo = (long long)tile * ix.tile_docs;
     bb_cp_async_wait_all();
     __syncwarp();
-    // this tile's slices become current; the next tile's postings and the skip entries of the
-    // tile after that are requested now
-#pragma unroll
+    // Tile switch (lane = token): this tile's slices become current; the next tile's postings
+    // and the skip entries of the tile after that are requested now and land during this tile.
     for (int qi = 0; qi < BB_QW; ++qi) {
-      if (ntok[qi] < 0) continue;
-      tk[qi].cur = 0;
-      tk[qi].end = tk[qi].kind == 3 ? tk[qi].n1 - tk[qi].n0 : 0u;
-      tk[qi].src = staged[qi] != nullptr ? staged[qi] : tk[qi].post + tk[qi].n0;
-      tk[qi].n0 = tk[qi].m0;
-      tk[qi].n1 = tk[qi].m1;
-      tk[qi].m0 = tk[qi].m1 = 0;
+      const int ls = warp + qi * BB_CWARPS;
+      if (s_np[ls] < 0) continue;
+      BbTile tt;
+      tt.post = nullptr; tt.skip = nullptr; tt.n0 = tt.n1 = tt.m0 = tt.m1 = 0;
+      if (lane < BB_MAXT) tt = s_tile[ls * BB_MAXT + lane];
+      const bool sparse = tt.post != nullptr;
+      {
+        const u32 len = sparse ? tt.n1 - tt.n0 : 0u;
+        const int off = bb_arena_offset(len, lane);  // where the staging pass put it
+        if (lane < BB_MAXT) {
+          BbCur c;
+          c.cur = 0;
+          c.end = len;
+          c.src = off >= 0 ? s_arena + (size_t)(ls * 2 + par) * BB_ARENA + off : tt.post + tt.n0;
+          s_cur[ls * BB_MAXT + lane] = c;
+        }
+      }
+      tt.n0 = tt.m0;
+      tt.n1 = tt.m1;
       if (tile + G < ix.n_tiles) {
-        staged[qi] = bb_stage_slices(tk[qi], w_arena + (qi * 2 + (par ^ 1u)) * BB_ARENA, lane);
-        if (tk[qi].kind == 3 && tile + 2 * G < ix.n_tiles) {
-          tk[qi].m0 = tk[qi].skip[tile + 2 * G];
-          tk[qi].m1 = tk[qi].skip[tile + 2 * G + 1];
+        const u32 len = sparse ? tt.n1 - tt.n0 : 0u;
+        const int off = bb_arena_offset(len, lane);
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, off >= 0);
+        u32* arena = s_arena + (size_t)(ls * 2 + (par ^ 1u)) * BB_ARENA;
+        while (todo) {
+          const int j = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const u32 l = __shfl_sync(0xFFFFFFFFu, len, j);
+          const u32* g = reinterpret_cast<const u32*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tt.post + tt.n0), j));
+          const u32 dst = bb_smem_u32(arena + __shfl_sync(0xFFFFFFFFu, off, j));
+          for (u32 i = lane; i < l; i += 32) bb_cp_async4(dst + 4u * i, g + i);
+        }
+      }
+      if (sparse) {
+        BbTile* dstt = s_tile + ls * BB_MAXT + lane;
+        dstt->n0 = tt.n0;
+        dstt->n1 = tt.n1;
+        if (tile + 2 * G < ix.n_tiles) {
+          bb_cp_async4(bb_smem_u32(&dstt->m0), tt.skip + tile + 2 * G);
+          bb_cp_async4(bb_smem_u32(&dstt->m1), tt.skip + tile + 2 * G + 1);
         }
       }
     }
+    __syncwarp();
     for (int s = 0; s < subs; ++s, ++it) {
       const long long doc0 = tile_lo + (long long)s * BB_SUB;
       if (doc0 >= ix.n_docs) break;
@@ -788,18 +809,16 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
       const u32 st = it % BB_STAGES, ph = (it / BB_STAGES) & 1u;
       const u32 loc_lo = (u32)(s * BB_SUB), loc_hi = loc_lo + BB_SUB;
       bb_mbar_wait(bar_full + 8 * st, ph);
-      const double* cols = s_cols + (size_t)st * BB_NC * BB_SUB;
-#pragma unroll
+      const unsigned char* cols_b = reinterpret_cast<const unsigned char*>(s_cols + (size_t)st * BB_NC * BB_SUB) + lane * 8;
       for (int qi = 0; qi < BB_QW; ++qi) {
-        const int m = ntok[qi];
-        if (m < 0) continue;  // warp-uniform
+        const int ls = warp + qi * BB_CWARPS;
+        const int np = s_np[ls];
+        if (np < 0) continue;  // warp-uniform
         double a[BB_R];
 #pragma unroll
         for (int r = 0; r < BB_R; ++r) a[r] = 0.0;
         bool spilled = false;  // the warp's strip in shared memory, not a[], holds the accumulators
-        const BbOp* prog = s_prog + (size_t)(warp + qi * BB_CWARPS) * BB_MAXT;
-        const unsigned char* cols_b = reinterpret_cast<const unsigned char*>(cols) + lane * 8;
-        const int np = nprog[qi];
+        const BbOp* prog = s_prog + ls * BB_MAXT;
         for (int t = 0; t < np; ++t) {
           const BbOp o = prog[t];  // broadcast LDS.128
           const double w = o.w;
@@ -810,28 +829,27 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
               for (int r = 0; r < BB_R; ++r) a[r] = w_acc[r * 32 + lane];
               spilled = false;
             }
+            double f[BB_R];
             if (o.op == BB_OP_COL) {
               const double* cp = reinterpret_cast<const double*>(cols_b + o.arg);
 #pragma unroll
-              for (int r = 0; r < BB_R; ++r) a[r] = __dadd_rn(a[r], __dmul_rn(w, cp[r * 32]));  // no fma (rank_bm25 rounds the product)
+              for (int r = 0; r < BB_R; ++r) f[r] = cp[r * 32];
             } else {
               const double* gp = ix.dense_imp + (size_t)o.arg * ix.n_docs + doc0 + lane;
 #pragma unroll
-              for (int r = 0; r < BB_R; ++r) {
-                const double f = (r * 32 + lane < n_here) ? ldg_stream_f64(gp + r * 32) : 0.0;
-                a[r] = __dadd_rn(a[r], __dmul_rn(w, f));
-              }
+              for (int r = 0; r < BB_R; ++r) f[r] = (r * 32 + lane < n_here) ? ldg_stream_f64(gp + r * 32) : 0.0;
             }
+#pragma unroll
+            for (int r = 0; r < BB_R; ++r) a[r] = __dadd_rn(a[r], __dmul_rn(w, f[r]));  // no fma (rank_bm25 rounds the product)
             continue;
           }
           // sparse token: anything of its slice inside these 256 documents?
-          const int j = (int)o.arg;
-          u32 c = __shfl_sync(0xFFFFFFFFu, tk[qi].cur, j);
-          const u32 e = __shfl_sync(0xFFFFFFFFu, tk[qi].end, j);
+          BbCur* cs = s_cur + ls * BB_MAXT + o.arg;
+          const BbCur cc = *cs;  // broadcast LDS.128
+          u32 c = cc.cur;
+          const u32 e = cc.end;
           if (c >= e) continue;
-          const u32* src = reinterpret_cast<const u32*>(
-              __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(tk[qi].src), j));
-          u32 pk = c + lane < e ? src[c + lane] : 0xFFFFFFFFu;
+          u32 pk = c + lane < e ? cc.src[c + lane] : 0xFFFFFFFFu;
           if ((__shfl_sync(0xFFFFFFFFu, pk, 0) & 0xFFFFu) >= loc_hi) continue;  // sorted by document
           if (!spilled) {
 #pragma unroll
@@ -849,9 +867,9 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
             const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, in));
             c += (u32)cnt;
             if (cnt < 32) break;
-            pk = c + lane < e ? src[c + lane] : 0xFFFFFFFFu;
+            pk = c + lane < e ? cc.src[c + lane] : 0xFFFFFFFFu;
           }
-          if (lane == j) tk[qi].cur = c;
+          if (lane == 0) cs->cur = c;  // read again at the next slice (a __syncwarp away)
         }
         if (spilled) {
           __syncwarp();
@@ -861,11 +879,12 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
         }
 
         // ---- selection straight from the registers ------------------------------------------
-        KeyD* list = s_lists + (size_t)(warp + qi * BB_CWARPS) * BB_KP;
-        if (!seeded[qi]) {
+        KeyD* list = s_lists + (size_t)ls * BB_KP;
+        double thr = s_thr[ls];
+        const double thr_in = thr;
+        if (first_slice) {
           // first slice of this CTA: each lane's best score is reached by a distinct document,
           // so the smallest of the 32 lane maxima is a lower bound of the CTA's 32nd best score
-          seeded[qi] = true;
           double mx = -INFINITY;
 #pragma unroll
           for (int r = 0; r < BB_R; ++r) {
@@ -877,29 +896,22 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
           double mn = mx;
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
-          if (mn > -INFINITY) thr[qi] = bb_below(mn);
+          if (mn > -INFINITY) thr = bb_below(mn);
         }
         {
           // Fast reject: for a threshold >= +0.0, x > thr needs x > 0 and then the bit patterns
           // compare like signed integers, so "no high word reaches the threshold's" proves no hit.
-          const double t0 = thr[qi];
-          const int t_hi = __double2hiint(t0);
-          bool any_hit;
-          if (t_hi >= 0) {
-            int mx = __double2hiint(a[0]);
+          // (A negative threshold -- the list is not full yet -- takes the exact path below.)
+          const int t_hi = __double2hiint(thr);
+          int mx = __double2hiint(a[0]);
 #pragma unroll
-            for (int r = 1; r < BB_R; ++r) mx = max(mx, __double2hiint(a[r]));
-            any_hit = mx >= t_hi;
-          } else {
-            any_hit = false;
-#pragma unroll
-            for (int r = 0; r < BB_R; ++r) any_hit |= a[r] > t0;
-          }
+          for (int r = 1; r < BB_R; ++r) mx = max(mx, __double2hiint(a[r]));
+          const bool any_hit = t_hi < 0 || mx >= t_hi;
           if (__any_sync(0xFFFFFFFFu, any_hit)) {
 #pragma unroll
             for (int r = 0; r < BB_R; ++r) {
               const int i = r * 32 + lane;
-              bool ok = (i < n_here) && (a[r] > thr[qi]);
+              bool ok = (i < n_here) && (a[r] > thr);
               if (ok && row_mask != nullptr) ok = row_mask[doc0 + i] != 0;
               unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
               while (bal) {
@@ -909,35 +921,35 @@ bm25_batch_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
                 key.s = __shfl_sync(0xFFFFFFFFu, a[r], src_lane);
                 key.id = (u32)(doc0 + r * 32 + src_lane);
                 key.pad = 0;
-                if (key.s > thr[qi]) {
+                if (key.s > thr) {
                   KeyD new_last;
                   key_clear(new_last);
-                  if (warp_list_insert<BB_KP, KeyD>(list, key, lane, new_last) && !key_empty(new_last)) thr[qi] = new_last.s;
+                  if (warp_list_insert<BB_KP, KeyD>(list, key, lane, new_last) && !key_empty(new_last)) thr = new_last.s;
                 }
               }
             }
           }
         }
+        if (lane == 0 && thr != thr_in) s_thr[ls] = thr;
       }
+      first_slice = false;
       __syncwarp();
       if (lane == 0) bb_mbar_arrive(bar_empty + 8 * st);
     }
   }
 
-#pragma unroll
   for (int qi = 0; qi < BB_QW; ++qi) {
-    if (ntok[qi] < 0) continue;
-    const KeyD* list = s_lists + (size_t)(warp + qi * BB_CWARPS) * BB_KP;
-    KeyD* dst = part + ((size_t)qid[qi] * gridDim.x + blockIdx.x) * BB_KP;
-    dst[lane] = list[lane];
+    const int ls = warp + qi * BB_CWARPS;
+    if (s_np[ls] < 0) continue;
+    KeyD* dst = part + ((size_t)s_qid[ls] * gridDim.x + blockIdx.x) * BB_KP;
+    dst[lane] = s_lists[(size_t)ls * BB_KP + lane];
   }
 }
 
 static inline size_t bb_smem_bytes(int n_dense) {
   return (size_t)BB_STAGES * BB_NC * BB_SUB * 8 + (size_t)BB_CWARPS * BB_SUB * 8 + (size_t)BB_QB * BB_KP * sizeof(KeyD) +
-         (size_t)BB_CWARPS * BB_QW * 2 * BB_ARENA * 4 + 2 * BB_STAGES * 8 + BB_NC * 4 + 16 + 2 * BB_QB * 4 +
-         (size_t)BB_QB * BB_MAXT * sizeof(BbOp) +
-         (size_t)((n_dense + 7) / 8 * 8) * 2 + 128;
+         (size_t)BB_QB * BB_MAXT * (sizeof(BbOp) + sizeof(BbCur) + sizeof(BbTile)) + (size_t)BB_QB * 2 * BB_ARENA * 4 +
+         (size_t)BB_QB * 8 + 2 * BB_STAGES * 8 + BB_NC * 4 + 16 + 4 * BB_QB * 4 + (size_t)((n_dense + 7) / 8 * 8) * 2 + 128;
 }
 
 struct Bm25Plan {

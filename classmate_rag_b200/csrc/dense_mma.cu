@@ -523,6 +523,7 @@ dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__
   }
   __syncthreads();
   const int m = s_total < cap_total ? s_total : cap_total;
+  __syncthreads();  // every thread has read s_total before it is reused as a counter below
   // Ranking m keys against each other is quadratic, and only the KP best matter: find the
   // KP-th largest score word by bisection (32 rounds of counting), then rank just the keys
   // that reach it (the KP best plus ties of the last one).

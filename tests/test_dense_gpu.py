@@ -163,6 +163,29 @@ def test_dense_mma_many_queries_multiple_blocks():
     _check_mma(bits, _queries(rng, bits, 300), 10)
 
 
+def test_dense_mma_repeated_runs_equal_exhaustive_scan():
+    """Race check: the batched path, run repeatedly on shapes with several query blocks, must
+    give the exhaustive float64 scan's answer every time (a missing barrier in the candidate
+    finalize once dropped candidates in about 1 run in 25 -- tools/stress_dense.py)."""
+    from classmate_rag_b200 import ops
+    shapes = [(9000, 256, 300, 10), (9000, 768, 520, 24), (40000, 128, 300, 10)]
+    for it in range(9):
+        n, d, b, k = shapes[it % len(shapes)]
+        g = torch.Generator(device="cuda").manual_seed(1000 + it)
+        x = torch.nn.functional.normalize(torch.randn((n, d), device="cuda", generator=g), dim=1).to(torch.bfloat16)
+        x[63::64] = x[31::64][: x[63::64].shape[0]]          # exact duplicates: ties at every rank
+        rows = torch.randint(0, n, (b,), device="cuda", generator=g)
+        q = x[rows].float() + 0.5 * torch.randn((b, d), device="cuda", generator=g) / d ** 0.5
+        q = torch.nn.functional.normalize(q, dim=1).to(torch.bfloat16)
+        ref = [t.clone() for t in ops.dense_topk(x, q, k, algo="exact")]
+        for _ in range(8):
+            out = [t.clone() for t in ops.dense_topk(x, q, k, algo="mma")]
+            torch.cuda.synchronize()
+            assert int((out[3] != 0).sum()) == 0
+            assert torch.equal(out[1], ref[1]) and torch.equal(out[2], ref[2])
+            assert out[0].cpu().numpy().tobytes() == ref[0].cpu().numpy().tobytes()
+
+
 def test_dense_mma_sampled_bound_large_matrix():
     """Enough tiles that the sample pass really strides (every 16th tile) and uses
     whole-tile maxima; oracle on a subset of the queries, scan kernel on all."""
