@@ -58,9 +58,13 @@ class HybridEngine:
         self.device = emb.device
         self._dense_ws = {}
         self._bm_buf = {}
-        # overlap: the BM25 kernels run on a side stream next to the dense scan.  The scan is
-        # HBM-bound and leaves most issue slots idle, BM25 is latency-bound and moves few bytes,
-        # so together they take little longer than the scan alone (CMRAG_OVERLAP=0 serialises).
+        # overlap: for batches on the tcgen05 path (> 8 queries) the BM25 kernels run on a side
+        # stream, launched first; the dense pass starts on the SMs BM25 has already left, so the
+        # tail of one overlaps the head of the other (10M x 768, batch 32: 3.73 -> 3.56 ms per
+        # step).  Truly concurrent execution does not pay: both want the SM's shared memory and
+        # registers (tools/overlap_sweep.py: 5.0 ms with BM25 held to 3 CTAs per SM), and for a
+        # single query the persistent scan kernel loses more than BM25 gains (p50 2.5 -> 3.0 ms),
+        # so small batches stay serial.  CMRAG_OVERLAP=0 serialises everything.
         if overlap is None:
             overlap = os.environ.get("CMRAG_OVERLAP", "1") != "0"
         self.overlap = bool(overlap)
@@ -146,7 +150,7 @@ class HybridEngine:
             return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
         mark()
         join = None
-        if hybrid and self.overlap:
+        if hybrid and self.overlap and q_bf16.shape[0] > 8:
             (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
         scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
         self.last_dense_flags = flags
@@ -177,7 +181,7 @@ class HybridEngine:
         comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
         try:
             join = None
-            if hybrid and self.overlap:
+            if hybrid and self.overlap and q_bf16.shape[0] > 8:
                 (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
             dense = self.dense_pool(q_bf16, pool, dense_mask)
             bm_local = None
