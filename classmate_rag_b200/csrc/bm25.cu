@@ -964,12 +964,8 @@ struct Bm25Plan {
 };
 
 static bool batch_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("CMR_BM25_BATCH");
-    on = (e && e[0] == '1') ? 1 : 0;  // opt-in: see the note above bm25_batch_kernel
-  }
-  return on != 0;
+  const char* e = getenv("CMR_BM25_BATCH");  // read per call: cheap, and a process may change it
+  return e && e[0] == '1';                   // opt-in: see the note above bm25_batch_kernel
 }
 
 static int check_index(const cmr_lex_index* ix) {

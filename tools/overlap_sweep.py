@@ -13,7 +13,7 @@ variants = sys.argv[3:] or ["0:4:0", "1:4:0", "1:3:5", "1:3:4", "1:2:6", "1:2:5"
 d, vocab, steps = 768, 30000, 12
 emb = synth.dense_corpus(n, d, "cuda")
 doc_ptr, tokens = synth.lexical_corpus(n, vocab, 64, "cuda")
-lex = lexical.build_lexical_index(doc_ptr, tokens, vocab)
+lex = lexical.build_lexical_index(doc_ptr, tokens, vocab, tile_docs=int(os.environ.get("TILE", "2048")))
 del doc_ptr, tokens
 q, _ = synth.dense_queries(n, d, b * steps, "cuda")
 terms = synth.lexical_queries(b * steps, vocab)
@@ -21,7 +21,8 @@ dev_terms = [tuple(t.cuda() for t in lexical.pack_queries(terms[s * b:(s + 1) * 
 p = SearchParams(top_k=10)
 ref = None
 for v in variants:
-    ov, st, cap = v.split(":")
+    ov, st, cap, *rest = v.split(":")
+    os.environ["CMR_BM25_BATCH"] = rest[0] if rest else "0"
     os.environ["CMR_MM_STAGES"] = st
     os.environ["CMR_BM25_CTAS_PER_SM"] = cap
     eng = HybridEngine(emb, lex, overlap=ov == "1")
@@ -38,6 +39,6 @@ for v in variants:
     res = [t.cpu().numpy().tobytes() for t in out]
     if ref is None:
         ref = res
-    print(json.dumps({"overlap": ov, "stages": st, "bm25_ctas_per_sm": cap, "ms_per_step": e0.elapsed_time(e1) / (steps - 3),
+    print(json.dumps({"overlap": ov, "stages": st, "bm25_ctas_per_sm": cap, "bm25_batch": os.environ["CMR_BM25_BATCH"], "tile": os.environ.get("TILE", "2048"), "ms_per_step": e0.elapsed_time(e1) / (steps - 3),
                       "same_as_first": res == ref}), flush=True)
     del g, eng
