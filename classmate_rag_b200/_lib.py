@@ -44,6 +44,7 @@ _SIGNATURES = {
     "cmr_neardup_edges": (C.c_int, [_vp, _i64, C.c_int, C.c_float, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cmr_neardup_rescore": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _f64, _vp, _vp, _vp]),
     "cmr_neardup_resolve": (C.c_int, [_vp, C.c_uint64, _i64, _vp, _vp]),
+    "cmr_jaccard_edges": (C.c_int, [_vp, _vp, C.c_int, _f64, _vp, C.c_uint64, _vp, _vp]),
     "cmr_shard_msg_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "cmr_shard_pack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _i64, C.c_int, _i64,
                                  C.c_int, _vp, _vp]),

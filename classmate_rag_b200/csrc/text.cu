@@ -111,6 +111,68 @@ __global__ void tokenize_kernel(const uint8_t* __restrict__ text, const long lon
   out_counts[q] = count;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// N4  Jaccard near-duplicate edges between shingle sets (ingest-side text dedup,
+//     rag/utils/dedup.py:19-55).  Set i = the sorted, unique ids of chunk i's token 5-gram
+//     shingles (the host maps shingle tuples to ids through a dictionary, so equal ids <=>
+//     equal shingles: no hashing, no collisions).  An edge (i, j < i) is emitted when
+//         |A_i ^ A_j| / |A_i v A_j| >= threshold      (float64 division, like Python's)
+//     with the reference's conventions: two empty sets 1.0, one empty set 0.0.
+//     One CTA per set i (largest first: the triangle's long rows start early), set i staged in
+//     shared memory; warp w takes j = w, w + 8, ...: the lanes read set j coalesced and bisect
+//     set i.  A pair whose sizes already rule the threshold out (min/max < threshold; the
+//     division is monotonic, so this is exact) is skipped without touching the sets.
+// ---------------------------------------------------------------------------------------
+constexpr int JAC_THREADS = 256;
+constexpr int JAC_SMEM_ITEMS = 8192;  // a larger set i is bisected in global memory
+
+__global__ void __launch_bounds__(JAC_THREADS)
+jaccard_edges_kernel(const int* __restrict__ set_ptr, const int* __restrict__ items, int n_sets, double threshold,
+                     unsigned long long* __restrict__ edges, unsigned long long edge_cap,
+                     unsigned long long* __restrict__ edge_count) {
+  __shared__ int s_a[JAC_SMEM_ITEMS];
+  const int i = n_sets - 1 - (int)blockIdx.x;
+  const int a_lo = set_ptr[i], na = set_ptr[i + 1] - a_lo;
+  const int* a = items + a_lo;
+  if (na <= JAC_SMEM_ITEMS) {
+    for (int t = threadIdx.x; t < na; t += JAC_THREADS) s_a[t] = a[t];
+    __syncthreads();
+    a = s_a;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < i; j += JAC_THREADS / 32) {
+    const int b_lo = set_ptr[j], nb = set_ptr[j + 1] - b_lo;
+    double jac;
+    if (na == 0 && nb == 0) {
+      jac = 1.0;
+    } else if (na == 0 || nb == 0) {
+      jac = 0.0;
+    } else {
+      const int mn = na < nb ? na : nb, mx = na < nb ? nb : na;
+      if ((double)mn / (double)mx < threshold) continue;  // |A^B| <= mn and |AvB| >= mx
+      const int* b = items + b_lo;
+      int inter = 0;
+      for (int t = lane; t < nb; t += 32) {
+        const int x = b[t];
+        int lo = 0, hi = na;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (a[mid] < x) lo = mid + 1;
+          else hi = mid;
+        }
+        inter += (lo < na && a[lo] == x) ? 1 : 0;
+      }
+      inter = __reduce_add_sync(0xFFFFFFFFu, inter);
+      jac = (double)inter / (double)(na + nb - inter);
+    }
+    if (lane == 0 && jac >= threshold) {
+      const unsigned long long slot = atomicAdd(edge_count, 1ull);
+      if (slot < edge_cap) edges[slot] = ((unsigned long long)(unsigned)i << 32) | (unsigned long long)(unsigned)j;
+    }
+  }
+}
+
 }  // namespace cmr
 
 using namespace cmr;
@@ -126,6 +188,21 @@ extern "C" int cmr_tokenize_queries(const uint8_t* text, const int64_t* text_ptr
                 "token table must have a power-of-two capacity and all arrays");
   tokenize_kernel<<<(n_queries + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       text, (const long long*)text_ptr, lang_it, n_queries, *table, max_terms, out_terms, out_counts);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+extern "C" int cmr_jaccard_edges(const int32_t* set_ptr, const int32_t* set_items, int n_sets, double threshold,
+                                 uint64_t* out_edges, uint64_t edge_cap, uint64_t* out_count, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_sets >= 0, "n_sets negative");
+  CMR_CHECK_ARG(out_count != nullptr, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CMR_CUDA(cudaMemsetAsync(out_count, 0, sizeof(uint64_t), st));
+  if (n_sets < 2) return CMR_OK;
+  CMR_CHECK_ARG(set_ptr && (out_edges || edge_cap == 0), "null pointer argument");
+  jaccard_edges_kernel<<<n_sets, JAC_THREADS, 0, st>>>(set_ptr, set_items, n_sets, threshold,
+                                                      (unsigned long long*)out_edges, edge_cap,
+                                                      (unsigned long long*)out_count);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }

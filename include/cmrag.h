@@ -345,6 +345,19 @@ int cmr_neardup_rescore(const uint16_t* emb, int dim, const uint64_t* edges, uin
 int cmr_neardup_resolve(const uint64_t* sorted_edges, uint64_t n_edges, int64_t n_rows, uint8_t* keep,
                         cmr_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * N4  Ingest-side text dedup: Jaccard similarity between token 5-gram shingle sets
+ *     (rag/utils/dedup.py:19-55, called from ingest_file, rag/pipeline/rag.py:308-324).
+ *     set_ptr int32 [n_sets + 1], set_items int32: set i = the ascending, unique shingle ids
+ *     of chunk i (ids from a host dictionary: equal id <=> equal shingle).  Pairs (i, j < i)
+ *     with |A_i ^ A_j| / |A_i v A_j| >= threshold (float64; both empty = 1.0, one empty =
+ *     0.0, as _jaccard :32-39) are appended to out_edges as (i << 32 | j), unordered;
+ *     out_count may exceed edge_cap (retry with more room).  The greedy keep-first pass of
+ *     dedup_text_blocks (:46-53) is cmr_neardup_resolve on the sorted edges.
+ * ---------------------------------------------------------------------- */
+int cmr_jaccard_edges(const int32_t* set_ptr, const int32_t* set_items, int n_sets, double threshold,
+                      uint64_t* out_edges, uint64_t edge_cap, uint64_t* out_count, cmr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -543,3 +543,48 @@ def neardup_keep_mask(c_bits: np.ndarray, threshold: float = 0.95) -> np.ndarray
             keep[i] = True
             kept_rows.append(i)
     return keep
+
+
+# --------------------------------------------------------------------------
+# N4: ingest-side text dedup (rag/utils/dedup.py:19-55): Jaccard similarity of
+#     token 5-gram shingle sets, greedy keep-first, comparison '>=' (:50).
+#     Pinned by tests/golden/reference_dedup.json (live reference outputs).
+# --------------------------------------------------------------------------
+_DEDUP_PUNCT = re.compile(r"[^\w\s]", re.UNICODE)
+
+
+def dedup_norm_tokens(text: str) -> List[str]:
+    """dedup.py:19-23: lower-case, punctuation -> space, split on whitespace."""
+    return _DEDUP_PUNCT.sub(" ", (text or "").lower()).split()
+
+
+def dedup_shingles(tokens: Sequence[str], k: int = 5) -> set:
+    """dedup.py:25-29: all k-grams; a shorter non-empty text is one shingle; empty -> empty set."""
+    toks = tuple(tokens)
+    if not toks:
+        return set()
+    if len(toks) < k:
+        return {toks}
+    return {toks[i:i + k] for i in range(len(toks) - k + 1)}
+
+
+def dedup_jaccard(a: set, b: set) -> float:
+    """dedup.py:31-38."""
+    if not a and not b:
+        return 1.0
+    if not a or not b:
+        return 0.0
+    inter = len(a & b)
+    return inter / (len(a) + len(b) - inter)
+
+
+def dedup_keep_indices(blocks: Sequence[str], threshold: float = 0.92) -> List[int]:
+    """dedup.py:40-55 as indices: block i is kept iff no previously KEPT block has Jaccard >= threshold."""
+    kept: List[int] = []
+    kept_sets: List[set] = []
+    for i, text in enumerate(blocks):
+        sh = dedup_shingles(dedup_norm_tokens(text))
+        if not any(dedup_jaccard(sh, other) >= threshold for other in kept_sets):
+            kept.append(i)
+            kept_sets.append(sh)
+    return kept
