@@ -68,20 +68,39 @@ class HybridEngine:
         if overlap is None:
             overlap = os.environ.get("CMRAG_OVERLAP", "1") != "0"
         self.overlap = bool(overlap)
+        self.bm25_first = os.environ.get("CMRAG_BM25_ORDER", "first") != "after"
         self._side = None
 
     def _fork_lexical(self, q_terms, q_ptr, k, lex_mask):
-        """BM25 top-k on the side stream, forked from the current stream; returns (result, join)
-        where join() makes the current stream wait for it.  Works eagerly and under CUDA-graph
-        capture (the fork/join become graph edges)."""
+        """BM25 top-k on the side stream, forked from the current stream at the point of this
+        call; returns (launch, join): launch() enqueues the kernels on the side stream and
+        returns their result, join() makes the current stream wait for them.  Works eagerly and
+        under CUDA-graph capture (the fork/join become graph edges)."""
         cur = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         side = self._side
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            out = self.lexical_topk(q_terms, q_ptr, k, lex_mask)
-        return out, (lambda: cur.wait_stream(side))
+
+        def launch():
+            with torch.cuda.stream(side):
+                return self.lexical_topk(q_terms, q_ptr, k, lex_mask)
+        return launch, (lambda: cur.wait_stream(side))
+
+    def _dense_and_lexical(self, q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, k_bm25, lex_mask):
+        """The two retrievers of a step; BM25 on the side stream when overlap applies."""
+        if not hybrid:
+            return self.dense_pool(q_bf16, pool, dense_mask), None, None
+        if not (self.overlap and q_bf16.shape[0] > 8):
+            return self.dense_pool(q_bf16, pool, dense_mask), None, lambda: self.lexical_topk(q_terms, q_ptr, k_bm25, lex_mask)
+        launch, join = self._fork_lexical(q_terms, q_ptr, k_bm25, lex_mask)
+        if self.bm25_first:
+            bm = launch()
+            dense = self.dense_pool(q_bf16, pool, dense_mask)
+        else:
+            dense = self.dense_pool(q_bf16, pool, dense_mask)
+            bm = launch()
+        return dense, join, lambda: bm
 
     # -- stage helpers -------------------------------------------------------
     def _cert_eps(self, dim: int) -> float:
@@ -149,10 +168,8 @@ class HybridEngine:
         if self.comm is not None:
             return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
         mark()
-        join = None
-        if hybrid and self.overlap and q_bf16.shape[0] > 8:
-            (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
-        scores, ids, counts, flags = self.dense_pool(q_bf16, pool, dense_mask)
+        (scores, ids, counts, flags), join, lexical = self._dense_and_lexical(
+            q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, p.k_bm25, lex_mask)
         self.last_dense_flags = flags
         mark()
         if p.use_mmr:
@@ -165,8 +182,7 @@ class HybridEngine:
         if hybrid:
             if join is not None:
                 join()
-            else:
-                b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+            b_sc, b_ids, b_cnt, _ = lexical()
             bm = (b_ids, b_sc, b_cnt)
         mark()
         out = ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
@@ -180,16 +196,13 @@ class HybridEngine:
         cmr_shard_pack -> all-gather -> cmr_shard_merge -> MMR -> fuse."""
         comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
         try:
-            join = None
-            if hybrid and self.overlap and q_bf16.shape[0] > 8:
-                (b_sc, b_ids, b_cnt, _), join = self._fork_lexical(q_terms, q_ptr, p.k_bm25, lex_mask)
-            dense = self.dense_pool(q_bf16, pool, dense_mask)
+            dense, join, lexical = self._dense_and_lexical(q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr,
+                                                           p.k_bm25, lex_mask)
             bm_local = None
             if hybrid:
                 if join is not None:
                     join()
-                else:
-                    b_sc, b_ids, b_cnt, _ = self.lexical_topk(q_terms, q_ptr, p.k_bm25, lex_mask)
+                b_sc, b_ids, b_cnt, _ = lexical()
                 bm_local = (b_sc, b_ids, b_cnt)
         finally:
             self.comm = comm

@@ -25,7 +25,8 @@ for v in variants:
     os.environ["CMR_BM25_BATCH"] = rest[0] if rest else "0"
     os.environ["CMR_MM_STAGES"] = st
     os.environ["CMR_BM25_CTAS_PER_SM"] = cap
-    eng = HybridEngine(emb, lex, overlap=ov == "1")
+    eng = HybridEngine(emb, lex, overlap=ov in ("1", "2"))
+    eng.bm25_first = ov != "2"     # overlap "2": dense pass enqueued first, BM25 after it
     g = GraphedSearch(eng, p, b, max_terms=16)
     for s in range(3):
         g.launch_resident(q[s * b:(s + 1) * b], *dev_terms[s])
