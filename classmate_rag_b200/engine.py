@@ -247,6 +247,7 @@ class GraphedSearch:
         self.max_terms = max_terms
         # static device inputs
         self.q_f32 = torch.zeros((n_queries, d), dtype=torch.float32, device=dev)
+        self.q_f32[:, 0] = 1.0   # capture warm-ups run on this buffer: a unit vector, not the all-ties zero query
         self.q_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32, device=dev)
         self.q_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32, device=dev)
         # pinned host staging
