@@ -107,3 +107,28 @@ def test_bm25_dense_columns_do_not_change_results(density, max_terms):
     rng = np.random.default_rng(5)
     _run(docs, doc_ptr, tokens, v, queries, 10, 2048, mask=(rng.random(11000) < 0.5).astype(np.uint8),
          dense_density=density, **kw)
+
+
+def test_bm25_batch_kernel_equals_tile_kernel_and_oracle(monkeypatch):
+    """The opt-in tile-parallel kernel (CMR_BM25_BATCH=1, read per call): same bytes as the
+    default kernel and the oracle on batches it serves (>= 8 queries, k <= 32), with queries it
+    hands back to the tile kernel (> 16 tokens), masks, ragged sizes, dense columns on and off."""
+    from classmate_rag_b200 import lexical, ops
+    rng = np.random.default_rng(12)
+    for n_docs, vocab, k, tile, density in ((20000, 300, 8, 2048, 0.125), (5002, 60, 24, 512, 0.01),
+                                            (40000, 3000, 10, 4096, None), (777, 40, 8, 512, 0.125)):
+        docs, doc_ptr, tokens, v = zipf_corpus(seed=n_docs, n_docs=n_docs, vocab=vocab, mean_len=20)
+        queries = zipf_queries(7, 40, vocab) + [rng.integers(0, vocab, 30).tolist(), [], [-1, 0, 0, 1]]
+        mask = (rng.random(n_docs) < 0.6).astype(np.uint8)
+        for m in (None, mask):
+            monkeypatch.setenv("CMR_BM25_BATCH", "1")
+            ix = _run(docs, doc_ptr, tokens, v, queries, k, tile, mask=m, dense_density=density)
+            qt, qp = lexical.pack_queries(queries)
+            mm = None if m is None else torch.from_numpy(m).cuda()
+            got = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=mm)]
+            monkeypatch.setenv("CMR_BM25_BATCH", "0")
+            want = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=mm)]
+            torch.cuda.synchronize()
+            for a, b in zip(got, want):
+                assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+
