@@ -26,8 +26,14 @@
 //  bm25_finalize_kernel  one CTA per query: selects the k best keys over all CTA
 //                        lists (score desc, doc asc) and writes them out.
 //
-// Algorithmic bytes per query: 12 * sum over query tokens of df(token)
-// (int32 doc + float64 impact per posting).
+//  bm25_batch_kernel     (opt-in, CMR_BM25_BATCH=1) the tile-parallel form for batches: one
+//                        persistent CTA per SM owns document tiles, all queries of a chunk visit
+//                        a slice while its dense columns sit in shared memory (bulk copies +
+//                        mbarriers), accumulators in registers.  Bit-identical output; at parity
+//                        with the tile kernel on B200, hence not the default.
+//
+// Algorithmic bytes per query: 4 * df for a sparse token (packed posting), 8 * documents for a
+// dense token (its factor column); SURVEY.md section 8(d) counts 8 bytes per posting.
 #include <stdlib.h>
 
 #include "topk.cuh"

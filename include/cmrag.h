@@ -166,7 +166,10 @@ size_t cmr_bm25_workspace_bytes(const cmr_lex_index* ix, int n_queries, int k);
  *   row_mask   device, uint8 [n_docs] or NULL (candidate filter only; subset
  *              statistics are the caller's business)
  *   outputs as cmr_dense_topk; zero-score documents are ranked too, in
- *   ascending id order (bm25.py:199 sorts ALL candidates, stably).            */
+ *   ascending id order (bm25.py:199 sorts ALL candidates, stably).
+ *   Environment (read per call): CMR_BM25_BATCH=1 selects the tile-parallel kernel for
+ *   batches of >= 8 queries with k <= 32 (same output); CMR_BM25_CTAS_PER_SM=n plans the
+ *   grid for n resident CTAs per SM.                                           */
 int cmr_bm25_topk(const cmr_lex_index* ix, const int32_t* q_terms, const int32_t* q_ptr,
                   int n_queries, int k, const uint8_t* row_mask,
                   int64_t row_offset, double* out_scores, int64_t* out_ids,
