@@ -180,7 +180,10 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
 
     for (int c0 = qlo; c0 < qhi; c0 += BM_MAXQ) {
       const int m = (qhi - c0) < BM_MAXQ ? (qhi - c0) : BM_MAXQ;
-      __syncthreads();  // previous users of the staging arrays and of the accumulators are done
+      // A later chunk of a long query re-uses the staging arrays the previous chunk's passes read.
+      // (The first chunk needs no barrier: the tile loop ends with one, and before the first tile
+      // nobody has read the staging arrays yet.)
+      if (c0 != qlo) __syncthreads();
       if (one_chunk) {
         if (tid < m) {
           s_lo[tid] = tk_base + pre0;   // dense / unknown tokens: an empty slice (0, 0)
@@ -310,10 +313,10 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
         ++j;
       }
     }
-    if (fresh) {  // no token touched this tile: every document scores 0.0
+    if (fresh) {  // no token touched this tile: every document scores 0.0 (otherwise the last pass ended with a barrier)
       for (int i = tid; i < ix.tile_docs; i += BM_THREADS) acc[i] = 0.0;
+      __syncthreads();
     }
-    __syncthreads();
 
     // Threshold seeding (first tile of this CTA only).  Split the tile into BM_THREADS/4
     // groups of documents and take each group's best score: the KP-th largest of
