@@ -91,4 +91,109 @@ class E5MultilingualEmbedder:
         return self._encode(self._fmt_passages(texts))
 
 
-__all__ = ["E5MultilingualEmbedder"]
+class GraphedQueryEncoder:
+    """Fixed-shape query encode for the serving loop (N4 of SURVEY.md section 8f): the E5
+    forward for ``n_queries`` x ``max_tokens`` token ids is captured in a CUDA graph next to the
+    search graph, reads its ids from static device buffers and writes the unit-norm float32 rows
+    into ``out`` on the device -- e.g. straight into ``GraphedSearch.q_f32`` -- so a question goes
+    text -> ids (host tokeniser) -> one H2D copy of the ids -> encoder graph -> search graph
+    without the device -> host -> device hop of the reference (rag/pipeline/rag.py:533-545 loads
+    the model per ask and passes NumPy arrays).  The model stays PyTorch (north star).
+
+    If the model's forward cannot be captured (a data-dependent host check inside the
+    attention-mask preparation of some transformers versions), the encoder runs eagerly on the
+    same buffers: ``graph`` is then None.  Results are identical either way."""
+
+    def __init__(self, embedder: E5MultilingualEmbedder, n_queries: int, max_tokens: int = 64, *,
+                 out: Optional[torch.Tensor] = None, stream=None, use_graph: bool = True) -> None:
+        self.emb, self.b, self.l = embedder, int(n_queries), int(max_tokens)
+        dev = embedder.device
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        d = int(embedder.model.config.hidden_size)
+        pad_id = getattr(embedder.model.config, "pad_token_id", None)
+        self.pad_id = 0 if pad_id is None else int(pad_id)
+        self.ids = torch.full((self.b, self.l), self.pad_id, dtype=torch.long, device=dev)
+        self.mask = torch.zeros((self.b, self.l), dtype=torch.long, device=dev)
+        self.mask[:, 0] = 1                      # warm-up runs need a non-empty row
+        self.h_ids = torch.full((self.b, self.l), self.pad_id, dtype=torch.long)
+        self.h_mask = torch.zeros((self.b, self.l), dtype=torch.long)
+        if dev.type == "cuda":
+            self.h_ids, self.h_mask = self.h_ids.pin_memory(), self.h_mask.pin_memory()
+        self.out = out if out is not None else torch.zeros((self.b, d), dtype=torch.float32, device=dev)
+        if tuple(self.out.shape) != (self.b, d) or self.out.dtype != torch.float32 or self.out.device != dev:
+            raise ValueError("out must be a float32 [n_queries, hidden_size] tensor on the encoder's device")
+        self.stream = stream
+        self.graph = None
+        self.capture_error: Optional[str] = None
+        if use_graph and dev.type == "cuda":
+            self._capture()
+
+    @torch.no_grad()
+    def _forward(self) -> None:
+        hidden = self.emb.model(input_ids=self.ids, attention_mask=self.mask).last_hidden_state.float()
+        m = self.mask.unsqueeze(-1).float()
+        pooled = (hidden * m).sum(1) / m.sum(1).clamp(min=1e-9)
+        if self.emb.normalize:
+            pooled = torch.nn.functional.normalize(pooled, p=2, dim=1)
+        self.out.copy_(pooled)
+
+    def _capture(self) -> None:
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            for _ in range(2):
+                self._forward()
+            self.stream.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._forward()
+                self.graph = g
+            except Exception as e:  # capture refused: stay eager (same buffers, same result)
+                self.graph = None
+                self.capture_error = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize(self.device)
+
+    def set_texts(self, queries: List[str]) -> None:
+        """Tokenise ("query: " prefix, truncation to max_tokens) into the pinned host buffers;
+        fewer than n_queries texts leave the remaining rows empty (their output rows are unused)."""
+        if len(queries) > self.b:
+            raise ValueError(f"{len(queries)} queries for an encoder captured for {self.b}")
+        self.h_ids.fill_(self.pad_id)
+        self.h_mask.zero_()
+        self.h_mask[:, 0] = 1
+        if queries:
+            enc = self.emb.tokenizer(self.emb._fmt_queries(queries), padding=True, truncation=True,
+                                     max_length=self.l, return_tensors="pt")
+            ids, mask = enc["input_ids"][:, : self.l], enc["attention_mask"][:, : self.l]
+            self.h_ids[: ids.shape[0], : ids.shape[1]] = ids
+            self.h_mask[: ids.shape[0]] = 0
+            self.h_mask[: ids.shape[0], : ids.shape[1]] = mask
+
+    def launch(self) -> torch.Tensor:
+        """H2D copy of the ids + the encoder (graph replay or eager) on ``stream``; returns
+        ``out`` (valid in stream order, nothing is synchronised)."""
+        if self.device.type != "cuda":
+            self.ids.copy_(self.h_ids)
+            self.mask.copy_(self.h_mask)
+            self._forward()
+            return self.out
+        if self.stream is None:
+            self.stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.ids.copy_(self.h_ids, non_blocking=True)
+            self.mask.copy_(self.h_mask, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._forward()
+        return self.out
+
+    def __call__(self, queries: List[str]) -> torch.Tensor:
+        self.set_texts(queries)
+        return self.launch()
+
+
+__all__ = ["E5MultilingualEmbedder", "GraphedQueryEncoder"]

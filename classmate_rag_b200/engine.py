@@ -338,8 +338,17 @@ class GraphedSearch:
         q_f32 [B, dim] float32, q_terms int32 (at most B * max_terms), q_ptr int32 [B + 1]).
         Results stay on the device (``self.out``); nothing is copied to the host."""
         self._check_graph()
+        # the inputs were produced on the caller's stream and may be temporaries: order this
+        # stream after it and keep their memory from being reused while the copies are pending
+        cur = torch.cuda.current_stream(self.engine.device)
+        if cur != self.stream:
+            self.stream.wait_stream(cur)
+            for t in (q_f32, q_terms, q_ptr):
+                if t is not None:
+                    t.record_stream(self.stream)
         with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
-            self.q_f32.copy_(q_f32, non_blocking=True)
+            if q_f32.data_ptr() != self.q_f32.data_ptr():   # an encoder may have written the buffer itself
+                self.q_f32.copy_(q_f32, non_blocking=True)
             if self.hybrid:
                 n = q_terms.numel()
                 if n > self.q_terms.numel():

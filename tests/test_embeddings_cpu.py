@@ -45,3 +45,25 @@ def test_contract_prefix_pooling_norm():
     assert emb.encode_queries([]).shape == (0, 64)
     raw = E5MultilingualEmbedder(model=_tiny(), tokenizer=_Tok(), device="cpu", normalize=False).encode_queries(["kernel"])
     assert not np.isclose(np.linalg.norm(raw[0]), 1.0, atol=1e-3)
+
+
+def test_fixed_shape_encoder_equals_wrapper_on_cpu():
+    """GraphedQueryEncoder's host logic (padding to the captured width, empty rows, truncation)
+    on the CPU in eager mode: same rows as the wrapper."""
+    from classmate_rag_b200.embeddings import E5MultilingualEmbedder, GraphedQueryEncoder
+    emb = E5MultilingualEmbedder(model=_tiny(), tokenizer=_Tok(), device="cpu")
+    enc = GraphedQueryEncoder(emb, n_queries=4, max_tokens=16)
+    assert enc.graph is None
+    qs = ["what is a gradient", "kernel", "memory bandwidth of HBM"]
+    got = enc(qs).numpy().copy()
+    want = emb.encode_queries(qs)
+    assert got.shape == (4, 64) and np.allclose(got[:3], want, atol=1e-5)
+    again = enc(["kernel"]).numpy()
+    assert np.allclose(again[0], want[1], atol=1e-5)
+    long_q = " ".join(["token"] * 60)
+    assert np.allclose(enc([long_q]).numpy()[0], E5MultilingualEmbedder(
+        model=emb.model, tokenizer=_Tok(), device="cpu", max_length=16).encode_queries([long_q])[0], atol=1e-5)
+    import pytest
+    with pytest.raises(ValueError):
+        enc(["a"] * 5)
+
