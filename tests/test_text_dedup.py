@@ -37,6 +37,50 @@ def test_host_shingle_sets_equal_oracle_sets():
         assert np.intersect1d(a, b).size == len(sets[i] & sets[j])
 
 
+def test_id_sets_plus_pair_rule_reproduce_the_reference_on_random_text():
+    """Host side end to end on the CPU: the id sets the GPU receives, pushed through the pair rule
+    the kernel implements (integer intersection, float64 inter/union >= thr, empty-set conventions)
+    and the greedy keep-first pass, give the oracle's kept indices on random punctuated /
+    accented / repeated text."""
+    from classmate_rag_b200.retrieval import dedup
+    rng = np.random.default_rng(99)
+    alphabet = ["alpha", "Beta", "GAMMA", "été", "naïve", "x1", "under_score", "l'Hôpital", "a-b", "42", "ß"]
+    seps = [" ", "  ", ", ", ". ", "\n", " - ", "!", "\t"]
+    for trial in range(20):
+        blocks = []
+        for i in range(int(rng.integers(2, 40))):
+            if blocks and rng.random() < 0.4:
+                toks = blocks[int(rng.integers(0, len(blocks)))].split(" ")
+                if toks and rng.random() < 0.7:
+                    toks[int(rng.integers(0, len(toks)))] = alphabet[int(rng.integers(0, len(alphabet)))]
+                blocks.append(" ".join(toks))
+            else:
+                n = int(rng.integers(0, 25))
+                blocks.append("".join(alphabet[int(rng.integers(0, len(alphabet)))] + seps[int(rng.integers(0, len(seps)))]
+                                      for _ in range(n)))
+        ptr, items = dedup.shingle_sets(blocks)
+        sets = [items[ptr[i]:ptr[i + 1]] for i in range(len(blocks))]
+        for thr in (0.92, 0.6, 1.0):
+            keep = []
+            for i, a in enumerate(sets):
+                dup = False
+                for j in keep:
+                    b = sets[j]
+                    if a.size == 0 and b.size == 0:
+                        jac = 1.0
+                    elif a.size == 0 or b.size == 0:
+                        jac = 0.0
+                    else:
+                        inter = np.intersect1d(a, b).size
+                        jac = float(inter) / float(a.size + b.size - inter)
+                    if jac >= thr:
+                        dup = True
+                        break
+                if not dup:
+                    keep.append(i)
+            assert keep == o.dedup_keep_indices(blocks, thr), (trial, thr)
+
+
 @pytest.mark.gpu
 def test_dedup_text_blocks_matches_reference_golden():
     from classmate_rag_b200.retrieval import dedup
