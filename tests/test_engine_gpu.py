@@ -87,6 +87,38 @@ def test_engine_matches_oracle_pipeline(small_world, hybrid, use_mmr, top_k):
             assert int(planted[b]) in [w["id"] for w in want[b]] or hybrid
 
 
+def test_side_stream_schedules_give_identical_results(small_world):
+    """Batches on the tcgen05 path (> 8 queries) run BM25 on a side stream (engine overlap): serial,
+    BM25-first and dense-first schedules, eager and from a CUDA graph, must return the same bytes,
+    and those must be the oracle pipeline's."""
+    from classmate_rag_b200 import lexical, ops, synth
+    from classmate_rag_b200.engine import GraphedSearch, HybridEngine, SearchParams
+    eng0, emb, lex, _, _, _, lex_arrays = small_world
+    nq = 20
+    q, _ = synth.dense_queries(emb.shape[0], emb.shape[1], nq, "cuda")
+    terms = synth.lexical_queries(nq, 3000)
+    q_bf16 = ops.f32_to_bf16(q)
+    qt, qp = [t.cuda() for t in lexical.pack_queries(terms)]
+    p = SearchParams(top_k=10)
+    ref = None
+    for overlap, first in ((False, True), (True, True), (True, False)):
+        eng = HybridEngine(emb, lex, overlap=overlap)
+        eng.bm25_first = first
+        for rep in range(3):
+            out = [t.clone() for t in eng.search(q_bf16, qt, qp, p)]
+            torch.cuda.synchronize()
+            got = [t.cpu().numpy().tobytes() for t in out]
+            ref = ref or got
+            assert got == ref, (overlap, first, rep)
+        gs = GraphedSearch(eng, p, nq, max_terms=16)
+        for rep in range(3):
+            g = gs(q.cpu().numpy(), terms)
+            assert [a.tobytes() for a in g] == ref, (overlap, first, "graph", rep)
+    emb_bits, q_bits = _bits(emb), _bits(q_bf16)
+    want = [_oracle_hybrid(emb_bits, q_bits[b], lex_arrays, terms[b], p) for b in range(4)]
+    _check([t.cpu().numpy()[:4] for t in eng.search(q_bf16, qt, qp, p)], want)
+
+
 def test_graphed_search_equals_eager_and_is_deterministic(small_world):
     from classmate_rag_b200 import lexical, ops
     from classmate_rag_b200.engine import GraphedSearch, SearchParams
