@@ -20,6 +20,7 @@ CMR_FLAG_UNCERTIFIED = 1
 CMR_MAX_K = 120
 CMR_SLACK = 8
 CMR_DENSE_AUTO, CMR_DENSE_SCAN, CMR_DENSE_MMA, CMR_DENSE_EXACT = 0, 1, 2, 3
+CMR_BM25_AUTO, CMR_BM25_EXACT, CMR_BM25_HEAD, CMR_BM25_HEAD_NOFALLBACK = 0, 1, 2, 3
 
 _lib = None
 
@@ -59,6 +60,8 @@ _SIGNATURES = {
     "cmr_bm25_workspace_bytes": (_sz, [_vp, C.c_int, C.c_int]),
     "cmr_bm25_topk": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cmr_bm25_topk_ex": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _i64,
+                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp, C.c_int]),
 }
 
 

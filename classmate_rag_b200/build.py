@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcmrag.so"
-SOURCES = ["api.cu", "dense.cu", "dense_mma.cu", "bm25.cu", "fuse.cu", "text.cu"]
+SOURCES = ["api.cu", "dense.cu", "dense_mma.cu", "bm25.cu", "bm25_mma.cu", "fuse.cu", "text.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

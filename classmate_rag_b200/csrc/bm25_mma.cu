@@ -1,0 +1,712 @@
+// bm25_mma.cu -- A2 batched: BM25 top-k for a batch of queries with the head terms on the tensor cores.
+//
+// Replaces BM25Okapi.get_scores + sorted(...)[:k] inside BM25Store.search (reference
+// rag/retrieval/bm25.py:175-212) for batches; the exact kernels of bm25.cu cost ~43 us per query
+// at 10M documents because every query sweeps every document on its own.  Here the part of the
+// score that every document has -- the contributions of the up to 64 terms with the longest
+// posting lists ("head" terms: 97 % of the posting volume a Zipf query touches) -- is one matrix
+// product per block of 32 queries:
+//
+//     approx[d, q] = sum_c head_mat[d, c] * count[q, c]  +  sum over sparse tokens t of q: fp16(idf_t * f(t, d))
+//
+// head_mat [n_docs, 64] holds fp16(idf * factor) (built with the index), count[q, c] is how often
+// head term c occurs in query q (exact in fp16), the products are exact and the tensor pipe
+// accumulates in fp32.  The sparse remainder is a CSR posting-list scatter:
+//
+//   bm25x_prep_kernel     per block of 32 queries: the count matrix and the list of (query,
+//                         sparse term, idf) pairs; queries with more than 16 tokens or a negative
+//                         idf are flagged (the exact kernels serve them).
+//   bm25x_bucket_kernel   one CTA per tile of the index: the slices of the pairs' posting lists
+//                         that fall into the tile (skip table, no search) are scattered in
+//                         shared memory into one bucket per 32 documents as (document, query,
+//                         fp16 contribution) words; buckets go to HBM with coalesced stores
+//                         (~100 B per 32 documents: 3 % of the head matrix).
+//   bm25x_mma_kernel      persistent, one CTA per SM.  warp 0: TMA producer, one [128 documents x
+//                         64 terms] box of head_mat per item into an 8-stage ring of 128-byte
+//                         swizzled tiles (16 KB each).  warp 1: one thread issues 4 x tcgen05.mma
+//                         (cta_group::1, kind::f16, M = 128 documents = TMEM lanes, N = 32 queries =
+//                         TMEM columns, K = 16) per item into a ring of 8 TMEM accumulators;
+//                         tcgen05.commit frees the ring slot and publishes the accumulator.
+//                         warps 2-9: epilogue, two warps per TMEM lane quarter on alternating items.
+//                         A warp scatters its bucket (prefetched one item ahead) into a 32 x 32
+//                         fp32 tile in shared memory, reads the accumulator with tcgen05.ld (one
+//                         document per thread, 32 queries per load), adds its row of the tile and
+//                         compares with the 32 admission bounds held in registers; the rare
+//                         survivors are appended to the CTA's candidate list of the query.
+//                         SAMPLE mode visits every 16th tile and keeps per-thread running maxima;
+//                         the KP-th largest of those group maxima (launch_admission_bound) is
+//                         attained by KP different documents, hence a lower bound of the KP-th best
+//                         approximate score: MAIN mode with that bound keeps a superset of the
+//                         approximate top KP.
+//   bm25x_finalize_kernel one CTA per query: the KP best candidates by approximate score are
+//                         rescored exactly -- float64, query-token order, idf * factor rounded then
+//                         added (rank_bm25's operation order), the factor of every (token, document)
+//                         found by bisection in the term's tile slice -- and ranked (score desc,
+//                         document asc).  Certificate: every document outside the KP has approximate
+//                         score <= cut-off, hence exact score <= (cut-off + abs) / (1 - rho) with
+//                         rho = 2^-11 (fp16 rounding of each contribution) + accumulation slack;
+//                         if the k-th exact score is above that, the top k is THE top k and its
+//                         scores are bit-identical to the exact kernels'.  Otherwise the query is
+//                         flagged and bm25.cu re-runs it.
+//
+// Algorithmic bytes per block of 32 queries: n_docs * 128 (head_mat, read once) + 4 per sparse
+// posting (read by the bucket kernel) + 2 * 4 per bucket entry (written, read back), + 1/16 of
+// the matrix for the sample pass.  HBM-bound: the MMA work per item is 128 x 32 x 64.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "bm25_head.cuh"
+#include "mma_common.cuh"
+
+namespace cmr {
+
+constexpr int BX_M = 128;                     // documents per item (UMMA M, TMEM lanes)
+constexpr int BX_N = 32;                      // queries per block (UMMA N, TMEM columns)
+constexpr int BX_K = 64;                      // head terms: one 128-byte swizzle span of fp16
+constexpr int BX_STAGES = 8;                  // ring of head_mat boxes (128 KB in flight per SM)
+constexpr int BX_ACC = 8;                     // TMEM accumulators (8 x 32 columns)
+constexpr int BX_A_BYTES = BX_M * BX_K * 2;   // 16 KiB
+constexpr int BX_Q_BYTES = BX_N * BX_K * 2;   // 4 KiB
+constexpr int BX_EPI_WARPS = 8;
+constexpr int BX_THREADS = (2 + BX_EPI_WARPS) * 32;
+constexpr int BX_S_BYTES = 32 * BX_N * 4;     // one epilogue warp's 32 documents x 32 queries fp32 tile
+constexpr int BX_CAP = 256;                   // words per bucket of 32 documents; word 0 = entry count
+constexpr int BX_MAXT = 16;                   // tokens per query served here
+constexpr int BX_MAX_PAIRS = BX_N * BX_MAXT;  // (query, sparse term) pairs per block
+constexpr int BX_SAMPLE = 0, BX_MAIN = 1;
+constexpr int BX_SAMPLE_STRIDE = 16;
+constexpr int BX_GROUPS_PER_CTA = BX_EPI_WARPS * 2;   // SAMPLE: group maxima each CTA hands to the bound kernel
+constexpr int BX_LIST_CAP = 256;              // candidate slots per (CTA, query)
+constexpr int BX_CAP_PER_KP = 128;            // candidates finalize can collect per query = 128 * KP
+constexpr int BX_MAX_TILE_DOCS = 2048;        // bucket kernel: tile_docs / 32 buckets of BX_CAP words in shared memory
+// kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), both K-major, N >> 3, M >> 4
+constexpr u32 BX_IDESC = (1u << 4) | ((u32)(BX_N >> 3) << 17) | ((u32)(BX_M >> 4) << 24);
+
+// reasons a query is handed back to the exact kernels (bit 0 = CMR_FLAG_UNCERTIFIED is always set with them)
+constexpr int BX_F_LONG = 2, BX_F_NEG = 4, BX_F_BUCKET = 8, BX_F_LIST = 16, BX_F_CERT = 32;
+
+// |approx - exact| <= BX_RHO * exact + BX_ABS for non-negative contributions: every contribution is
+// rounded to fp16 once (2^-11 relative; below the fp16 normal range 2^-25 absolute), products with
+// the integer counts are exact, at most 64 + 16 fp32 additions (2^-23 relative each, the tensor
+// pipe may truncate) -> 2^-11 + 80 * 2^-23 < 2^-11 * 1.03; 1.0625 leaves a margin.
+constexpr double BX_RHO = 1.0625 / 2048.0;
+constexpr double BX_ABS = 4e-6;
+
+struct __align__(16) BxPair {
+  int term;
+  int q;      // query within the block
+  double w;   // idf
+};
+
+__device__ __forceinline__ u32 ldg_stream_word(const u32* p) {
+  u32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// One CTA per block of 32 queries.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bm25x_prep_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr, int n_queries,
+                  __half* __restrict__ qmat, BxPair* __restrict__ pairs, int* __restrict__ n_pairs,
+                  int* __restrict__ flags) {
+  __shared__ int s_cnt[BX_N][BX_K];
+  __shared__ int s_np;
+  const int blk = blockIdx.x, tid = threadIdx.x, q0 = blk * BX_N;
+  for (int i = tid; i < BX_N * BX_K; i += 256) (&s_cnt[0][0])[i] = 0;
+  if (tid == 0) s_np = 0;
+  __syncthreads();
+  if (tid < BX_N && q0 + tid < n_queries) {
+    const int q = q0 + tid;
+    int flag = 0, real = 0;
+    for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+      const int t = q_terms[i];
+      if (t < 0 || t >= ix.n_terms) continue;
+      if (++real > BX_MAXT) {
+        flag |= BX_F_LONG;
+        break;
+      }
+      const double w = ix.idf[t];
+      if (w < 0.0) flag |= BX_F_NEG;
+      if (w == 0.0) continue;
+      const int slot = ix.head_slot[t];
+      if (slot >= 0) {
+        s_cnt[tid][slot]++;
+      } else {
+        const int p = atomicAdd(&s_np, 1);   // <= BX_MAXT per query
+        BxPair pr;
+        pr.term = t;
+        pr.q = tid;
+        pr.w = w;
+        pairs[(size_t)blk * BX_MAX_PAIRS + p] = pr;
+      }
+    }
+    flags[q] = flag ? (CMR_FLAG_UNCERTIFIED | flag) : 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < BX_N * BX_K; i += 256) qmat[(size_t)blk * BX_N * BX_K + i] = __int2half_rn((&s_cnt[0][0])[i]);
+  if (tid == 0) n_pairs[blk] = s_np;
+}
+
+// ---------------------------------------------------------------------------------------
+// One CTA per tile of the index: bucket the block's sparse postings by 32-document group.
+// buckets [n_tiles * tile_docs / 32][BX_CAP]: word 0 = number of entries (<= BX_CAP - 1), then
+// entries  bits 0-4 document within the group | bits 5-9 query | bits 16-31 fp16(idf * factor).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const int* __restrict__ n_pairs_p, int q_base,
+                    u32* __restrict__ buckets, int* __restrict__ flags) {
+  extern __shared__ u32 s_b[];                  // [n_b][BX_CAP]
+  __shared__ long long s_lo[BX_MAX_PAIRS];
+  __shared__ int s_off[BX_MAX_PAIRS + 1];
+  __shared__ int s_cnt[BX_MAX_TILE_DOCS / 32];
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_b = ix.tile_docs / 32;
+  const int np = *n_pairs_p;
+  for (int b = tid; b < n_b; b += 256) s_cnt[b] = 0;
+  if (tid == 0) s_off[0] = 0;
+  for (int p = tid; p < np; p += 256) {
+    const int t = pairs[p].term;
+    const u32* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
+    const u32 a = sk[0], z = sk[1];
+    s_lo[p] = ix.term_ptr[t] + a;
+    s_off[p + 1] = (int)(z - a);
+  }
+  __syncthreads();
+  if (warp == 0) {  // inclusive scan of the slice lengths
+    int carry = 0;
+    for (int base = 0; base < np; base += 32) {
+      const int i = base + lane;
+      int v = i < np ? s_off[i + 1] : 0;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, v, off);
+        if (lane >= off) v += o;
+      }
+      if (i < np) s_off[i + 1] = carry + v;
+      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+  }
+  __syncthreads();
+  const int total = s_off[np];
+  for (int i = tid; i < total; i += 256) {
+    int lo = 0, hi = np;   // the pair whose slice holds posting i: largest p with s_off[p] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    const u32 pk = ldg_stream_word(ix.post_pack + s_lo[lo] + (i - s_off[lo]));
+    const BxPair pr = pairs[lo];
+    const u32 local = pk & 0xFFFFu;
+    const __half h = __double2half(__dmul_rn(pr.w, __ldg(ix.imp_table + (pk >> 16))));
+    const int b = (int)(local >> 5);
+    const int slot = atomicAdd(&s_cnt[b], 1) + 1;
+    if (slot < BX_CAP) s_b[b * BX_CAP + slot] = (local & 31u) | ((u32)pr.q << 5) | ((u32)__half_as_ushort(h) << 16);
+    else atomicOr(&flags[q_base + pr.q], CMR_FLAG_UNCERTIFIED | BX_F_BUCKET);
+  }
+  __syncthreads();
+  for (int b = warp; b < n_b; b += 8) {
+    const int c = s_cnt[b] < BX_CAP - 1 ? s_cnt[b] : BX_CAP - 1;
+    u32* dst = buckets + ((size_t)tile * n_b + b) * BX_CAP;
+    for (int i = lane; i <= c; i += 32) dst[i] = i == 0 ? (u32)c : s_b[b * BX_CAP + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct BxParams {
+  long long n_docs;
+  int n_items;          // tiles of 128 documents this launch visits
+  int stride;           // SAMPLE: visited tile = item * stride (full tiles only); MAIN: 1
+  int n_queries;        // queries of this block (<= 32)
+  const u32* buckets;   // [ceil(n_docs / 32) rounded up to whole index tiles][BX_CAP]
+  float* gmax;          // SAMPLE: [gridDim.x * BX_GROUPS_PER_CTA][32]
+  const float* thr;     // MAIN: [32] admission bounds
+  u64* cand;            // MAIN: [gridDim.x][32][cap] keys (orderable fp32 score, ~document)
+  int* cnt;             // MAIN: [gridDim.x][32] entries appended (may exceed cap)
+  int cap;
+};
+
+// shared memory (offsets from the 1024-byte aligned base): ring, query tile, epilogue tiles, control
+constexpr u32 BX_OFF_Q = BX_STAGES * BX_A_BYTES;
+constexpr u32 BX_OFF_S = BX_OFF_Q + BX_Q_BYTES;
+constexpr u32 BX_OFF_BAR = BX_OFF_S + BX_EPI_WARPS * BX_S_BYTES;
+// barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +192+8a, qfull +256; TMEM base +264; list counters +272
+constexpr u32 BX_OFF_CNT = BX_OFF_BAR + 272;
+constexpr size_t BX_SMEM = 1024 + BX_OFF_CNT + BX_N * 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(BX_THREADS, 1)
+bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_rows,
+                 const BxParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const u32 raw = smem_u32(smem_raw);
+  const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* gen = smem_raw + (base - raw);
+  const u32 bars = base + BX_OFF_BAR;
+  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(gen + BX_OFF_BAR + 264);
+  int* s_cnt = reinterpret_cast<int*>(gen + BX_OFF_CNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < BX_EPI_WARPS * BX_S_BYTES / 16; i += BX_THREADS)
+    reinterpret_cast<float4*>(gen + BX_OFF_S)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < BX_N) s_cnt[threadIdx.x] = 0;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+    for (int s = 0; s < BX_STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 64 + 8 * s, 1);
+    }
+    for (int a = 0; a < BX_ACC; ++a) {
+      mbar_init(bars + 128 + 8 * a, 1);
+      mbar_init(bars + 192 + 8 * a, 4);  // one arrival per epilogue warp of the accumulator's group
+    }
+    mbar_init(bars + 256, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the allocating warp also frees
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 264),
+                 "r"((u32)(BX_ACC * BX_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+  const int first = (int)blockIdx.x, step = (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_expect_tx(bars + 256, BX_Q_BYTES);
+      tma_load_2d(base + BX_OFF_Q, &tm_q, bars + 256, 0, 0, TMA_EVICT_LAST);
+      u32 s = 0, ph = 0;
+      for (int it = first; it < p.n_items; it += step) {
+        mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
+        mbar_expect_tx(bars + 8 * s, BX_A_BYTES);
+        tma_load_2d(base + s * BX_A_BYTES, &tm_rows, bars + 8 * s, 0, it * p.stride * BX_M, TMA_EVICT_FIRST);
+        if (++s == BX_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      mbar_wait(bars + 256, 0);
+      tc_fence_after();
+      const unsigned long long dq = umma_desc_sw128(base + BX_OFF_Q);
+      u32 s = 0, ph = 0, li = 0;
+      for (int it = first; it < p.n_items; it += step, ++li) {
+        const u32 acc = li % BX_ACC, aph = (li / BX_ACC) & 1u;
+        mbar_wait(bars + 192 + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        mbar_wait(bars + 8 * s, ph);                // TMA bytes have landed
+        tc_fence_after();
+        const unsigned long long da = umma_desc_sw128(base + s * BX_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BX_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
+          tc_mma_bf16(tmem_base + acc * BX_N, da + 2ull * k, dq + 2ull * k, BX_IDESC, k != 0);
+        tc_commit(bars + 64 + 8 * s);        // frees the ring slot when these MMAs retire
+        tc_commit(bars + 128 + 8 * acc);     // accumulator complete
+        if (++s == BX_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. +31; group g takes items li = g, g+2, ... =====
+    const int e = warp - 2, lq = warp & 3, g = e >> 2;
+    float* S = reinterpret_cast<float*>(gen + BX_OFF_S + e * BX_S_BYTES);
+    float4* S4 = reinterpret_cast<float4*>(S) + lane * 8;
+    float bnd[32], gm[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      bnd[j] = INFINITY;
+      gm[j] = -INFINITY;
+      if (MODE == BX_MAIN && j < p.n_queries) bnd[j] = p.thr[j];
+    }
+    u32 li = (u32)g;
+    long long it = (long long)first + (long long)li * step;
+    u32 w0 = 0, w1 = 0;
+    if (it < p.n_items) {
+      const u32* bp = p.buckets + ((size_t)it * p.stride * 4 + lq) * BX_CAP;
+      w0 = ldg_stream_word(bp + lane);
+      w1 = ldg_stream_word(bp + 32 + lane);
+    }
+    for (; it < p.n_items; li += 2, it += 2ll * step) {
+      const long long tile = it * p.stride;
+      const u32* bp = p.buckets + ((size_t)tile * 4 + lq) * BX_CAP;
+      const long long nit = it + 2ll * step;
+      u32 n0 = 0, n1 = 0;
+      if (nit < p.n_items) {   // the next item's bucket is in flight while this one is processed
+        const u32* nb = p.buckets + ((size_t)nit * p.stride * 4 + lq) * BX_CAP;
+        n0 = ldg_stream_word(nb + lane);
+        n1 = ldg_stream_word(nb + 32 + lane);
+      }
+      // ---- scatter the bucket's sparse contributions into the warp's tile ----
+      int cnt = (int)__shfl_sync(0xFFFFFFFFu, w0, 0);
+      cnt = cnt < BX_CAP - 1 ? cnt : BX_CAP - 1;
+      {
+        auto apply = [&](u32 w) {
+          const u32 r = w & 31u, q = (w >> 5) & 31u;
+          const float val = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+          atomicAdd(S + r * 32 + ((((q >> 2) ^ (r & 7u))) << 2) + (q & 3u), val);
+        };
+        if (lane >= 1 && lane - 1 < cnt) apply(w0);
+        if (31 + lane < cnt) apply(w1);
+        for (int x = 63 + lane; x < cnt; x += 32) apply(bp[1 + x]);
+      }
+      __syncwarp();
+      // ---- accumulator -> registers; release it at once ----
+      const u32 acc = li % BX_ACC, aph = (li / BX_ACC) & 1u;
+      mbar_wait(bars + 128 + 8 * acc, aph);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 192 + 8 * acc);
+      // ---- add this document's row of the tile (16-byte chunks XOR-swizzled by the row) and clear it ----
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4* pp = S4 + (c ^ (lane & 7));
+        const float4 s4 = *pp;
+        *pp = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * c] += s4.x;
+        v[4 * c + 1] += s4.y;
+        v[4 * c + 2] += s4.z;
+        v[4 * c + 3] += s4.w;
+      }
+      __syncwarp();
+      if (MODE == BX_SAMPLE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gm[j] = fmaxf(gm[j], v[j]);
+      } else {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) any |= v[j] >= bnd[j];
+        if (any) {
+          // Rare (about 16 * KP documents per query over the whole pass).
+          const long long row = tile * BX_M + lq * 32 + lane;
+          if (row < p.n_docs) {
+            u32 hits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hits |= (v[j] >= bnd[j] ? 1u : 0u) << j;
+            while (hits) {
+              const int j = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const int slot = atomicAdd(&s_cnt[j], 1);
+              if (slot < p.cap)
+                p.cand[((size_t)blockIdx.x * BX_N + j) * p.cap + slot] = make_key(pick32(v, j), (u32)row);
+            }
+          }
+        }
+      }
+      w0 = n0;
+      w1 = n1;
+    }
+    if (MODE == BX_SAMPLE) {
+      // group maxima: 16 lanes each -> BX_GROUPS_PER_CTA groups per CTA (a group that saw no
+      // document reports -inf, which is a valid maximum of nothing)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float m = gm[j];
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 8));
+        gm[j] = m;
+      }
+      if ((lane & 15) == 0) {
+        float* dst = p.gmax + ((size_t)blockIdx.x * BX_GROUPS_PER_CTA + e * 2 + (lane >> 4)) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = gm[j];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (MODE == BX_MAIN && threadIdx.x < BX_N) p.cnt[(size_t)blockIdx.x * BX_N + threadIdx.x] = s_cnt[threadIdx.x];
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)(BX_ACC * BX_N))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One CTA per query of the block: KP best candidates -> exact float64 scores -> rank -> certificate.
+// ---------------------------------------------------------------------------------------
+template <int KPL>
+__global__ void __launch_bounds__(FIN_THREADS)
+bm25x_finalize_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr, int q_base,
+                      const u64* __restrict__ cand, const int* __restrict__ cnt, int n_lists, int cap, int cap_total,
+                      const float* __restrict__ thr, long long row_offset, int k, double* __restrict__ out_scores,
+                      long long* __restrict__ out_ids, int* __restrict__ out_counts, int* __restrict__ out_flags) {
+  constexpr int KP = 32 * KPL;
+  extern __shared__ __align__(16) unsigned char smem_fin[];
+  u64* s_keys = reinterpret_cast<u64*>(smem_fin);          // [cap_total]
+  u64* s_out = s_keys + cap_total;                         // [KP]
+  double* s_score = reinterpret_cast<double*>(s_out + KP); // [KP]
+  u64* s_surv = reinterpret_cast<u64*>(s_score + KP);      // [4 * KP]
+  double* s_contrib = reinterpret_cast<double*>(s_surv + 4 * KP);  // [KP][BX_MAXT]
+  __shared__ int s_ctl[2];
+  __shared__ int s_tok[BX_MAXT];
+  __shared__ int s_ntok;
+  const int ql = blockIdx.x, q = q_base + ql, tid = threadIdx.x;
+  if (out_flags[q] != 0) {  // flagged by the prep / bucket kernels: the exact kernels serve it (CTA-uniform)
+    if (tid == 0) out_counts[q] = 0;
+    return;
+  }
+  int n_total, over;
+  cand_collect_select<KP>(cand, cnt, n_lists, BX_N, cap, cap_total, ql, s_keys, s_out, s_surv, s_ctl, &n_total, &over);
+  if (tid == 0) {
+    int n = 0;
+    for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+      const int t = q_terms[i];
+      if (t >= 0 && t < ix.n_terms && n < BX_MAXT) s_tok[n++] = t;
+    }
+    s_ntok = n;
+  }
+  __syncthreads();
+  const int n_valid = count_valid(s_out, KP);
+  const int ntok = s_ntok;
+  // exact contribution of every (candidate, token): bisection in the term's slice of the document's tile
+  for (int idx = tid; idx < n_valid * BX_MAXT; idx += FIN_THREADS) {
+    const int c = idx / BX_MAXT, j = idx - c * BX_MAXT;
+    double contrib = 0.0;
+    if (j < ntok) {
+      const int t = s_tok[j];
+      const u32 row = key_row(s_out[c]);
+      const u32 tile = row / (u32)ix.tile_docs, local = row - tile * (u32)ix.tile_docs;
+      const u32* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
+      const long long tbase = ix.term_ptr[t];
+      u32 lo = sk[0];
+      const u32 end = sk[1];
+      u32 hi = end;
+      while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if ((ix.post_pack[tbase + mid] & 0xFFFFu) < local) lo = mid + 1;
+        else hi = mid;
+      }
+      if (lo < end) {
+        const u32 pk = ix.post_pack[tbase + lo];
+        if ((pk & 0xFFFFu) == local) contrib = __dmul_rn(ix.idf[t], ix.imp_table[pk >> 16]);  // rounded product, as rank_bm25
+      }
+    }
+    s_contrib[idx] = contrib;
+  }
+  __syncthreads();
+  if (tid < n_valid) {
+    double s = 0.0;
+    for (int j = 0; j < ntok; ++j) s = __dadd_rn(s, s_contrib[tid * BX_MAXT + j]);  // query-token order; x + 0.0 == x
+    s_score[tid] = s;
+  }
+  __syncthreads();
+  const int n_out = n_valid < k ? n_valid : k;
+  // every document outside s_out has approximate score <= cutoff
+  double cutoff;
+  if (n_total > KP) cutoff = (double)key_score(s_out[KP - 1]);
+  else cutoff = (double)thr[ql];   // every candidate was selected; the rest stayed below the admission bound
+  const bool open_ended = !(cutoff > -INFINITY);   // no bound at all: every document was a candidate
+  if (tid < n_valid) {
+    const double s = s_score[tid];
+    const u32 r = key_row(s_out[tid]);
+    int rank = 0;
+    for (int j = 0; j < n_valid; ++j) {
+      const double sj = s_score[j];
+      const u32 rj = key_row(s_out[j]);
+      rank += (sj > s) || (sj == s && rj < r);
+    }
+    if (rank < n_out) {
+      out_scores[(size_t)q * k + rank] = s;
+      out_ids[(size_t)q * k + rank] = (long long)r + row_offset;
+    }
+    if (rank == n_out - 1) {
+      int flag = over ? (CMR_FLAG_UNCERTIFIED | BX_F_LIST) : 0;
+      if (!open_ended) {
+        const double reach = (cutoff + BX_ABS) / (1.0 - BX_RHO);   // the best exact score an outsider can have
+        if (n_out < k || !(s > reach)) flag |= CMR_FLAG_UNCERTIFIED | BX_F_CERT;
+      }
+      out_flags[q] = flag;
+    }
+  }
+  for (int i = n_out + tid; i < k; i += FIN_THREADS) {
+    out_scores[(size_t)q * k + i] = 0.0;
+    out_ids[(size_t)q * k + i] = -1;
+  }
+  if (tid == 0) {
+    out_counts[q] = n_out;
+    if (n_out == 0) out_flags[q] = (over || !open_ended) ? (CMR_FLAG_UNCERTIFIED | BX_F_CERT) : 0;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------
+struct BxPlan {
+  int kpl, kp, cap, cap_total;
+  int n_blocks, n_items, n_sample, stride, grid_main, grid_sample, n_groups, n_b;
+  size_t off_qmat, off_pairs, off_npairs, off_thr, off_gmax, off_cand, off_cnt, off_buckets, total;
+  size_t smem_fin, smem_bucket;
+};
+
+static void bx_plan(const cmr_lex_index& ix, int n_queries, int k, int sms, BxPlan* p) {
+  const int need = k + CMR_SLACK;
+  p->kpl = need <= 32 ? 1 : (need <= 64 ? 2 : 4);
+  p->kp = 32 * p->kpl;
+  p->cap = BX_LIST_CAP;
+  p->cap_total = BX_CAP_PER_KP * p->kp;
+  p->n_blocks = (n_queries + BX_N - 1) / BX_N;
+  p->n_items = (int)((ix.n_docs + BX_M - 1) / BX_M);
+  const int full = (int)(ix.n_docs / BX_M);
+  int stride = full / BX_SAMPLE_STRIDE;   // small indexes: sample (nearly) every tile
+  if (stride < 1) stride = 1;
+  if (stride > BX_SAMPLE_STRIDE) stride = BX_SAMPLE_STRIDE;
+  p->stride = stride;
+  p->n_sample = full > 0 ? (full + stride - 1) / stride : 0;
+  p->grid_main = p->n_items < sms ? p->n_items : sms;
+  p->grid_sample = p->n_sample < sms ? p->n_sample : sms;
+  if (p->grid_sample < 1) p->grid_sample = 1;
+  p->n_groups = p->grid_sample * BX_GROUPS_PER_CTA;
+  if (p->n_groups < p->kp) {
+    // no bound (tiny index): every document of a CTA's tiles is a candidate of every query
+    const int per_cta = BX_M * ((p->n_items + p->grid_main - 1) / p->grid_main);
+    if (per_cta > p->cap) p->cap = per_cta;
+  }
+  p->n_b = ix.tile_docs / 32;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t off = 0;
+  p->off_qmat = off;    off += up((size_t)p->n_blocks * BX_N * BX_K * 2);
+  p->off_pairs = off;   off += up((size_t)p->n_blocks * BX_MAX_PAIRS * sizeof(BxPair));
+  p->off_npairs = off;  off += up((size_t)p->n_blocks * 4);
+  p->off_thr = off;     off += up(32 * 4);
+  p->off_gmax = off;    off += up((size_t)p->n_groups * 32 * 4);
+  p->off_cand = off;    off += up((size_t)p->grid_main * BX_N * p->cap * 8);
+  p->off_cnt = off;     off += up((size_t)p->grid_main * BX_N * 4);
+  p->off_buckets = off; off += up((size_t)ix.n_tiles * p->n_b * BX_CAP * 4);
+  p->total = off;
+  p->smem_fin = (size_t)p->cap_total * 8 + (size_t)p->kp * 16 + (size_t)4 * p->kp * 8 + (size_t)p->kp * BX_MAXT * 8 + 16;
+  p->smem_bucket = (size_t)p->n_b * BX_CAP * 4;
+}
+
+bool bm25_head_eligible(const cmr_lex_index& ix, int k, bool has_mask) {
+  return !has_mask && ix.head_mat != nullptr && ix.head_slot != nullptr && ix.post_pack != nullptr &&
+         ix.imp_table != nullptr && ix.n_terms > 0 && ix.n_head >= 0 && ix.n_head <= BX_K && ix.n_docs >= BX_M &&
+         ix.n_docs < 0x7FFFFF00ll && ix.tile_docs <= BX_MAX_TILE_DOCS && ix.tile_docs % BX_M == 0 &&
+         ((uintptr_t)ix.head_mat % 16) == 0 && k >= 1 && k + CMR_SLACK <= 128;
+}
+
+size_t bm25_head_workspace_bytes(const cmr_lex_index& ix, int n_queries, int k) {
+  BxPlan p;
+  const int sms = sm_count();
+  bx_plan(ix, n_queries, k, sms > 0 ? sms : 148, &p);
+  return p.total;
+}
+
+static int bx_opt_in() {
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_dev_mask & (1 << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(bm25x_mma_kernel<BX_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(bm25x_mma_kernel<BX_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(bm25x_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               BX_MAX_TILE_DOCS / 32 * BX_CAP * 4);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(bm25x_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(bm25x_finalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(bm25x_finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(bm25x)");
+    attr_dev_mask |= (1 << dev);
+  }
+  return CMR_OK;
+}
+
+int bm25_head_topk(const cmr_lex_index& ix, const int* q_terms, const int* q_ptr, int n_queries, int k,
+                   long long row_offset, double* out_scores, long long* out_ids, int* out_counts, int* out_flags,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int sms = sm_count();
+  if (sms <= 0) return CMR_ECUDA;
+  BxPlan p;
+  bx_plan(ix, n_queries, k, sms, &p);
+  if (!workspace || workspace_bytes < p.total) {
+    set_error("bm25 head path: workspace too small: %zu < %zu", workspace_bytes, p.total);
+    return CMR_EWORKSPACE;
+  }
+  if (p.smem_fin > 200 * 1024) {
+    set_error("bm25 head path: finalize shared memory %zu too large", p.smem_fin);
+    return CMR_EUNSUPPORTED;
+  }
+  int rc = bx_opt_in();
+  if (rc != CMR_OK) return rc;
+  unsigned char* ws = (unsigned char*)workspace;
+  __half* qmat = (__half*)(ws + p.off_qmat);
+  BxPair* pairs = (BxPair*)(ws + p.off_pairs);
+  int* n_pairs = (int*)(ws + p.off_npairs);
+  float* thr = (float*)(ws + p.off_thr);
+  float* gmax = (float*)(ws + p.off_gmax);
+  u64* cand = (u64*)(ws + p.off_cand);
+  int* cnt = (int*)(ws + p.off_cnt);
+  u32* buckets = (u32*)(ws + p.off_buckets);
+
+  alignas(64) CUtensorMap tm_rows, tm_q;
+  rc = make_tmap(&tm_rows, ix.head_mat, ix.n_docs, BX_K, BX_M, true);
+  if (rc != CMR_OK) return rc;
+  bm25x_prep_kernel<<<p.n_blocks, 256, 0, st>>>(ix, q_terms, q_ptr, n_queries, qmat, pairs, n_pairs, out_flags);
+
+  for (int blk = 0; blk < p.n_blocks; ++blk) {
+    const int q_base = blk * BX_N;
+    const int nq = n_queries - q_base < BX_N ? n_queries - q_base : BX_N;
+    rc = make_tmap(&tm_q, qmat + (size_t)blk * BX_N * BX_K, BX_N, BX_K, BX_N, true);
+    if (rc != CMR_OK) return rc;
+    bm25x_bucket_kernel<<<ix.n_tiles, 256, p.smem_bucket, st>>>(ix, pairs + (size_t)blk * BX_MAX_PAIRS, n_pairs + blk,
+                                                               q_base, buckets, out_flags);
+    BxParams kp{};
+    kp.n_docs = ix.n_docs;
+    kp.n_queries = nq;
+    kp.buckets = buckets;
+    kp.gmax = gmax;
+    kp.thr = thr;
+    kp.cand = cand;
+    kp.cnt = cnt;
+    kp.cap = p.cap;
+    if (p.n_sample > 0) {
+      kp.n_items = p.n_sample;
+      kp.stride = p.stride;
+      bm25x_mma_kernel<BX_SAMPLE><<<p.grid_sample, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
+    }
+    rc = launch_admission_bound(gmax, p.n_sample > 0 ? p.n_groups : 0, 32, p.kp, nq, thr, st);
+    if (rc != CMR_OK) return rc;
+    kp.n_items = p.n_items;
+    kp.stride = 1;
+    bm25x_mma_kernel<BX_MAIN><<<p.grid_main, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
+    switch (p.kpl) {
+      case 1:
+        bm25x_finalize_kernel<1><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
+                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
+                                                                     out_ids, out_counts, out_flags);
+        break;
+      case 2:
+        bm25x_finalize_kernel<2><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
+                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
+                                                                     out_ids, out_counts, out_flags);
+        break;
+      default:
+        bm25x_finalize_kernel<4><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
+                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
+                                                                     out_ids, out_counts, out_flags);
+        break;
+    }
+  }
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
+
+}  // namespace cmr

@@ -33,7 +33,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "dense_common.cuh"
+#include "mma_common.cuh"
 
 namespace cmr {
 
@@ -52,100 +52,9 @@ constexpr int MM_SAMPLE_STRIDE_LARGE = 32;   // ... every 32nd from MM_LARGE_TIL
 #define CMR_MM_LARGE_TILES 8192
 #endif
 constexpr int MM_LARGE_TILES = CMR_MM_LARGE_TILES;   // bound is then still the KP-th of >= 256 tile maxima
-constexpr int MM_MAX_GROUPS = 49152; // threshold kernel keeps the group maxima in shared memory
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
 constexpr u32 MM_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(MM_R >> 3) << 17) | ((u32)(MM_Q >> 4) << 24);
-
-constexpr unsigned long long TMA_EVICT_NORMAL = 0x1000000000000000ull;
-constexpr unsigned long long TMA_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr unsigned long long TMA_EVICT_LAST = 0x14F0000000000000ull;
-
-// ---- PTX wrappers ---------------------------------------------------------------------
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u32 bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MBAR_DONE;\n"
-      "bra MBAR_WAIT;\n"
-      "MBAR_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap* map, u32 bar, int c0, int c1,
-                                            unsigned long long hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(u32 bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(u32 d_tmem, unsigned long long a_desc, unsigned long long b_desc,
-                                            u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// shared-memory matrix descriptor of a K-major tile with 128-byte swizzle: rows of 64 bf16
-// (128 B), groups of 8 rows 1024 B apart (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ unsigned long long umma_desc_sw128(u32 smem_addr) {
-  const u32 lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);              // start address, LBO = 1 (unused)
-  const u32 hi = (1024u >> 4) | (1u << 14) | (2u << 29);                  // SBO, version, SWIZZLE_128B
-  return ((unsigned long long)hi << 32) | lo;
-}
-// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread, complete on return
-__device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
-  u32 r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// v[j] for a run-time j: registers cannot be indexed, a dense switch becomes one indirect branch
-__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
-  switch (j) {
-#define CMR_PICK(i) case i: return v[i];
-    CMR_PICK(0) CMR_PICK(1) CMR_PICK(2) CMR_PICK(3) CMR_PICK(4) CMR_PICK(5) CMR_PICK(6) CMR_PICK(7)
-    CMR_PICK(8) CMR_PICK(9) CMR_PICK(10) CMR_PICK(11) CMR_PICK(12) CMR_PICK(13) CMR_PICK(14) CMR_PICK(15)
-    CMR_PICK(16) CMR_PICK(17) CMR_PICK(18) CMR_PICK(19) CMR_PICK(20) CMR_PICK(21) CMR_PICK(22) CMR_PICK(23)
-    CMR_PICK(24) CMR_PICK(25) CMR_PICK(26) CMR_PICK(27) CMR_PICK(28) CMR_PICK(29) CMR_PICK(30)
-#undef CMR_PICK
-    default: return v[31];
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // Work enumeration shared by the three warp roles.  An item is one (A block of 128 rows of
@@ -496,83 +405,12 @@ dense_finalize_cand_kernel(const u64* __restrict__ cand, const int* __restrict__
   u64* s_keys = reinterpret_cast<u64*>(smem_fin);  // [cap_total]
   u64* s_out = s_keys + cap_total;                 // [KP]
   double* s_score = reinterpret_cast<double*>(s_out + KP);
-  __shared__ int s_total, s_over;
-  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    s_total = 0;
-    s_over = 0;
-  }
-  for (int i = tid; i < KP; i += FIN_THREADS) s_out[i] = 0ull;
-  __syncthreads();
-  // one warp per CTA list: claim a range of the shared buffer, copy the keys
-  for (int l = warp; l < n_lists; l += FIN_THREADS / 32) {
-    const int have = cnt[(size_t)l * n_queries + qi];
-    if (have == 0) continue;  // warp-uniform
-    const int take = have < cap ? have : cap;
-    int base = 0;
-    if (lane == 0) {
-      base = atomicAdd(&s_total, take);
-      if (have > cap) s_over = 1;
-    }
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    const u64* src = cand + ((size_t)l * n_queries + qi) * cap;
-    for (int i = lane; i < take; i += 32) {
-      if (base + i < cap_total) s_keys[base + i] = src[i];
-      else s_over = 1;
-    }
-  }
-  __syncthreads();
-  const int m = s_total < cap_total ? s_total : cap_total;
-  __syncthreads();  // every thread has read s_total before it is reused as a counter below
-  // Ranking m keys against each other is quadratic, and only the KP best matter: find the
-  // KP-th largest score word by bisection (32 rounds of counting), then rank just the keys
-  // that reach it (the KP best plus ties of the last one).
-  u32 floor_word = 0;
-  if (m > 4 * KP) {
-    for (int bit = 31; bit >= 0; --bit) {
-      const u32 c = floor_word | (1u << bit);
-      int local = 0;
-      for (int e = tid; e < m; e += FIN_THREADS) local += (u32)(s_keys[e] >> 32) >= c;
-      local = __reduce_add_sync(0xFFFFFFFFu, local);
-      if (tid == 0) s_total = 0;
-      __syncthreads();
-      if (lane == 0 && local) atomicAdd(&s_total, local);
-      __syncthreads();
-      if (s_total >= KP) floor_word = c;
-      __syncthreads();
-    }
-  }
-  // survivors (score word >= floor) are compacted and ranked among themselves; with more than
-  // 4*KP of them (a crowd of ties at the boundary) every key is ranked against all m instead
   u64* s_surv = reinterpret_cast<u64*>(s_score + KP);   // [4 * KP]
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-  for (int e = tid; e < m; e += FIN_THREADS) {
-    const u64 key = s_keys[e];
-    if ((u32)(key >> 32) >= floor_word) {
-      const int slot = atomicAdd(&s_total, 1);
-      if (slot < 4 * KP) s_surv[slot] = key;
-    }
-  }
-  __syncthreads();
-  const int n_surv = s_total;
-  if (n_surv <= 4 * KP) {
-    for (int e = tid; e < n_surv; e += FIN_THREADS) {
-      const u64 key = s_surv[e];
-      int rank = 0;
-      for (int j = 0; j < n_surv; ++j) rank += s_surv[j] > key;
-      if (rank < KP) s_out[rank] = key;
-    }
-  } else {
-    for (int e = tid; e < m; e += FIN_THREADS) {
-      const u64 key = s_keys[e];
-      if ((u32)(key >> 32) < floor_word) continue;
-      int rank = 0;
-      for (int j = 0; j < m && rank < KP; ++j) rank += s_keys[j] > key;
-      if (rank < KP) s_out[rank] = key;
-    }
-  }
-  __syncthreads();
+  __shared__ int s_ctl[2];
+  const int qi = blockIdx.x;
+  int n_total, s_over;
+  cand_collect_select<KP>(cand, cnt, n_lists, n_queries, cap, cap_total, qi, s_keys, s_out, s_surv, s_ctl,
+                          &n_total, &s_over);
   dense_finalize_tail<KP>(s_out, s_score, emb, dim, queries + (size_t)qi * dim, row_offset, k, cert_eps,
                           s_over ? CMR_FLAG_UNCERTIFIED : 0, qi, out_scores, out_ids, out_counts, out_flags);
 }
@@ -594,9 +432,7 @@ static tmap_encode_fn tmap_encoder() {
   return fn;
 }
 
-// [n_rows, dim] bf16 row-major matrix, boxes of [box_rows, 64] columns, 128-byte swizzle,
-// out-of-bounds elements read as zero
-static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int dim, int box_rows) {
+int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int dim, int box_rows, bool f16) {
   tmap_encode_fn enc = tmap_encoder();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -606,7 +442,8 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long n_rows, int di
   const cuuint64_t gstr[1] = {(cuuint64_t)dim * 2};
   const cuuint32_t box[2] = {(cuuint32_t)MM_K, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  const CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(ptr), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -744,6 +581,23 @@ static int mma_opt_in() {
   return CMR_OK;
 }
 
+int launch_admission_bound(const float* gmax, int n_groups, int gstride, int kp, int n_queries, float* thr,
+                           cudaStream_t st) {
+  const int rc = mma_opt_in();
+  if (rc != CMR_OK) return rc;
+  if (n_groups > MM_MAX_GROUPS) {
+    set_error("admission bound: %d groups exceed %d", n_groups, MM_MAX_GROUPS);
+    return CMR_EUNSUPPORTED;
+  }
+  if (n_groups <= THR_WARP_MAX_GROUPS)
+    dense_thresh_warp_kernel<<<(n_queries + THR_WARPS - 1) / THR_WARPS, THR_WARPS * 32,
+                               (size_t)THR_WARPS * (n_groups > 0 ? n_groups : 1) * 4, st>>>(
+        gmax, n_groups, gstride, kp, n_queries, thr);
+  else
+    dense_thresh_kernel<<<n_queries, 256, (size_t)n_groups * 4, st>>>(gmax, n_groups, gstride, kp, thr);
+  return CMR_OK;
+}
+
 int dense_mma_topk(const DenseArgs& a) {
   MmaPlan p;
   const int sms = sm_count();
@@ -802,12 +656,8 @@ int dense_mma_topk(const DenseArgs& a) {
     kp.rows_evict_first = 0;
     dense_mma_kernel<MM_SAMPLE><<<grid, MM_THREADS, smem_bytes, a.stream>>>(tm_q, tm_rows, kp);
   }
-  if (p.n_groups <= THR_WARP_MAX_GROUPS)
-    dense_thresh_warp_kernel<<<(a.n_queries + THR_WARPS - 1) / THR_WARPS, THR_WARPS * 32,
-                               (size_t)THR_WARPS * (p.n_groups > 0 ? p.n_groups : 1) * 4, a.stream>>>(
-        gmax, p.n_groups, p.bpad, p.kp, a.n_queries, thr);
-  else
-    dense_thresh_kernel<<<a.n_queries, 256, (size_t)p.n_groups * 4, a.stream>>>(gmax, p.n_groups, p.bpad, p.kp, thr);
+  rc = launch_admission_bound(gmax, p.n_groups, p.bpad, p.kp, a.n_queries, thr, a.stream);
+  if (rc != CMR_OK) return rc;
   {
     const int grid = p.n_lists;
     kp.n_outer = p.n_tiles;

@@ -8,8 +8,13 @@ This is what HybridRetriever.retrieve (reference rag/retrieval/fusion.py:108-167
 drives per question; the engine exposes it batched and asynchronous on the
 current CUDA stream, optionally replayed from a CUDA graph so that one query is
 one graph launch.  On a row-sharded corpus (one process per GPU) the per-shard
-top-k lists are exchanged with one all-gather each and merged by
-cmr_topk_merge (classmate_rag_b200.sharding).
+dense pool and BM25 list are packed into ONE message per query, exchanged once (stores into
+every rank's receive buffer over NVLink + epoch flags, or an NCCL all-gather) and merged by
+cmr_shard_merge (classmate_rag_b200.sharding).
+
+Queries whose dense result could not be certified (CMR_FLAG_UNCERTIFIED) are reported in
+``HybridEngine.last_dense_flags``; GraphedSearch / PipelinedSearch read them back with the
+results and re-run such a batch on the exhaustive float64 scan before handing it out.
 """
 from __future__ import annotations
 
@@ -68,6 +73,8 @@ class HybridEngine:
         if overlap is None:
             overlap = os.environ.get("CMRAG_OVERLAP", "1") != "0"
         self.overlap = bool(overlap)
+        self.last_dense_flags = None
+        self.last_exchange_timeout = None
         self.bm25_first = os.environ.get("CMRAG_BM25_ORDER", "first") != "after"
         self._side = None
 
@@ -87,27 +94,27 @@ class HybridEngine:
                 return self.lexical_topk(q_terms, q_ptr, k, lex_mask)
         return launch, (lambda: cur.wait_stream(side))
 
-    def _dense_and_lexical(self, q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, k_bm25, lex_mask):
+    def _dense_and_lexical(self, q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, k_bm25, lex_mask, dense_algo="auto"):
         """The two retrievers of a step; BM25 on the side stream when overlap applies."""
         if not hybrid:
-            return self.dense_pool(q_bf16, pool, dense_mask), None, None
+            return self.dense_pool(q_bf16, pool, dense_mask, dense_algo), None, None
         if not (self.overlap and q_bf16.shape[0] > 8):
-            return self.dense_pool(q_bf16, pool, dense_mask), None, lambda: self.lexical_topk(q_terms, q_ptr, k_bm25, lex_mask)
+            return (self.dense_pool(q_bf16, pool, dense_mask, dense_algo), None,
+                    lambda: self.lexical_topk(q_terms, q_ptr, k_bm25, lex_mask))
         launch, join = self._fork_lexical(q_terms, q_ptr, k_bm25, lex_mask)
         if self.bm25_first:
             bm = launch()
-            dense = self.dense_pool(q_bf16, pool, dense_mask)
+            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo)
         else:
-            dense = self.dense_pool(q_bf16, pool, dense_mask)
+            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo)
             bm = launch()
         return dense, join, lambda: bm
 
     # -- stage helpers -------------------------------------------------------
     def _cert_eps(self, dim: int) -> float:
-        # |fp32 tensor-pipe score - exact| <= dim * 2^-22 * |q| * max|c| (conservative)
-        return dim * 2.0 ** -22 * 1.01 * self.max_row_norm
+        return ops.dense_cert_eps(dim, 1.0, self.max_row_norm)
 
-    def dense_pool(self, q_bf16: torch.Tensor, k: int, row_mask: Optional[torch.Tensor] = None):
+    def dense_pool(self, q_bf16: torch.Tensor, k: int, row_mask: Optional[torch.Tensor] = None, algo: str = "auto"):
         n, d = self.emb.shape
         b = q_bf16.shape[0]
         key = (n, d, b, k)
@@ -115,7 +122,7 @@ class HybridEngine:
         if ws is None:
             ws = self._dense_ws[key] = ops.DenseWorkspace(n, d, b, k, self.device)
         out = ops.dense_topk(self.emb, q_bf16, k, row_mask=row_mask, row_offset=self.row_offset,
-                             cert_eps=self._cert_eps(d), workspace=ws)
+                             cert_eps=self._cert_eps(d), workspace=ws, algo=algo)
         if self.comm is not None:
             out = self.comm.merge_topk(*out)
         return out
@@ -149,11 +156,15 @@ class HybridEngine:
     # -- the hot path --------------------------------------------------------
     def search(self, q_bf16: torch.Tensor, q_terms: Optional[torch.Tensor], q_ptr: Optional[torch.Tensor],
                p: SearchParams, *, dense_mask: Optional[torch.Tensor] = None,
-               lex_mask: Optional[torch.Tensor] = None, stage_events: Optional[list] = None):
+               lex_mask: Optional[torch.Tensor] = None, stage_events: Optional[list] = None,
+               dense_algo: str = "auto"):
         """Returns device tensors (ids i64 [B,top_k], fused f64, vector_distance f64
         (NaN = None), bm25_score f64 (NaN = None), counts i32 [B]); nothing is
-        synchronised.  ``stage_events``: a list that receives timing events at the stage
-        boundaries (start, dense done, MMR done, BM25 done, fused) -- single-shard path only."""
+        synchronised.  ``self.last_dense_flags`` (int32 [B], device) is non-zero for queries
+        whose dense pool could not be certified: re-run those with ``dense_algo="exact"`` (the
+        exhaustive float64 scan; GraphedSearch.result() does).  ``stage_events``: a list that
+        receives timing events at the stage boundaries (start, dense done, MMR done, BM25
+        done, fused) -- single-shard path only."""
         def mark():
             if stage_events is not None:
                 e = torch.cuda.Event(enable_timing=True)
@@ -166,10 +177,10 @@ class HybridEngine:
         pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
         pool = min(pool, 64) if p.use_mmr else pool
         if self.comm is not None:
-            return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask)
+            return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo)
         mark()
         (scores, ids, counts, flags), join, lexical = self._dense_and_lexical(
-            q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, p.k_bm25, lex_mask)
+            q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, p.k_bm25, lex_mask, dense_algo)
         self.last_dense_flags = flags
         mark()
         if p.use_mmr:
@@ -191,13 +202,13 @@ class HybridEngine:
         return out
 
 
-    def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask):
+    def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo="auto"):
         """Row-sharded step with ONE collective: local dense pool + local BM25 list ->
         cmr_shard_pack -> all-gather -> cmr_shard_merge -> MMR -> fuse."""
         comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
         try:
             dense, join, lexical = self._dense_and_lexical(q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr,
-                                                           p.k_bm25, lex_mask)
+                                                           p.k_bm25, lex_mask, dense_algo)
             bm_local = None
             if hybrid:
                 if join is not None:
@@ -216,6 +227,7 @@ class HybridEngine:
                                     row_offset=self.row_offset)
             d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_exchange_merge(
                 peer.recv, peer.flags, peer.struct, peer.timeout, b, pool, kb, dim)
+            self.last_exchange_timeout = peer.timeout   # int32 [1], device: non-zero = a rank never arrived
         else:
             msg = ops.shard_pack(dense, bm_local, self.emb if p.use_mmr else None, row_offset=self.row_offset)
             gathered = comm.all_gather_bytes(msg)
@@ -280,6 +292,12 @@ class GraphedSearch:
                 self.graph = g
                 self._peer_generation = getattr(self.engine.comm, "peer_generation", 0)
             ids, fused, vd, bm, cnt = self.out
+            # dense certificate flags (+ the peer exchange's timeout word) travel with the results
+            self.flags = self.engine.last_dense_flags
+            self.timeout = self.engine.last_exchange_timeout
+            self.h_flags = torch.zeros(self.flags.shape, dtype=self.flags.dtype).pin_memory()
+            self.h_timeout = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self.reruns = 0
             self.h_ids = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
             self.h_fused = torch.empty(fused.shape, dtype=fused.dtype).pin_memory()
             self.h_vd = torch.empty(vd.shape, dtype=vd.dtype).pin_memory()
@@ -295,7 +313,8 @@ class GraphedSearch:
 
     @property
     def d2h_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt))
+        return sum(t.numel() * t.element_size() for t in (self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt,
+                                                          self.h_flags))
 
     def set_queries(self, q_f32: np.ndarray, term_lists: Optional[Sequence[Sequence[int]]]):
         """Stage host inputs into the pinned buffers (not part of the device work)."""
@@ -330,7 +349,30 @@ class GraphedSearch:
             self.h_vd.copy_(vd, non_blocking=True)
             self.h_bm.copy_(bm, non_blocking=True)
             self.h_cnt.copy_(cnt, non_blocking=True)
+            self.h_flags.copy_(self.flags, non_blocking=True)
+            if self.timeout is not None:
+                self.h_timeout.copy_(self.timeout, non_blocking=True)
             self.done.record(self.stream)
+
+    def _copy_out(self, out):
+        for h, t in zip((self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt), out):
+            h.copy_(t, non_blocking=True)
+
+    def _rerun_exact(self):
+        """A query of the batch could not be certified by the fp32 pass (thousands of exact
+        duplicates around rank k): the batch is run again, eagerly, with the exhaustive float64
+        scan as the dense stage (same inputs -- they are still in the static buffers -- same
+        exchange on every rank, since the merged flags are identical everywhere)."""
+        self.reruns += 1
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            q_bf16 = ops.f32_to_bf16(self.q_f32)
+            out = self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
+                                     self.q_ptr if self.hybrid else None, self.p, dense_algo="exact")
+            self._copy_out(out)
+            self.h_flags.copy_(self.engine.last_dense_flags, non_blocking=True)
+            self.stream.synchronize()
+        if int(self.h_flags.sum()) != 0:
+            raise RuntimeError("the exhaustive dense scan returned an uncertified result")
 
     def launch_resident(self, q_f32: torch.Tensor, q_terms: Optional[torch.Tensor] = None,
                         q_ptr: Optional[torch.Tensor] = None):
@@ -363,8 +405,14 @@ class GraphedSearch:
         return self.out
 
     def result(self):
-        """Wait for the last launch() of THIS object and hand back its pinned result buffers."""
+        """Wait for the last launch() of THIS object and hand back its pinned result buffers.
+        Fails loudly when a rank never arrived at the peer exchange; re-runs the batch on the
+        exhaustive scan when the dense certificate failed for one of its queries."""
         self.done.synchronize()
+        if int(self.h_timeout[0]) != 0:
+            raise RuntimeError("shard exchange timed out: a rank did not deliver its message (results are invalid)")
+        if int(self.h_flags.sum()) != 0:
+            self._rerun_exact()
         return self.h_ids.numpy(), self.h_fused.numpy(), self.h_vd.numpy(), self.h_bm.numpy(), self.h_cnt.numpy()
 
     def __call__(self, q_f32: np.ndarray, term_lists=None):

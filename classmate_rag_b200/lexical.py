@@ -23,6 +23,7 @@ BM25_EPS = 0.25
 DEFAULT_TILE_DOCS = 2048   # 16 documents per thread of a 128-thread CTA (csrc/bm25.cu)
 DENSE_DENSITY = 0.125    # terms in at least this share of the documents get a factor column
 DENSE_MAX_TERMS = 64     # 8 B x n_docs each
+HEAD_TERMS = 64          # columns of the fp16 head matrix (one 128-byte row per document; csrc/bm25_mma.cu)
 
 
 class LexIndexStruct(C.Structure):
@@ -31,8 +32,9 @@ class LexIndexStruct(C.Structure):
         ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_pack", C.c_void_p), ("imp_table", C.c_void_p),
         ("post_doc", C.c_void_p), ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p),
         ("idf", C.c_void_p), ("dense_imp", C.c_void_p), ("dense_slot", C.c_void_p),
+        ("head_mat", C.c_void_p), ("head_slot", C.c_void_p),
         ("n_docs", C.c_int64), ("n_terms", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
-        ("n_codes", C.c_int32), ("n_dense", C.c_int32), ("reserved_", C.c_int32),
+        ("n_codes", C.c_int32), ("n_dense", C.c_int32), ("n_head", C.c_int32),
         ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
     ]
 
@@ -79,6 +81,9 @@ class LexicalIndex:
     dense_imp: Optional[torch.Tensor] = None   # float64 [n_dense, N]: factor column of each dense term
     dense_slot: Optional[torch.Tensor] = None  # int32 [V]: column of the term or -1
     dense_terms: Optional[np.ndarray] = field(default=None, repr=False)  # term id of each column
+    head_mat: Optional[torch.Tensor] = None    # float16 [N, 64]: fp16(idf * factor) of the head terms, 0 where absent
+    head_slot: Optional[torch.Tensor] = None   # int32 [V]: column of the term in head_mat or -1
+    head_terms: Optional[np.ndarray] = field(default=None, repr=False)   # term id of each head column
     idf_host: np.ndarray = field(default=None, repr=False)
     df_host: np.ndarray = field(default=None, repr=False)        # corpus-wide df
     shard_df_host: np.ndarray = field(default=None, repr=False)  # postings per term in THIS shard
@@ -99,9 +104,11 @@ class LexicalIndex:
                 self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), opt(self.post_pack), opt(self.imp_table),
                 self.post_doc.data_ptr(), opt(self.post_imp), self.post_tf.data_ptr(), self.doc_len.data_ptr(),
                 self.idf.data_ptr(), opt(self.dense_imp), opt(self.dense_slot),
+                opt(self.head_mat), opt(self.head_slot),
                 self.n_docs, self.n_terms, self.tile_docs, self.n_tiles,
                 0 if self.imp_table is None else int(self.imp_table.numel()),
-                0 if self.dense_imp is None else int(self.dense_imp.shape[0]), 0, self.avgdl, self.k1, self.b)
+                0 if self.dense_imp is None else int(self.dense_imp.shape[0]),
+                0 if self.head_terms is None else int(len(self.head_terms)), self.avgdl, self.k1, self.b)
         return self._struct
 
     def posting_bytes(self, terms: Sequence[int]) -> int:
@@ -160,13 +167,15 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
                         stats: Optional[GlobalStats] = None, fmt: str = "auto",
                         k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS,
                         dense_density: Optional[float] = DENSE_DENSITY,
-                        dense_max_terms: int = DENSE_MAX_TERMS) -> LexicalIndex:
+                        dense_max_terms: int = DENSE_MAX_TERMS, head_terms: int = HEAD_TERMS) -> LexicalIndex:
     """Build the CSR index of the documents ``tokens[doc_ptr[i]:doc_ptr[i+1]]``.
 
     ``stats`` (optional) supplies corpus-wide df / N / total tokens when this
     call builds one shard of a larger corpus.  ``dense_density`` (None = off):
     terms present in at least that share of the documents also get a dense
-    float64 factor column, swept instead of scattered by the kernel."""
+    float64 factor column, swept instead of scattered by the kernel.  ``head_terms`` (0 = off):
+    the terms with the longest posting lists in this shard, at most 64, get a column of the fp16
+    head matrix the batched kernels score on the tensor cores (packed postings only)."""
     if device is None:
         device = tokens.device
     doc_ptr = doc_ptr.to(device).long()
@@ -248,6 +257,24 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
                 else:
                     f_t = imp[a:z]
                 dense_imp[c, d_t] = f_t
+    # head terms: fp16(idf * factor) columns of a [n_docs, 64] matrix (cmr_lex_index.head_mat)
+    head_mat = head_slot = head_ids = None
+    if head_terms and post_pack is not None and total > 0 and n_docs > 0:
+        if not 0 < head_terms <= HEAD_TERMS:
+            raise ValueError(f"head_terms must be in 0..{HEAD_TERMS}")
+        shard_df = (term_ptr[1:] - term_ptr[:-1])
+        top = torch.argsort(shard_df, descending=True, stable=True)[:head_terms]
+        top = top[shard_df[top] > 0].sort().values
+        if top.numel() > 0:
+            head_ids = top.cpu().numpy()
+            head_mat = torch.zeros((n_docs, HEAD_TERMS), dtype=torch.float16, device=device)
+            hs = torch.full((n_terms,), -1, dtype=torch.int32, device=device)
+            hs[top] = torch.arange(top.numel(), dtype=torch.int32, device=device)
+            head_slot = hs
+            for c, t in enumerate(head_ids.tolist()):
+                a, z = int(term_ptr[t]), int(term_ptr[t + 1])
+                f_t = imp_table[((post_pack[a:z].long() >> 16) & 0xFFFF)]
+                head_mat[doc[a:z], c] = (float(idf_host[t]) * f_t).to(torch.float16)
     tf32 = counts.clamp(max=65535).to(torch.int32)
     tf16 = torch.where(tf32 >= 32768, tf32 - 65536, tf32).to(torch.int16)
     return LexicalIndex(
@@ -255,6 +282,7 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
         post_doc=doc.to(torch.int32).contiguous(), post_imp=None if imp is None else imp.contiguous(),
         post_pack=post_pack, imp_table=imp_table, pair_tf=pair_tf, pair_dl=pair_dl,
         dense_imp=dense_imp, dense_slot=dense_slot, dense_terms=dense_terms,
+        head_mat=head_mat, head_slot=head_slot, head_terms=head_ids,
         post_tf=tf16.contiguous(), doc_len=doc_len.to(torch.int32).contiguous(),
         idf=torch.from_numpy(idf_host).to(device), n_docs=n_docs, n_terms=n_terms, tile_docs=tile_docs,
         n_tiles=n_tiles, avgdl=float(avgdl), k1=k1, b=b, idf_host=idf_host, df_host=stats.df,
@@ -277,7 +305,7 @@ def pack_queries(queries: Sequence[Sequence[int]]):
 # BM25Okapi rebuild of the reference, rag/retrieval/bm25.py:220-248, rag/pipeline/rag.py:532)
 # --------------------------------------------------------------------------
 _SNAPSHOT_TENSORS = ("term_ptr", "tile_skip", "post_doc", "post_imp", "post_tf", "doc_len", "idf", "post_pack",
-                     "imp_table", "pair_tf", "pair_dl", "dense_imp", "dense_slot")
+                     "imp_table", "pair_tf", "pair_dl", "dense_imp", "dense_slot", "head_mat", "head_slot")
 _SNAPSHOT_VERSION = 1
 
 
@@ -293,7 +321,7 @@ def save_lexical_index(ix: LexicalIndex, path) -> None:
         if t is not None:
             np.save(path / f"{name}.npy", t.detach().cpu().numpy())
             present.append(name)
-    for name in ("idf_host", "df_host", "shard_df_host", "dense_terms"):
+    for name in ("idf_host", "df_host", "shard_df_host", "dense_terms", "head_terms"):
         a = getattr(ix, name)
         if a is not None:
             np.save(path / f"{name}.npy", np.asarray(a))

@@ -66,6 +66,13 @@ class DenseWorkspace:
         self.flags = torch.empty((n_queries,), dtype=torch.int32, device=device)
 
 
+def dense_cert_eps(dim: int, q_norm: float = 1.0, max_row_norm: float = 1.0) -> float:
+    """The one bound every caller of the fp32 tensor-pipe scores uses:
+    |fp32 score - exact| <= dim * 2^-22 * |q| * max|c| (accumulation on the tensor pipe is not
+    round-to-nearest, so 2^-24 per addition would not be a bound), with 1 % slack."""
+    return dim * 2.0 ** -22 * 1.01 * float(q_norm) * float(max_row_norm)
+
+
 def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Optional[torch.Tensor] = None,
                row_offset: int = 0, cert_eps: Optional[float] = None,
                workspace: Optional[DenseWorkspace] = None, algo: str = "auto"):
@@ -91,8 +98,8 @@ def dense_topk(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Op
         _require_cuda(row_mask, "row_mask")
         if row_mask.dtype != torch.uint8 or row_mask.numel() != n_rows:
             raise ValueError("row_mask must be uint8 [n_rows]")
-    if cert_eps is None:
-        cert_eps = dim * 2.0 ** -24 * 1.02
+    if cert_eps is None:   # unit rows and queries (the E5 contract); other callers pass their norms' bound
+        cert_eps = dense_cert_eps(dim)
     if workspace is None or workspace.key != (n_rows, dim, b, k):
         workspace = DenseWorkspace(n_rows, dim, b, k, emb.device)
     lib = _lib.load()
@@ -117,12 +124,20 @@ class TopkBuffers:
         self.flags = torch.empty((n_queries,), dtype=torch.int32, device=device)
 
 
+_BM25_ALGO = {"auto": _lib.CMR_BM25_AUTO, "exact": _lib.CMR_BM25_EXACT, "head": _lib.CMR_BM25_HEAD,
+              "head_nofallback": _lib.CMR_BM25_HEAD_NOFALLBACK}
+
+
 def bm25_topk(index, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int, *,
               row_mask: Optional[torch.Tensor] = None, row_offset: int = 0,
-              buffers: Optional[TopkBuffers] = None):
+              buffers: Optional[TopkBuffers] = None, algo: str = "auto"):
     """Exact BM25 top-k for a batch of tokenised queries (device tensors:
     q_terms int32, q_ptr int32 [B+1]).  Returns (scores f64 [B,k], ids i64 [B,k],
-    counts, flags) on the device, enqueued on the current stream."""
+    counts, flags) on the device, enqueued on the current stream.
+
+    algo: "auto" | "exact" (per-query float64 tile kernel) | "head" (head-term matrix on the
+    tensor cores + bucketed sparse postings + exact rescoring, flagged queries re-run by the
+    exact kernel) | "head_nofallback" (flags left for the caller); see cmr_bm25_topk_ex."""
     import ctypes as C
     for name, t in (("q_terms", q_terms), ("q_ptr", q_ptr)):
         _require_cuda(t, name)
@@ -141,10 +156,10 @@ def bm25_topk(index, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int, *,
             if nbytes == 0:
                 raise ValueError(f"unsupported bm25 shape B={b} k={k}: " + _lib.last_error())
             buffers = TopkBuffers(b, k, nbytes, index.device)
-        rc = lib.cmr_bm25_topk(C.byref(st), q_terms.data_ptr(), q_ptr.data_ptr(), b, k,
-                               _ptr(row_mask), row_offset, buffers.scores.data_ptr(), buffers.ids.data_ptr(),
-                               buffers.counts.data_ptr(), buffers.flags.data_ptr(), buffers.ws.data_ptr(),
-                               buffers.ws.numel(), _stream())
+        rc = lib.cmr_bm25_topk_ex(C.byref(st), q_terms.data_ptr(), q_ptr.data_ptr(), b, k,
+                                  _ptr(row_mask), row_offset, buffers.scores.data_ptr(), buffers.ids.data_ptr(),
+                                  buffers.counts.data_ptr(), buffers.flags.data_ptr(), buffers.ws.data_ptr(),
+                                  buffers.ws.numel(), _stream(), _BM25_ALGO[algo])
     _lib.check(rc)
     return buffers.scores, buffers.ids, buffers.counts, buffers.flags
 

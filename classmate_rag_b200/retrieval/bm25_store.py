@@ -85,13 +85,18 @@ class BM25Store:
     _dev_tokens: Optional[Tuple[torch.Tensor, torch.Tensor, np.ndarray]] = field(default=None, repr=False)
     _gids: Optional[torch.Tensor] = field(default=None, repr=False)
     loaded_from_snapshot: bool = field(default=False, repr=False)
+    _snapshot_ok: bool = field(default=False, repr=False)   # entries came straight from load(): the sidecar may describe them
     device_tokenize_from: int = 64          # batches of at least this many queries are tokenised on the device
     _tokenizer: Any = field(default=None, repr=False)
 
     # ---------- core ops ----------
-    def _rebuild(self) -> None:
+    def _rebuild(self, from_disk: bool = False) -> None:
         """Reference: rebuild BM25Okapi from the token lists after every mutation.  Here the
-        id order is refreshed at once and the device index lazily, on the next search."""
+        id order is refreshed at once and the device index lazily, on the next search.
+        ``from_disk``: the entries are exactly what load() read from the JSONL file -- only
+        then may the binary sidecar stand in for a rebuild (an upsert that replaces an id or a
+        delete + upsert leaves the file stamp and the entry count unchanged)."""
+        self._snapshot_ok = bool(from_disk)
         self._id_list = list(self._entries.keys())
         self._dirty = True
         self._full = None
@@ -105,7 +110,7 @@ class BM25Store:
         if not torch.cuda.is_available():
             raise RuntimeError("BM25Store needs a CUDA device: classmate_rag_b200 has no CPU path")
         dev = torch.device(self.device)
-        if self._load_snapshot(dev):
+        if self._snapshot_ok and self._load_snapshot(dev):
             return
         vocab = self._vocab
         lens = np.zeros(len(self._id_list), dtype=np.int64)
@@ -329,7 +334,7 @@ class BM25Store:
                     self._entries[rec["id"]] = _Entry(id=rec["id"], text=rec.get("text", ""),
                                                       tokens=list(rec.get("tokens", [])),
                                                       metadata=dict(rec.get("metadata", {})))
-        self._rebuild()
+        self._rebuild(from_disk=True)
 
     def catalog(self) -> Dict[str, Tuple[str, Dict[str, Any]]]:
         """id -> (text, metadata): what expand_with_neighbors reads from the JSONL file."""

@@ -8,13 +8,22 @@ top-k, not an approximation.  Rows live in HBM as one bf16 ``[rows, dim]`` matri
 insertion order; ids, documents and metadata stay on the host.
 
 distance = 1 - q.c ("cosine" space on unit vectors: the reference always stores and
-queries L2-normalised E5 output, rag/embeddings/__init__.py:85-105).  Ties are broken by
-insertion order.
+queries L2-normalised E5 output, rag/embeddings/__init__.py:85-105).  Like hnswlib's cosine
+space, rows and queries that are NOT unit length (norm off by more than 1e-3, e.g. an embedder
+run with normalize=False) are L2-normalised on the way in; unit input is left bit for bit as
+it is, so the bf16 matrix equals the oracle's.  Ties are broken by insertion order.
+
+Durability follows the reference's ``chromadb.PersistentClient``: every upsert / delete is
+appended to ``<persist_dir>/<collection>.cmrag/`` (raw bf16 rows + one JSON line per
+operation) before the call returns, so a later process finds what an earlier one ingested
+without anyone calling ``persist()`` (rag/pipeline/rag.py:411-413 never does).  ``persist()``
+/ ``compact()`` rewrite the directory without tombstones, atomically (temp dir + rename).
 """
 from __future__ import annotations
 
 import json
 import os
+import shutil
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Any, Dict, List, Mapping, Optional, Sequence
@@ -46,6 +55,8 @@ class _Collection:
         self.n_dead = 0
         self.columns = MetaColumns(self.device)
         self.version = 0
+        self.max_row_norm = 1.0       # largest |row| of the bf16 matrix (certificate bound)
+        self.log_dir: Optional[Path] = None   # append-only operation log (None: in-memory collection)
         self._ws: Dict[tuple, ops.DenseWorkspace] = {}
 
     def workspace(self, n_queries: int, k: int) -> "ops.DenseWorkspace":
@@ -78,22 +89,33 @@ class _Collection:
                 new[: self.n_rows] = old[: self.n_rows]
                 setattr(self, name, new)
 
-    def delete(self, ids: Sequence[str]) -> int:
-        rows = [self.row_of.pop(i) for i in ids if i in self.row_of]
+    def delete(self, ids: Sequence[str], log: bool = True) -> int:
+        gone = [i for i in ids if i in self.row_of]
+        rows = [self.row_of.pop(i) for i in gone]
         if rows:
             self.alive[torch.tensor(rows, dtype=torch.int64, device=self.device)] = 0
             self.n_dead += len(rows)
             self.version += 1
+            if log and self.log_dir is not None:
+                _log_append(self.log_dir, self.dim, None, [{"delete": gone}])
         return len(rows)
 
-    def add(self, ids, documents, metadatas, emb_f32: np.ndarray) -> None:
+    def add(self, ids, documents, metadatas, emb_f32: np.ndarray, log: bool = True, bits: Optional[torch.Tensor] = None) -> None:
         n = len(ids)
         if n == 0:
             return
-        self._reserve(n, int(emb_f32.shape[1]))
         lo = self.n_rows
-        x = torch.from_numpy(np.ascontiguousarray(emb_f32, dtype=np.float32)).to(self.device)
-        self.emb[lo:lo + n] = ops.f32_to_bf16(x)
+        if bits is None:
+            self._reserve(n, int(emb_f32.shape[1]))
+            x = unit_rows(torch.from_numpy(np.ascontiguousarray(emb_f32, dtype=np.float32)).to(self.device))
+            bits = ops.f32_to_bf16(x)
+        else:
+            self._reserve(n, int(bits.shape[1]))
+        self.emb[lo:lo + n] = bits
+        self.max_row_norm = max(self.max_row_norm, float(bits.float().norm(dim=1).max()))
+        if log and self.log_dir is not None:
+            _log_append(self.log_dir, self.dim, bits,
+                        [{"id": i, "document": d, "metadata": dict(m or {})} for i, d, m in zip(ids, documents, metadatas)])
         self.alive[lo:lo + n] = 1
         self.gids[lo:lo + n] = torch.tensor([REGISTRY.intern(i) for i in ids], dtype=torch.int64, device=self.device)
         for j, cid in enumerate(ids):
@@ -135,6 +157,10 @@ class _Collection:
             return None
         return self.columns.mask(clauses, alive=self.alive[: self.n_rows])
 
+    def cert_eps(self, q_bf16: torch.Tensor) -> float:
+        """Bound on |fp32 tensor-pipe score - exact| for these queries against this matrix."""
+        return ops.dense_cert_eps(self.dim, float(q_bf16.float().norm(dim=-1).max()), self.max_row_norm)
+
     def algo_for(self, mask: Optional[torch.Tensor]) -> str:
         """A very selective filter is served best by the exhaustive float64 scan, which only
         reads the allowed rows; otherwise the library picks scan / tcgen05 by batch size."""
@@ -166,20 +192,20 @@ class ChromaVectorStore:
             col = _COLLECTIONS.get(self._key())
             if col is None:
                 col = _COLLECTIONS[self._key()] = _Collection(self.device)
-                snap = Path(self.persist_dir) / f"{self.collection_name}.cmrag"
+                snap = self._snap_dir()
                 if snap.exists():
                     _load_snapshot(col, snap)
+                col.log_dir = snap
             self._collection = col
         return self._collection
+
+    def _snap_dir(self) -> Path:
+        return Path(self.persist_dir) / f"{self.collection_name}.cmrag"
 
     def reset_collection(self) -> None:
         _COLLECTIONS.pop(self._key(), None)
         self._collection = None
-        snap = Path(self.persist_dir) / f"{self.collection_name}.cmrag"
-        if snap.exists():
-            for f in snap.iterdir():
-                f.unlink()
-            snap.rmdir()
+        shutil.rmtree(self._snap_dir(), ignore_errors=True)
         self._ensure_collection()
 
     @classmethod
@@ -218,7 +244,8 @@ class ChromaVectorStore:
         return self._ensure_collection().delete(list(ids))
 
     def compact(self) -> None:
-        self._ensure_collection().compact()
+        """Drop tombstoned rows from the matrix and from the directory on disk."""
+        self.persist()
 
     def dedupe(self, threshold: float = 0.95) -> List[str]:
         """Near-duplicate filter over the stored embeddings (the `rag rebuild` hook,
@@ -247,14 +274,14 @@ class ChromaVectorStore:
             return col, None
         if q_f32.shape[1] != col.dim:
             raise ValueError(f"query dimension {q_f32.shape[1]} does not match the collection's {col.dim}")
-        q = ops.f32_to_bf16(torch.from_numpy(np.ascontiguousarray(q_f32)).to(col.device))
+        q = ops.f32_to_bf16(unit_rows(torch.from_numpy(np.ascontiguousarray(q_f32)).to(col.device)))
         mask = col.mask(where)
         k = min(int(top_k), ops_max_k())
         if k <= 0:
             raise ValueError("top_k must be positive")
         # flagged (uncertifiable) queries are re-run on the exhaustive float64 scan
         out = ops.dense_topk_certified(col.matrix(), q, k, row_mask=mask, workspace=col.workspace(q.shape[0], k),
-                                       algo=col.algo_for(mask))
+                                       algo=col.algo_for(mask), cert_eps=col.cert_eps(q))
         return col, out
 
     def query(self, *, query_embeddings: np.ndarray, where: Optional[Dict[str, Any]] = None, top_k: int = 8,
@@ -294,18 +321,53 @@ class ChromaVectorStore:
             result.append(items)
         return result
 
-    # ---- persistence (the Chroma directory of the reference becomes a binary snapshot) -----
+    # ---- persistence (the Chroma directory of the reference becomes a binary operation log) -----
     def persist(self) -> Path:
+        """Rewrite the collection's directory without tombstones: a temp directory is written in
+        full and then renamed over the old one, so a crash leaves either the old or the new state."""
         col = self._ensure_collection()
         col.compact()
-        snap = Path(self.persist_dir) / f"{self.collection_name}.cmrag"
-        snap.mkdir(parents=True, exist_ok=True)
-        bits = col.matrix().contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
-        np.save(snap / "embeddings_bf16.npy", bits)
-        with (snap / "records.jsonl").open("w", encoding="utf-8") as f:
-            for cid, doc, meta in zip(col.ids, col.documents, col.metadatas):
-                f.write(json.dumps({"id": cid, "document": doc, "metadata": meta}, ensure_ascii=False) + "\n")
+        snap = self._snap_dir()
+        tmp = snap.with_name(snap.name + ".tmp")
+        old = snap.with_name(snap.name + ".old")
+        shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(old, ignore_errors=True)
+        if col.n_rows:
+            _log_append(tmp, col.dim, col.matrix().contiguous(),
+                        [{"id": cid, "document": doc, "metadata": meta}
+                         for cid, doc, meta in zip(col.ids, col.documents, col.metadatas)])
+        else:
+            tmp.mkdir(parents=True, exist_ok=True)
+        if snap.exists():
+            os.replace(snap, old)
+        os.replace(tmp, snap)
+        shutil.rmtree(old, ignore_errors=True)
         return snap
+
+
+def unit_rows(x: torch.Tensor) -> torch.Tensor:
+    """hnswlib's cosine space normalises what it is given.  Rows whose norm is off by more than
+    1e-3 are divided by it; unit rows (the E5 contract) pass through untouched, zero rows stay."""
+    norms = x.norm(dim=1, keepdim=True)
+    off = ((norms - 1.0).abs() > 1e-3) & (norms > 0)
+    if bool(off.any()):
+        x = torch.where(off, x / norms.clamp(min=1e-30), x)
+    return x
+
+
+def _log_append(snap: Path, dim: int, bits: Optional[torch.Tensor], records: List[Dict[str, Any]]) -> None:
+    """Append rows (raw little-endian bf16, [n, dim]) and their records to the operation log;
+    the rows are written first, so a record line always has its row."""
+    snap.mkdir(parents=True, exist_ok=True)
+    meta = snap / "meta.json"
+    if not meta.exists():
+        meta.write_text(json.dumps({"version": 2, "dim": int(dim)}))
+    if bits is not None:
+        with (snap / "rows.bf16").open("ab") as f:
+            f.write(bits.contiguous().view(torch.int16).cpu().numpy().tobytes())
+    with (snap / "records.jsonl").open("a", encoding="utf-8") as f:
+        for rec in records:
+            f.write(json.dumps(rec, ensure_ascii=False) + "\n")
 
 
 def ops_max_k() -> int:
@@ -314,25 +376,41 @@ def ops_max_k() -> int:
 
 
 def _load_snapshot(col: _Collection, snap: Path) -> None:
-    bits = np.load(snap / "embeddings_bf16.npy")
-    ids, docs, metas = [], [], []
-    with (snap / "records.jsonl").open("r", encoding="utf-8") as f:
-        for line in f:
-            if line.strip():
-                rec = json.loads(line)
-                ids.append(rec["id"])
-                docs.append(rec.get("document"))
-                metas.append(rec.get("metadata") or {})
-    if len(ids) != bits.shape[0]:
-        raise RuntimeError(f"corrupt snapshot {snap}: {len(ids)} records, {bits.shape[0]} rows")
-    if not ids:
+    """Replay the operation log (version 2) or read a round-1 snapshot (embeddings_bf16.npy)."""
+    ops_log: List[Dict[str, Any]] = []
+    rec_path = snap / "records.jsonl"
+    if rec_path.exists():
+        with rec_path.open("r", encoding="utf-8") as f:
+            for line in f:
+                if line.strip():
+                    try:
+                        ops_log.append(json.loads(line))
+                    except json.JSONDecodeError:
+                        break       # a torn last line: everything before it is intact
+    if (snap / "meta.json").exists():
+        dim = int(json.loads((snap / "meta.json").read_text())["dim"])
+        raw = np.fromfile(snap / "rows.bf16", dtype=np.uint16) if (snap / "rows.bf16").exists() else np.zeros(0, np.uint16)
+        bits = raw[: raw.size // max(dim, 1) * max(dim, 1)].reshape(-1, max(dim, 1))
+    elif (snap / "embeddings_bf16.npy").exists():
+        bits = np.load(snap / "embeddings_bf16.npy")
+    else:
         return
-    col._reserve(len(ids), int(bits.shape[1]))
-    col.emb[: len(ids)] = torch.from_numpy(bits.view(np.int16)).to(col.device).view(torch.bfloat16)
-    col.alive[: len(ids)] = 1
-    col.gids[: len(ids)] = torch.tensor([REGISTRY.intern(i) for i in ids], dtype=torch.int64, device=col.device)
-    col.ids, col.documents, col.metadatas = ids, docs, metas
-    col.row_of = {cid: r for r, cid in enumerate(ids)}
-    col.n_rows = len(ids)
-    col.columns.reset(col.metadatas)
-    col.version += 1
+    n_adds = sum(1 for r in ops_log if "delete" not in r)
+    if n_adds > bits.shape[0]:
+        raise RuntimeError(f"corrupt snapshot {snap}: {n_adds} records, {bits.shape[0]} rows")
+    row, i = 0, 0
+    while i < len(ops_log):   # runs of adds go to the device in one copy
+        if "delete" in ops_log[i]:
+            col.delete(list(ops_log[i]["delete"]), log=False)
+            i += 1
+            continue
+        j = i
+        while j < len(ops_log) and "delete" not in ops_log[j]:
+            j += 1
+        run = ops_log[i:j]
+        ids = [r["id"] for r in run]
+        col.delete(ids, log=False)   # delete-then-add, as upsert does
+        chunk = torch.from_numpy(bits[row:row + len(run)].view(np.int16).copy()).to(col.device).view(torch.bfloat16)
+        col.add(ids, [r.get("document") for r in run], [r.get("metadata") or {} for r in run], None, log=False, bits=chunk)
+        row += len(run)
+        i = j

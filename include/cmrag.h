@@ -9,8 +9,7 @@
  * Conventions
  *   - Every pointer marked "device" is CUDA device memory owned by the caller
  *     (the library never allocates or frees caller tensors).  Work is enqueued
- *     on `stream` (a cudaStream_t) and NOT synchronised, except the *_host
- *     entry points, which copy from/to host buffers and synchronise.
+ *     on `stream` (a cudaStream_t) and NOT synchronised.
  *   - Row ids handed back are GLOBAL: local row + row_offset of the shard.
  *   - Ranking order everywhere: score descending, then row id ascending
  *     (reference: stable sorted(reverse=True) over insertion order,
@@ -66,7 +65,8 @@ int cmr_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   out_counts device, int32   [n_queries]     valid entries per query
  *   out_flags  device, int32   [n_queries]
  *   cert_eps   absolute bound on |fp32 score - exact score| used by the
- *              certificate (host passes dim * 2^-24 * |q| * max row norm)
+ *              certificate (host passes dim * 2^-22 * |q| * max row norm: tensor-pipe
+ *              accumulation is not round-to-nearest, so 2^-24 per add is not a bound)
  * ---------------------------------------------------------------------- */
 size_t cmr_dense_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k);
 
@@ -146,13 +146,20 @@ typedef struct cmr_lex_index {
    * arrays still hold their postings (filtered scoring, statistics).                    */
   const double* dense_imp;   /* [n_dense, n_docs] or NULL                               */
   const int32_t* dense_slot; /* [n_terms] column of the term in dense_imp, -1 = sparse; NULL when n_dense == 0 */
+  /* head terms (optional; the batched path CMR_BM25_HEAD): the up to 64 terms with the most
+   * postings in this shard also get one column each of an fp16 matrix [n_docs, 64] (row pitch
+   * 128 bytes, 16-byte aligned) that holds fp16(idf * factor) of the document for the term,
+   * 0 where the term is absent.  A batch of queries is scored against it on the tensor cores
+   * (the query side is the count of each head term in the query).                        */
+  const uint16_t* head_mat;  /* [n_docs, 64] fp16 bits or NULL                          */
+  const int32_t* head_slot;  /* [n_terms] column of the term in head_mat, -1 = none; NULL without head_mat */
   int64_t n_docs;
   int32_t n_terms;
   int32_t tile_docs;         /* multiple of 512, <= 65536                               */
   int32_t n_tiles;
   int32_t n_codes;
   int32_t n_dense;
-  int32_t reserved_;
+  int32_t n_head;            /* head_mat columns in use (<= 64)                         */
   double avgdl;
   double k1;
   double b;
@@ -167,14 +174,48 @@ size_t cmr_bm25_workspace_bytes(const cmr_lex_index* ix, int n_queries, int k);
  *              statistics are the caller's business)
  *   outputs as cmr_dense_topk; zero-score documents are ranked too, in
  *   ascending id order (bm25.py:199 sorts ALL candidates, stably).
- *   Environment (read per call): CMR_BM25_BATCH=1 selects the tile-parallel kernel for
- *   batches of >= 8 queries with k <= 32 (same output); CMR_BM25_CTAS_PER_SM=n plans the
- *   grid for n resident CTAs per SM.                                           */
+ *   Environment (read per call): CMR_BM25_CTAS_PER_SM=n plans the exact kernel's grid for n
+ *   resident CTAs per SM; CMR_BM25_HEAD_MIN_QUERIES=n moves the batch size from which
+ *   CMR_BM25_AUTO takes the head-matrix path (default 8).                          */
 int cmr_bm25_topk(const cmr_lex_index* ix, const int32_t* q_terms, const int32_t* q_ptr,
                   int n_queries, int k, const uint8_t* row_mask,
                   int64_t row_offset, double* out_scores, int64_t* out_ids,
                   int32_t* out_counts, int32_t* out_flags, void* workspace,
                   size_t workspace_bytes, cmr_stream_t stream);
+
+/* Same call with an explicit choice of kernel (tests, benchmarks).
+ *   CMR_BM25_EXACT  bm25_tile_kernel: every (query, tile of documents) accumulates float64 scores
+ *                   in shared memory in query-token order -- posting-list scatter for sparse
+ *                   terms, column sweep for dense ones -- and keeps the best keys; nothing to
+ *                   certify.  Cost grows linearly with the number of queries.
+ *   CMR_BM25_HEAD   batched selection on the tensor cores + exact rescoring.  Per block of 32
+ *                   queries: (1) the postings of the queries' sparse tokens are bucketed by
+ *                   32-document group (CSR scatter in shared memory, one CTA per tile);
+ *                   (2) head_mat streams once through TMA into tcgen05.mma (M = 128 documents,
+ *                   N = 32 queries, K = 64 head terms, fp32 accumulators in TMEM); the epilogue
+ *                   adds each document's bucketed sparse contributions and keeps the documents
+ *                   whose fp32 score reaches the query's admission bound (taken from a sample
+ *                   pass of the same kernel over 1/16 of the tiles); (3) the KP best candidates
+ *                   are rescored exactly -- float64, query-token order, the factor of every
+ *                   (token, document) looked up in the posting list -- and ranked.  A query whose
+ *                   certificate fails (|fp32 - exact| <= 2^-11-relative bound cannot separate rank
+ *                   k from the cut-off; a list or bucket overflowed; more than 16 tokens; a
+ *                   negative idf) is re-run by the exact kernel inside the same call, so out_flags
+ *                   is still always 0 and the output is bit-identical to CMR_BM25_EXACT.
+ *                   CMR_EUNSUPPORTED without head_mat / packed postings, with a row_mask, with
+ *                   fewer than 128 documents or tile_docs > 2048.
+ *   CMR_BM25_HEAD_NOFALLBACK  as CMR_BM25_HEAD without the exact re-run: out_flags != 0 marks the
+ *                   queries that were not certified (their outputs are unspecified).
+ *   CMR_BM25_AUTO   HEAD for >= 8 queries when the index and the call allow it, else EXACT.  */
+#define CMR_BM25_AUTO 0
+#define CMR_BM25_EXACT 1
+#define CMR_BM25_HEAD 2
+#define CMR_BM25_HEAD_NOFALLBACK 3
+int cmr_bm25_topk_ex(const cmr_lex_index* ix, const int32_t* q_terms, const int32_t* q_ptr,
+                     int n_queries, int k, const uint8_t* row_mask,
+                     int64_t row_offset, double* out_scores, int64_t* out_ids,
+                     int32_t* out_counts, int32_t* out_flags, void* workspace,
+                     size_t workspace_bytes, cmr_stream_t stream, int algo);
 
 /* ------------------------------------------------------------------------
  * A4  MMR re-ordering of the dense pool (rag/retrieval/fusion.py:39-61,80-102).

@@ -9,20 +9,25 @@ from tests.synth_small import zipf_corpus, zipf_queries
 pytestmark = pytest.mark.gpu
 
 
-def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0, fmt="auto", **build_kw):
+def _run(docs, doc_ptr, tokens, v, queries, k, tile_docs, mask=None, row_offset=0, fmt="auto", algo="auto",
+         allow_flags=False, ix=None, **build_kw):
     from classmate_rag_b200 import lexical, ops
-    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs, fmt=fmt, **build_kw)
-    assert (ix.post_pack is None) == (fmt == "wide")
+    if ix is None:
+        ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=tile_docs, fmt=fmt, **build_kw)
+        assert (ix.post_pack is None) == (fmt == "wide")
     qt, qp = lexical.pack_queries(queries)
     m = None if mask is None else torch.from_numpy(mask).cuda()
-    sc, ids, cnt, fl = ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=m, row_offset=row_offset)
+    sc, ids, cnt, fl = ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=m, row_offset=row_offset, algo=algo)
     torch.cuda.synchronize()
     sc, ids, cnt, fl = sc.cpu().numpy(), ids.cpu().numpy(), cnt.cpu().numpy(), fl.cpu().numpy()
+    ix.last_flags = fl
     tp = ix.term_ptr.cpu().numpy()
     pd = ix.post_doc.cpu().numpy()
     tf = (ix.post_tf.cpu().to(torch.int32) & 0xFFFF).numpy()
     dl = ix.doc_len.cpu().numpy()
     for b, q in enumerate(queries):
+        if allow_flags and fl[b] != 0:
+            continue      # head_nofallback: an uncertified query's output is unspecified
         full = o.bm25_scores_csr(tp, pd, tf, dl, ix.idf_host, ix.avgdl, q)
         idx = np.arange(len(full))
         if mask is not None:
@@ -109,26 +114,69 @@ def test_bm25_dense_columns_do_not_change_results(density, max_terms):
          dense_density=density, **kw)
 
 
-def test_bm25_batch_kernel_equals_tile_kernel_and_oracle(monkeypatch):
-    """The opt-in tile-parallel kernel (CMR_BM25_BATCH=1, read per call): same bytes as the
-    default kernel and the oracle on batches it serves (>= 8 queries, k <= 32), with queries it
-    hands back to the tile kernel (> 16 tokens), masks, ragged sizes, dense columns on and off."""
-    from classmate_rag_b200 import lexical, ops
-    rng = np.random.default_rng(12)
-    for n_docs, vocab, k, tile, density in ((20000, 300, 8, 2048, 0.125), (5002, 60, 24, 512, 0.01),
-                                            (40000, 3000, 10, 4096, None), (777, 40, 8, 512, 0.125)):
-        docs, doc_ptr, tokens, v = zipf_corpus(seed=n_docs, n_docs=n_docs, vocab=vocab, mean_len=20)
-        queries = zipf_queries(7, 40, vocab) + [rng.integers(0, vocab, 30).tolist(), [], [-1, 0, 0, 1]]
-        mask = (rng.random(n_docs) < 0.6).astype(np.uint8)
-        for m in (None, mask):
-            monkeypatch.setenv("CMR_BM25_BATCH", "1")
-            ix = _run(docs, doc_ptr, tokens, v, queries, k, tile, mask=m, dense_density=density)
-            qt, qp = lexical.pack_queries(queries)
-            mm = None if m is None else torch.from_numpy(m).cuda()
-            got = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=mm)]
-            monkeypatch.setenv("CMR_BM25_BATCH", "0")
-            want = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, row_mask=mm)]
-            torch.cuda.synchronize()
-            for a, b in zip(got, want):
-                assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+# ---- the batched path: head-term matrix on the tensor cores + bucketed sparse postings + exact rescoring ----
 
+@pytest.mark.parametrize("n_docs,vocab,k,tile,nq", [(20000, 300, 8, 2048, 12), (5002, 60, 24, 512, 40),
+                                                    (40000, 3000, 10, 2048, 70), (777, 40, 8, 512, 9),
+                                                    (130, 25, 10, 512, 33), (3000, 50, 100, 1024, 16),
+                                                    (66000, 30000, 10, 2048, 32)])
+def test_bm25_head_path_equals_oracle_and_exact_kernel(n_docs, vocab, k, tile, nq):
+    """CMR_BM25_HEAD (with its exact re-run of uncertified queries) returns the oracle's bytes: ragged sizes, more
+    than one block of 32 queries, tiny indexes without an admission bound, k = 100 (KP = 128), queries it
+    must hand back (empty, unknown-only, > 16 tokens), repeated tokens."""
+    from classmate_rag_b200 import lexical, ops
+    rng = np.random.default_rng(n_docs)
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=n_docs, n_docs=n_docs, vocab=vocab, mean_len=20)
+    queries = zipf_queries(7, nq - 3, vocab) + [rng.integers(0, vocab, 30).tolist(), [-1, -1], [0, 0, 1, -1, 0]]
+    ix = _run(docs, doc_ptr, tokens, v, queries, k, tile, algo="head")
+    assert ix.head_mat is not None and ix.head_mat.shape == (n_docs, 64)
+    qt, qp = lexical.pack_queries(queries)
+    got = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, algo="head")]
+    want = [t.clone() for t in ops.bm25_topk(ix, qt.cuda(), qp.cuda(), k, algo="exact")]
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+
+
+def test_bm25_head_path_certifies_normal_queries():
+    """Without the re-run (head_nofallback) the flags say which queries were certified; every certified query is
+    bit-exact, and on a Zipf corpus with 6-token queries (nearly) all of them are."""
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=77, n_docs=50000, vocab=5000, mean_len=30, empty_every=0)
+    queries = [q for q in zipf_queries(11, 64, 5000) if q]
+    ix = _run(docs, doc_ptr, tokens, v, queries, 10, 2048, algo="head_nofallback", allow_flags=True)
+    flagged = int((ix.last_flags != 0).sum())
+    assert flagged <= len(queries) // 8, ix.last_flags.tolist()
+    # the same queries, one block at a time and alone: identical bytes (batch independence)
+    _run(docs, doc_ptr, tokens, v, queries[:9], 10, 2048, algo="head", ix=ix)
+    # reasons are reported in the upper bits: unknown-only query -> not certified (all-zero ties), long query -> bit 1
+    _run(docs, doc_ptr, tokens, v, [[-1], list(range(40))] + queries[:8], 10, 2048, algo="head_nofallback",
+         allow_flags=True, ix=ix)
+    assert ix.last_flags[0] != 0 and (ix.last_flags[1] & 2)
+
+
+def test_bm25_head_path_needs_its_index():
+    from classmate_rag_b200 import lexical, ops
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=5, n_docs=4000, vocab=100, mean_len=10)
+    plain = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=2048, head_terms=0)
+    assert plain.head_mat is None
+    qt, qp = lexical.pack_queries(zipf_queries(1, 9, 100))
+    with pytest.raises(RuntimeError):
+        ops.bm25_topk(plain, qt.cuda(), qp.cuda(), 8, algo="head")
+    big = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=4096)
+    with pytest.raises(RuntimeError):
+        ops.bm25_topk(big, qt.cuda(), qp.cuda(), 8, algo="head")
+    # auto falls back to the exact kernel for both
+    _run(docs, doc_ptr, tokens, v, zipf_queries(1, 9, 100), 8, 4096)
+
+
+def test_bm25_head_path_repeated_runs_identical():
+    from classmate_rag_b200 import lexical, ops
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=31, n_docs=30000, vocab=800, mean_len=25)
+    ix = lexical.build_lexical_index(doc_ptr, tokens, v, device="cuda", tile_docs=2048)
+    qt, qp = lexical.pack_queries(zipf_queries(3, 48, 800))
+    qt, qp = qt.cuda(), qp.cuda()
+    first = None
+    for _ in range(20):
+        out = [t.cpu().numpy().tobytes() for t in ops.bm25_topk(ix, qt, qp, 10, algo="head")]
+        first = first or out
+        assert out == first

@@ -139,12 +139,25 @@ def test_vector_store_behaviour(world, golden):
     assert side.delete(["b", "zzz"]) == 1 and side.count() == 2
     assert [x["id"] for x in side.query(query_embeddings=emb_f32[1], top_k=3)] != [] and \
         "b" not in [x["id"] for x in side.query(query_embeddings=emb_f32[1], top_k=3)]
-    snap = side.persist()
-    assert (snap / "embeddings_bf16.npy").exists()
+    # durable without persist(), like chromadb.PersistentClient: a new process (simulated by dropping the live
+    # collection) replays the operation log -- upserts, the re-upsert that moved "a", the delete
     from classmate_rag_b200.retrieval import vector_store as vsm
+    before = side.query(query_embeddings=emb_f32[1], top_k=3)
+    vsm._COLLECTIONS.pop(side._key())
+    replay = ChromaVectorStore(persist_dir=td / "side", collection_name="t")
+    assert replay.count() == 2 and replay.query(query_embeddings=emb_f32[1], top_k=3) == before
+    assert replay.query(query_embeddings=emb_f32[3], top_k=1)[0]["document"] == "A2"
+    snap = replay.persist()             # compacted rewrite (atomic rename); 2 rows, no tombstones
+    assert (snap / "rows.bf16").stat().st_size == 2 * emb_f32.shape[1] * 2
+    assert not snap.with_name(snap.name + ".tmp").exists() and not snap.with_name(snap.name + ".old").exists()
     vsm._COLLECTIONS.pop(side._key())
     again = ChromaVectorStore(persist_dir=td / "side", collection_name="t")
     assert again.count() == 2 and again.query(query_embeddings=emb_f32[3], top_k=1)[0]["document"] == "A2"
+    assert again.query(query_embeddings=emb_f32[1], top_k=3) == before
+    # rows that are not unit length are normalised on the way in, like hnswlib's cosine space
+    again.upsert(ids=["long"], documents=["L"], metadatas=[{}], embeddings=emb_f32[7:8] * 5.0)
+    hit = again.query(query_embeddings=emb_f32[7] * 3.0, top_k=1)[0]
+    assert hit["id"] == "long" and abs(hit["distance"]) < 1e-2
     again.reset_collection()
     assert again.count() == 0 and again.query(query_embeddings=emb_f32[3], top_k=1) == []
 
@@ -185,6 +198,33 @@ def test_bm25store_snapshot_reload_gives_identical_results(world, golden, tmp_pa
     d = BM25Store.load_or_create(tmp_path / "bm25")
     assert d.count() == len(c["ids"]) + 1
     assert d.search(query="kernel", top_k=3)[0]["id"] == "extra" and not d.loaded_from_snapshot
+
+
+def test_bm25store_snapshot_is_not_used_after_a_mutation(tmp_path):
+    """The sidecar is validated by the JSONL stamp and the entry count only, so it may stand in for a rebuild
+    only while the entries are exactly what load() read: replacing an id (count unchanged, file untouched) or
+    filling a fresh store over a directory that holds an equally long snapshot must rebuild."""
+    from classmate_rag_b200.retrieval import BM25Store
+    ids = [f"d{i}" for i in range(6)]
+    texts = ["alpha beta", "beta gamma", "gamma delta", "delta alpha", "alpha alpha gamma", "beta delta delta"]
+    metas = [{"language": "en"}] * 6
+    a = BM25Store(index_dir=tmp_path / "bm25")
+    a.upsert_many(ids=ids, texts=texts, metadatas=metas)
+    a.save()
+    b = BM25Store.load_or_create(tmp_path / "bm25")
+    b.upsert_many(ids=["d0"], texts=["zeta zeta zeta"], metadatas=[{"language": "en"}])   # same count, same file
+    hit = b.search(query="zeta", top_k=1)
+    assert hit[0]["id"] == "d0" and hit[0]["score"] > 0 and not b.loaded_from_snapshot
+    assert all(x["id"] != "d0" or x["score"] == 0.0 for x in b.search(query="alpha", top_k=6))
+    b.save()
+    c = BM25Store.load_or_create(tmp_path / "bm25")
+    hit = c.search(query="zeta", top_k=1)
+    assert hit[0]["id"] == "d0" and hit[0]["score"] > 0 and c.loaded_from_snapshot
+    # a fresh store over the same directory, populated with as many (other) documents
+    d = BM25Store(index_dir=tmp_path / "bm25")
+    d.upsert_many(ids=ids, texts=["omega"] * 6, metadatas=metas)
+    assert d.search(query="omega", top_k=1)[0]["id"] == "d0" and not d.loaded_from_snapshot
+    assert d.search(query="zeta", top_k=1)[0]["score"] == 0.0
 
 
 def test_device_tokenizer_matches_host_tokenizer(golden):
