@@ -17,10 +17,11 @@
 //                         sparse term, idf) pairs; queries with more than 16 tokens or a negative
 //                         idf are flagged (the exact kernels serve them).
 //   bm25x_bucket_kernel   one CTA per tile of the index: the slices of the pairs' posting lists
-//                         that fall into the tile (skip table, no search) are scattered in
-//                         shared memory into one bucket per 32 documents as (document, query,
-//                         fp16 contribution) words; buckets go to HBM with coalesced stores
-//                         (~100 B per 32 documents: 3 % of the head matrix).
+//                         that fall into the tile (skip table, no search) are scattered into
+//                         one bucket per 32 documents as (document, query, fp16 contribution)
+//                         words; slots come from shared-memory counters, the words go straight
+//                         to the bucket rows in HBM (~200 B per 32 documents at 32 queries: 5 %
+//                         of the head matrix).
 //   bm25x_mma_kernel      persistent, one CTA per SM.  warp 0: TMA producer, one [128 documents x
 //                         64 terms] box of head_mat per item into an 8-stage ring of 128-byte
 //                         swizzled tiles (16 KB each).  warp 1: one thread issues 4 x tcgen05.mma
@@ -34,7 +35,7 @@
 //                         compares with the 32 admission bounds held in registers; the rare
 //                         survivors are appended to the CTA's candidate list of the query.
 //                         SAMPLE mode visits every 16th tile and keeps per-thread running maxima;
-//                         the KP-th largest of those group maxima (launch_admission_bound) is
+//                         the KP-th largest of those group maxima (bm25x_bound_kernel) is
 //                         attained by KP different documents, hence a lower bound of the KP-th best
 //                         approximate score: MAIN mode with that bound keeps a superset of the
 //                         approximate top KP.
@@ -76,7 +77,7 @@ constexpr int BX_MAXT = 16;                   // tokens per query served here
 constexpr int BX_MAX_PAIRS = BX_N * BX_MAXT;  // (query, sparse term) pairs per block
 constexpr int BX_SAMPLE = 0, BX_MAIN = 1;
 constexpr int BX_SAMPLE_STRIDE = 16;
-constexpr int BX_GROUPS_PER_CTA = BX_EPI_WARPS * 2;   // SAMPLE: group maxima each CTA hands to the bound kernel
+constexpr int BX_GROUPS_PER_CTA = BX_EPI_WARPS;       // SAMPLE: group maxima each CTA hands to the bound kernel (one per epilogue warp)
 constexpr int BX_LIST_CAP = 256;              // candidate slots per (CTA, query)
 constexpr int BX_CAP_PER_KP = 128;            // candidates finalize can collect per query = 128 * KP
 constexpr int BX_MAX_TILE_DOCS = 2048;        // bucket kernel: tile_docs / 32 buckets of BX_CAP words in shared memory
@@ -106,47 +107,62 @@ __device__ __forceinline__ u32 ldg_stream_word(const u32* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// One CTA per block of 32 queries.
+// One CTA per block of 32 queries, 16 lanes per query: a lane owns one token of a round of 16, so
+// the term / idf / head-slot loads of a query are three dependent round trips, not 3 per token.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BX_N * 16)
 bm25x_prep_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr, int n_queries,
                   __half* __restrict__ qmat, BxPair* __restrict__ pairs, int* __restrict__ n_pairs,
                   int* __restrict__ flags) {
   __shared__ int s_cnt[BX_N][BX_K];
   __shared__ int s_np;
   const int blk = blockIdx.x, tid = threadIdx.x, q0 = blk * BX_N;
-  for (int i = tid; i < BX_N * BX_K; i += 256) (&s_cnt[0][0])[i] = 0;
+  const int ql = tid >> 4, sub = tid & 15;
+  const unsigned half_mask = 0xFFFFu << (tid & 16);   // the 16 lanes of this query
+  for (int i = tid; i < BX_N * BX_K; i += BX_N * 16) (&s_cnt[0][0])[i] = 0;
   if (tid == 0) s_np = 0;
   __syncthreads();
-  if (tid < BX_N && q0 + tid < n_queries) {
-    const int q = q0 + tid;
+  if (q0 + ql < n_queries) {
+    const int q = q0 + ql;
+    const int lo = q_ptr[q], hi = q_ptr[q + 1];
     int flag = 0, real = 0;
-    for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
-      const int t = q_terms[i];
-      if (t < 0 || t >= ix.n_terms) continue;
-      if (++real > BX_MAXT) {
-        flag |= BX_F_LONG;
-        break;
+    for (int base = lo; base < hi; base += 16) {
+      const int i = base + sub;
+      int t = -1;
+      if (i < hi) t = q_terms[i];
+      const bool valid = t >= 0 && t < ix.n_terms;
+      double w = 0.0;
+      int slot = -1;
+      if (valid) {
+        w = ix.idf[t];
+        slot = ix.head_slot[t];
       }
-      const double w = ix.idf[t];
-      if (w < 0.0) flag |= BX_F_NEG;
-      if (w == 0.0) continue;
-      const int slot = ix.head_slot[t];
-      if (slot >= 0) {
-        s_cnt[tid][slot]++;
-      } else {
-        const int p = atomicAdd(&s_np, 1);   // <= BX_MAXT per query
-        BxPair pr;
-        pr.term = t;
-        pr.q = tid;
-        pr.w = w;
-        pairs[(size_t)blk * BX_MAX_PAIRS + p] = pr;
+      const unsigned vm = __ballot_sync(half_mask, valid) & half_mask;
+      const int before = real + __popc(vm & ((1u << (tid & 31)) - 1u));   // valid tokens ahead of this one
+      real += __popc(vm);
+      if (valid && before < BX_MAXT) {
+        if (w < 0.0) flag |= BX_F_NEG;
+        if (w != 0.0) {
+          if (slot >= 0) {
+            atomicAdd(&s_cnt[ql][slot], 1);
+          } else {
+            const int p = atomicAdd(&s_np, 1);   // <= BX_MAXT per query
+            BxPair pr;
+            pr.term = t;
+            pr.q = ql;
+            pr.w = w;
+            pairs[(size_t)blk * BX_MAX_PAIRS + p] = pr;
+          }
+        }
       }
     }
-    flags[q] = flag ? (CMR_FLAG_UNCERTIFIED | flag) : 0;
+    if (real > BX_MAXT) flag |= BX_F_LONG;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) flag |= __shfl_xor_sync(half_mask, flag, off);
+    if (sub == 0) flags[q] = flag ? (CMR_FLAG_UNCERTIFIED | flag) : 0;
   }
   __syncthreads();
-  for (int i = tid; i < BX_N * BX_K; i += 256) qmat[(size_t)blk * BX_N * BX_K + i] = __int2half_rn((&s_cnt[0][0])[i]);
+  for (int i = tid; i < BX_N * BX_K; i += BX_N * 16) qmat[(size_t)blk * BX_N * BX_K + i] = __int2half_rn((&s_cnt[0][0])[i]);
   if (tid == 0) n_pairs[blk] = s_np;
 }
 
@@ -154,25 +170,34 @@ bm25x_prep_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
 // One CTA per tile of the index: bucket the block's sparse postings by 32-document group.
 // buckets [n_tiles * tile_docs / 32][BX_CAP]: word 0 = number of entries (<= BX_CAP - 1), then
 // entries  bits 0-4 document within the group | bits 5-9 query | bits 16-31 fp16(idf * factor).
+// Slots are handed out by shared-memory counters; the entries go straight to the bucket rows in
+// global memory (all writers of a row are this CTA, within microseconds: L2 merges the sectors).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int BXB_THREADS = 256;
+constexpr int BXB_U = 4;   // postings in flight per thread
+
+__global__ void __launch_bounds__(BXB_THREADS)
 bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const int* __restrict__ n_pairs_p, int q_base,
                     u32* __restrict__ buckets, int* __restrict__ flags) {
-  extern __shared__ u32 s_b[];                  // [n_b][BX_CAP]
   __shared__ long long s_lo[BX_MAX_PAIRS];
   __shared__ int s_off[BX_MAX_PAIRS + 1];
+  __shared__ double s_w[BX_MAX_PAIRS];
+  __shared__ int s_q[BX_MAX_PAIRS];
   __shared__ int s_cnt[BX_MAX_TILE_DOCS / 32];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_b = ix.tile_docs / 32;
   const int np = *n_pairs_p;
-  for (int b = tid; b < n_b; b += 256) s_cnt[b] = 0;
+  u32* rows = buckets + (size_t)tile * n_b * BX_CAP;
+  for (int b = tid; b < n_b; b += BXB_THREADS) s_cnt[b] = 0;
   if (tid == 0) s_off[0] = 0;
-  for (int p = tid; p < np; p += 256) {
-    const int t = pairs[p].term;
-    const u32* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
+  for (int p = tid; p < np; p += BXB_THREADS) {
+    const BxPair pr = pairs[p];
+    const u32* sk = ix.tile_skip + (size_t)pr.term * (ix.n_tiles + 1) + tile;
     const u32 a = sk[0], z = sk[1];
-    s_lo[p] = ix.term_ptr[t] + a;
+    s_lo[p] = ix.term_ptr[pr.term] + a;
     s_off[p + 1] = (int)(z - a);
+    s_w[p] = pr.w;
+    s_q[p] = pr.q;
   }
   __syncthreads();
   if (warp == 0) {  // inclusive scan of the slice lengths
@@ -191,28 +216,37 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const in
   }
   __syncthreads();
   const int total = s_off[np];
-  for (int i = tid; i < total; i += 256) {
-    int lo = 0, hi = np;   // the pair whose slice holds posting i: largest p with s_off[p] <= i
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= i) lo = mid;
-      else hi = mid;
+  for (int i0 = tid; i0 < total; i0 += BXB_U * BXB_THREADS) {
+    int pr_of[BXB_U];
+    u32 pk[BXB_U];
+#pragma unroll
+    for (int u = 0; u < BXB_U; ++u) {   // the pair whose slice holds posting i: largest p with s_off[p] <= i
+      const int i = i0 + u * BXB_THREADS;
+      int lo = 0, hi = np;
+      if (i < total) {
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_off[mid] <= i) lo = mid;
+          else hi = mid;
+        }
+        pk[u] = ldg_stream_word(ix.post_pack + s_lo[lo] + (i - s_off[lo]));
+      }
+      pr_of[u] = lo;
     }
-    const u32 pk = ldg_stream_word(ix.post_pack + s_lo[lo] + (i - s_off[lo]));
-    const BxPair pr = pairs[lo];
-    const u32 local = pk & 0xFFFFu;
-    const __half h = __double2half(__dmul_rn(pr.w, __ldg(ix.imp_table + (pk >> 16))));
-    const int b = (int)(local >> 5);
-    const int slot = atomicAdd(&s_cnt[b], 1) + 1;
-    if (slot < BX_CAP) s_b[b * BX_CAP + slot] = (local & 31u) | ((u32)pr.q << 5) | ((u32)__half_as_ushort(h) << 16);
-    else atomicOr(&flags[q_base + pr.q], CMR_FLAG_UNCERTIFIED | BX_F_BUCKET);
+#pragma unroll
+    for (int u = 0; u < BXB_U; ++u) {
+      if (i0 + u * BXB_THREADS >= total) break;
+      const u32 local = pk[u] & 0xFFFFu;
+      const int q = s_q[pr_of[u]];
+      const __half h = __double2half(__dmul_rn(s_w[pr_of[u]], __ldg(ix.imp_table + (pk[u] >> 16))));
+      const int b = (int)(local >> 5);
+      const int slot = atomicAdd(&s_cnt[b], 1) + 1;
+      if (slot < BX_CAP) rows[b * BX_CAP + slot] = (local & 31u) | ((u32)q << 5) | ((u32)__half_as_ushort(h) << 16);
+      else atomicOr(&flags[q_base + q], CMR_FLAG_UNCERTIFIED | BX_F_BUCKET);
+    }
   }
   __syncthreads();
-  for (int b = warp; b < n_b; b += 8) {
-    const int c = s_cnt[b] < BX_CAP - 1 ? s_cnt[b] : BX_CAP - 1;
-    u32* dst = buckets + ((size_t)tile * n_b + b) * BX_CAP;
-    for (int i = lane; i <= c; i += 32) dst[i] = i == 0 ? (u32)c : s_b[b * BX_CAP + i];
-  }
+  for (int b = tid; b < n_b; b += BXB_THREADS) rows[b * BX_CAP] = (u32)(s_cnt[b] < BX_CAP - 1 ? s_cnt[b] : BX_CAP - 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -222,7 +256,7 @@ struct BxParams {
   int stride;           // SAMPLE: visited tile = item * stride (full tiles only); MAIN: 1
   int n_queries;        // queries of this block (<= 32)
   const u32* buckets;   // [ceil(n_docs / 32) rounded up to whole index tiles][BX_CAP]
-  float* gmax;          // SAMPLE: [gridDim.x * BX_GROUPS_PER_CTA][32]
+  float* gmax;          // SAMPLE: [32][gridDim.x * BX_GROUPS_PER_CTA] maxima of every group, per query
   const float* thr;     // MAIN: [32] admission bounds
   u64* cand;            // MAIN: [gridDim.x][32][cap] keys (orderable fp32 score, ~document)
   int* cnt;             // MAIN: [gridDim.x][32] entries appended (may exceed cap)
@@ -409,8 +443,10 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       w1 = n1;
     }
     if (MODE == BX_SAMPLE) {
-      // group maxima: 16 lanes each -> BX_GROUPS_PER_CTA groups per CTA (a group that saw no
-      // document reports -inf, which is a valid maximum of nothing)
+      // group maxima: the documents an epilogue warp saw form one group (a warp that saw none
+      // reports -inf, a valid maximum of nothing); lane j publishes query j's
+      const int n_groups = (int)gridDim.x * BX_GROUPS_PER_CTA;
+      float mine = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float m = gm[j];
@@ -418,13 +454,10 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 4));
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 8));
-        gm[j] = m;
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 16));
+        if (lane == j) mine = m;
       }
-      if ((lane & 15) == 0) {
-        float* dst = p.gmax + ((size_t)blockIdx.x * BX_GROUPS_PER_CTA + e * 2 + (lane >> 4)) * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = gm[j];
-      }
+      p.gmax[(size_t)lane * n_groups + (size_t)blockIdx.x * BX_GROUPS_PER_CTA + e] = mine;
     }
   }
 
@@ -436,6 +469,39 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)(BX_ACC * BX_N))
                  : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Admission bounds: thr[q] = the kp-th largest of the n_groups group maxima gmax[q][*] (attained by
+// kp different documents, hence a lower bound of the kp-th best approximate score); -inf with
+// fewer than kp groups.  One warp per query: coalesced loads into shared memory, then bit-wise
+// bisection on the orderable integer image of the floats (no block barrier).
+// ---------------------------------------------------------------------------------------
+constexpr int BXT_WARPS = 4;
+constexpr int BXT_MAX_GROUPS = 2048;
+
+__global__ void __launch_bounds__(BXT_WARPS * 32)
+bm25x_bound_kernel(const float* __restrict__ gmax, int n_groups, int kp, int n_queries, float* __restrict__ thr) {
+  __shared__ u32 s_vals[BXT_WARPS][BXT_MAX_GROUPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * BXT_WARPS + warp;
+  if (q >= n_queries) return;
+  if (n_groups < kp) {
+    if (lane == 0) thr[q] = -INFINITY;
+    return;
+  }
+  u32* v = s_vals[warp];
+  const float* src = gmax + (size_t)q * n_groups;
+  for (int g = lane; g < n_groups; g += 32) v[g] = f32_orderable(src[g]);
+  __syncwarp();
+  u32 prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const u32 c = prefix | (1u << bit);
+    int local = 0;
+    for (int g = lane; g < n_groups; g += 32) local += v[g] >= c;
+    if (__reduce_add_sync(0xFFFFFFFFu, local) >= kp) prefix = c;
+  }
+  if (lane == 0) thr[q] = orderable_f32(prefix);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -550,7 +616,7 @@ struct BxPlan {
   int kpl, kp, cap, cap_total;
   int n_blocks, n_items, n_sample, stride, grid_main, grid_sample, n_groups, n_b;
   size_t off_qmat, off_pairs, off_npairs, off_thr, off_gmax, off_cand, off_cnt, off_buckets, total;
-  size_t smem_fin, smem_bucket;
+  size_t smem_fin;
 };
 
 static void bx_plan(const cmr_lex_index& ix, int n_queries, int k, int sms, BxPlan* p) {
@@ -569,6 +635,7 @@ static void bx_plan(const cmr_lex_index& ix, int n_queries, int k, int sms, BxPl
   p->n_sample = full > 0 ? (full + stride - 1) / stride : 0;
   p->grid_main = p->n_items < sms ? p->n_items : sms;
   p->grid_sample = p->n_sample < sms ? p->n_sample : sms;
+  if (p->grid_sample > BXT_MAX_GROUPS / BX_GROUPS_PER_CTA) p->grid_sample = BXT_MAX_GROUPS / BX_GROUPS_PER_CTA;
   if (p->grid_sample < 1) p->grid_sample = 1;
   p->n_groups = p->grid_sample * BX_GROUPS_PER_CTA;
   if (p->n_groups < p->kp) {
@@ -589,7 +656,6 @@ static void bx_plan(const cmr_lex_index& ix, int n_queries, int k, int sms, BxPl
   p->off_buckets = off; off += up((size_t)ix.n_tiles * p->n_b * BX_CAP * 4);
   p->total = off;
   p->smem_fin = (size_t)p->cap_total * 8 + (size_t)p->kp * 16 + (size_t)4 * p->kp * 8 + (size_t)p->kp * BX_MAXT * 8 + 16;
-  p->smem_bucket = (size_t)p->n_b * BX_CAP * 4;
 }
 
 bool bm25_head_eligible(const cmr_lex_index& ix, int k, bool has_mask) {
@@ -614,9 +680,6 @@ static int bx_opt_in() {
     cudaError_t e = cudaFuncSetAttribute(bm25x_mma_kernel<BX_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(bm25x_mma_kernel<BX_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(bm25x_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               BX_MAX_TILE_DOCS / 32 * BX_CAP * 4);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(bm25x_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
@@ -659,14 +722,14 @@ int bm25_head_topk(const cmr_lex_index& ix, const int* q_terms, const int* q_ptr
   alignas(64) CUtensorMap tm_rows, tm_q;
   rc = make_tmap(&tm_rows, ix.head_mat, ix.n_docs, BX_K, BX_M, true);
   if (rc != CMR_OK) return rc;
-  bm25x_prep_kernel<<<p.n_blocks, 256, 0, st>>>(ix, q_terms, q_ptr, n_queries, qmat, pairs, n_pairs, out_flags);
+  bm25x_prep_kernel<<<p.n_blocks, BX_N * 16, 0, st>>>(ix, q_terms, q_ptr, n_queries, qmat, pairs, n_pairs, out_flags);
 
   for (int blk = 0; blk < p.n_blocks; ++blk) {
     const int q_base = blk * BX_N;
     const int nq = n_queries - q_base < BX_N ? n_queries - q_base : BX_N;
     rc = make_tmap(&tm_q, qmat + (size_t)blk * BX_N * BX_K, BX_N, BX_K, BX_N, true);
     if (rc != CMR_OK) return rc;
-    bm25x_bucket_kernel<<<ix.n_tiles, 256, p.smem_bucket, st>>>(ix, pairs + (size_t)blk * BX_MAX_PAIRS, n_pairs + blk,
+    bm25x_bucket_kernel<<<ix.n_tiles, BXB_THREADS, 0, st>>>(ix, pairs + (size_t)blk * BX_MAX_PAIRS, n_pairs + blk,
                                                                q_base, buckets, out_flags);
     BxParams kp{};
     kp.n_docs = ix.n_docs;
@@ -682,8 +745,8 @@ int bm25_head_topk(const cmr_lex_index& ix, const int* q_terms, const int* q_ptr
       kp.stride = p.stride;
       bm25x_mma_kernel<BX_SAMPLE><<<p.grid_sample, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
     }
-    rc = launch_admission_bound(gmax, p.n_sample > 0 ? p.n_groups : 0, 32, p.kp, nq, thr, st);
-    if (rc != CMR_OK) return rc;
+    bm25x_bound_kernel<<<(nq + BXT_WARPS - 1) / BXT_WARPS, BXT_WARPS * 32, 0, st>>>(gmax, p.n_sample > 0 ? p.n_groups : 0,
+                                                                                   p.kp, nq, thr);
     kp.n_items = p.n_items;
     kp.stride = 1;
     bm25x_mma_kernel<BX_MAIN><<<p.grid_main, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);

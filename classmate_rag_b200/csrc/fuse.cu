@@ -378,7 +378,8 @@ shard_pack_kernel(const double* __restrict__ d_scores, const long long* __restri
 // One CTA per query over the gathered messages [G][B][msg].  Ranking by counting over the
 // G*pool (G*kb) entries with the total order (score desc, id asc): identical for any G.
 __global__ void __launch_bounds__(SHARD_THREADS)
-shard_merge_kernel(const unsigned char* __restrict__ gathered, size_t slot_stride,
+shard_merge_kernel(const unsigned char* gathered /* peers store into it until the flags are up: no __restrict__,
+                   so its loads are ordinary ld.global after the acquire, never ld.global.nc */, size_t slot_stride,
                    const unsigned int* __restrict__ wait_flags, const unsigned int* __restrict__ wait_state,
                    unsigned long long parity_stride, int* __restrict__ timeout_flag,
                    int n_parts, int n_queries, int pool, int kb,

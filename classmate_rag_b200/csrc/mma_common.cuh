@@ -146,22 +146,39 @@ __device__ __forceinline__ void cand_collect_select(const u64* __restrict__ cand
   const int m = s_total < cap_total ? s_total : cap_total;
   __syncthreads();  // every thread has read s_total / s_over before s_total is reused as a counter below
   // Ranking m keys against each other is quadratic, and only the KP best matter: find the
-  // KP-th largest score word by bisection (32 rounds of counting), then rank just the keys
-  // that reach it (the KP best plus ties of the last one).
+  // KP-th largest score word by a radix select (4 passes over one byte each: histogram in shared
+  // memory, suffix sums, pick the byte that holds the KP-th), then rank just the keys that reach it
+  // (the KP best plus ties of the last one).
   u32 floor_word = 0;
   if (m > 4 * KP) {
-    for (int bit = 31; bit >= 0; --bit) {
-      const u32 c = floor_word | (1u << bit);
-      int local = 0;
-      for (int e = tid; e < m; e += FIN_THREADS) local += (u32)(s_keys[e] >> 32) >= c;
-      local = __reduce_add_sync(0xFFFFFFFFu, local);
-      if (tid == 0) s_total = 0;
+    __shared__ int s_hist[256];
+    __shared__ u32 s_sel[2];
+    u32 prefix = 0;
+    int need = KP;
+    for (int pass = 3; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      const u32 hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
-      if (lane == 0 && local) atomicAdd(&s_total, local);
+      for (int e = tid; e < m; e += FIN_THREADS) {
+        const u32 w = (u32)(s_keys[e] >> 32);
+        if ((w & hi_mask) == prefix) atomicAdd(&s_hist[(w >> shift) & 255u], 1);
+      }
       __syncthreads();
-      if (s_total >= KP) floor_word = c;
+      if (tid < 256) {
+        int suf = 0;   // keys (with the decided high bytes) whose byte is >= tid
+        for (int x = tid; x < 256; ++x) suf += s_hist[x];
+        const int above = suf - s_hist[tid];
+        if (suf >= need && above < need) {   // exactly one byte value holds the need-th largest
+          s_sel[0] = prefix | ((u32)tid << shift);
+          s_sel[1] = (u32)(need - above);
+        }
+      }
       __syncthreads();
+      prefix = s_sel[0];
+      need = (int)s_sel[1];
     }
+    floor_word = prefix;
   }
   // survivors (score word >= floor) are compacted and ranked among themselves; with more than
   // 4*KP of them (a crowd of ties at the boundary) every key is ranked against all m instead

@@ -9,11 +9,16 @@ insertion order, so the ranked ids match the reference's stable sort exactly.
 
 Filters follow ``_matches_filter`` to the letter (filters.bm25_clauses).  Like the
 reference, a filtered search scores over the statistics of the FILTERED subset (N, df,
-avgdl all change): the subset's index is built on the device once per distinct filter and
-cached until the store changes.
+avgdl all change, and with them idf and every BM25 factor).  No subset index is built:
+``_FilteredView`` derives the subset's statistics with masked reductions over the resident
+CSR (df = postings whose document passes, first appearances from the token array), the
+idf table and the (tf, doc_len) factor table are recomputed for them, and the exact kernel
+scores the FULL index with those tables and the filter's row mask.  A view is a mask and
+two small tables, cached per distinct filter until the store changes.
 """
 from __future__ import annotations
 
+import dataclasses
 import json
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -44,6 +49,9 @@ class _DeviceIndex:
                  all_doc_ptr_host: np.ndarray, device, lex: Optional["lexical.LexicalIndex"] = None):
         # rows: positions (in store order) of the documents this index covers
         self.rows = np.asarray(rows, dtype=np.int64)
+        # the same map on the device (None: the index covers every row of the store, in order)
+        self.rows_dev = (None if len(self.rows) == all_doc_ptr_host.shape[0] - 1
+                         else torch.from_numpy(self.rows).to(device))
         self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
         if lex is not None:     # loaded from a snapshot
             self.lex = lex
@@ -69,6 +77,51 @@ class _DeviceIndex:
         self.lex = lexical.build_lexical_index(sub_ptr, sub_tok, max(n_terms, 1), device=device, tile_docs=tile)
 
 
+class _FilteredView:
+    """The full index seen through a filter (reference: the per-query BM25Okapi rebuild over the
+    filtered entries, rag/retrieval/bm25.py:184-191).  ``lex`` shares every posting array with
+    the full index; only idf, the factor table and avgdl are the subset's.  Dense columns and
+    the head matrix hold factors of the FULL corpus's avgdl, so they are dropped: the exact
+    kernel walks the packed postings."""
+
+    def __init__(self, full: _DeviceIndex, mask: torch.Tensor, doc_ptr: torch.Tensor, tokens: torch.Tensor):
+        lex = full.lex
+        dev = mask.device
+        self.rows = full.rows
+        self.rows_dev = None
+        self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
+        self.mask = mask
+        keep = mask.bool()
+        n_terms, n_post = lex.n_terms, lex.n_postings
+        doc_len = (doc_ptr[1:] - doc_ptr[:-1])
+        # one read-back for the scalars: subset size and its token total
+        n_sub, total = [int(x) for x in torch.stack([keep.sum(), (doc_len * keep).sum()]).tolist()]
+        self.n_docs = n_sub
+        # df of the subset: postings whose document passes the filter (segmented sum over the CSR)
+        hit = keep.index_select(0, lex.post_doc).to(torch.int32 if n_post < 2 ** 31 else torch.int64)
+        cs = torch.zeros(n_post + 1, dtype=hit.dtype, device=dev)
+        torch.cumsum(hit, 0, out=cs[1:])
+        df = (cs[lex.term_ptr[1:]] - cs[lex.term_ptr[:-1]]).to(torch.int64)
+        del hit, cs
+        # rank_bm25 sums idf in dict order = first appearance of each term over the subset's token stream
+        n_tok = int(tokens.numel())
+        first = torch.full((max(n_terms, 1),), n_tok, dtype=torch.int64, device=dev)
+        if n_tok:
+            tok_keep = torch.repeat_interleave(keep, doc_len)
+            pos = torch.where(tok_keep, torch.arange(n_tok, device=dev), torch.full((), n_tok, dtype=torch.int64, device=dev))
+            first.scatter_reduce_(0, tokens.long(), pos, reduce="amin")
+        order = torch.argsort(first, stable=True)
+        df_h = df.cpu().numpy().astype(np.int64)
+        n_seen = int((df_h > 0).sum())
+        idf_host, _ = lexical.idf_table(df_h, n_sub, order[:n_seen].cpu().numpy())
+        avgdl = (total / n_sub) if n_sub > 0 else 0.0
+        imp = (lexical.bm25_factor(lex.pair_tf, lex.pair_dl, avgdl, lex.k1, lex.b) if avgdl > 0
+               else torch.zeros_like(lex.imp_table))
+        self.lex = dataclasses.replace(lex, idf=torch.from_numpy(idf_host).to(dev), imp_table=imp, avgdl=float(avgdl),
+                                       dense_imp=None, dense_slot=None, dense_terms=None, head_mat=None, head_slot=None,
+                                       head_terms=None, idf_host=idf_host, df_host=df_h, _struct=None)
+
+
 @dataclass
 class BM25Store:
     index_dir: Path = Path("./indexes/bm25")
@@ -79,7 +132,7 @@ class BM25Store:
     _id_list: List[str] = field(default_factory=list)           # order of the index rows
     _vocab: Dict[str, int] = field(default_factory=dict, repr=False)
     _full: Optional[_DeviceIndex] = field(default=None, repr=False)
-    _subsets: "OrderedDict[tuple, _DeviceIndex]" = field(default_factory=OrderedDict, repr=False)
+    _subsets: "OrderedDict[tuple, Any]" = field(default_factory=OrderedDict, repr=False)   # filter -> _FilteredView
     _columns: Optional[MetaColumns] = field(default=None, repr=False)
     _dirty: bool = field(default=True, repr=False)
     _dev_tokens: Optional[Tuple[torch.Tensor, torch.Tensor, np.ndarray]] = field(default=None, repr=False)
@@ -176,17 +229,24 @@ class BM25Store:
         if key is not None and key in self._subsets:
             self._subsets.move_to_end(key)
             return self._subsets[key]
-        mask = self._columns.mask(clauses).cpu().numpy().astype(bool)
-        rows = np.nonzero(mask)[0]
-        if rows.size == 0:
-            return None
-        if rows.size == len(self._id_list):
-            return self._full
+        mask = self._columns.mask(clauses)
         doc_ptr, tokens, ptr = self._dev_tokens
-        sub = _DeviceIndex(rows, doc_ptr, tokens, len(self._vocab), ptr, torch.device(self.device))
+        if self._full.lex.post_pack is not None and self._full.lex.pair_tf is not None:
+            sub = _FilteredView(self._full, mask, doc_ptr, tokens)      # subset statistics, no rebuild
+            if sub.n_docs == 0:
+                return None
+            if sub.n_docs == len(self._id_list):
+                return self._full
+        else:   # wide postings (> 65536 distinct (tf, doc_len) pairs): build the subset's own index
+            rows = np.nonzero(mask.cpu().numpy().astype(bool))[0]
+            if rows.size == 0:
+                return None
+            if rows.size == len(self._id_list):
+                return self._full
+            sub = _DeviceIndex(rows, doc_ptr, tokens, len(self._vocab), ptr, torch.device(self.device))
         if key is not None:
             self._subsets[key] = sub
-            while len(self._subsets) > 8:
+            while len(self._subsets) > 32:
                 self._subsets.popitem(last=False)
         return sub
 
@@ -225,7 +285,7 @@ class BM25Store:
             if nbytes == 0:
                 raise ValueError("unsupported bm25 shape: " + _lib.last_error())
             buf = ix.buffers[key] = ops.TopkBuffers(len(queries), k, nbytes, dev)
-        sc, docs, cnt, _ = ops.bm25_topk(ix.lex, qt, qp, k, buffers=buf)
+        sc, docs, cnt, _ = ops.bm25_topk(ix.lex, qt, qp, k, buffers=buf, row_mask=getattr(ix, "mask", None))
         return ix, sc, docs, cnt
 
     def search(self, *, query: str, where: Optional[Mapping[str, Any]] = None, top_k: int = 8) -> List[Dict[str, Any]]:

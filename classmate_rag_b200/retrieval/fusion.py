@@ -76,21 +76,33 @@ class HybridRetriever:
     mmr_max_pool: int = 24
 
     # -- the two searches, device level ---------------------------------------------------
-    def _vector_search_device(self, q_vec: np.ndarray, where, k: int):
-        """(gids i64 [1,k'], sims f64 [1,k'], counts i32 [1]) in final (post-MMR) order."""
+    def _stage_query(self, q_vec: np.ndarray, dev) -> torch.Tensor:
+        """fp32 query -> device through a pinned staging buffer kept on the retriever (no pageable copy)."""
+        q = np.ascontiguousarray(q_vec, dtype=np.float32).reshape(1, -1)
+        pin = getattr(self, "_pin_q", None)
+        if pin is None or pin.shape != q.shape:
+            pin = self._pin_q = torch.empty(q.shape, dtype=torch.float32).pin_memory()
+        pin.copy_(torch.from_numpy(q))
+        return pin.to(dev, non_blocking=True)
+
+    def _vector_search_device(self, q_vec: np.ndarray, where, k: int, certified: bool = True):
+        """(gids i64 [1,k'], sims f64 [1,k'], counts i32 [1], flags i32 [1]) in final (post-MMR)
+        order.  ``certified``: re-run an uncertified query on the exhaustive scan right here (one
+        host synchronisation); retrieve() defers that check to its single read-back instead."""
+        from .vector_store import unit_rows
         col = self.vector_store._ensure_collection()
         pool = max(k, self.mmr_max_pool) if self.use_mmr else k
         pool = min(pool, 64)
         dev = col.device
-        empty = (torch.full((1, max(k, 1)), -1, dtype=torch.int64, device=dev),
-                 torch.zeros((1, max(k, 1)), dtype=torch.float64, device=dev),
-                 torch.zeros((1,), dtype=torch.int32, device=dev))
         if col.n_rows == 0:
-            return empty
-        q = ops.f32_to_bf16(torch.from_numpy(np.ascontiguousarray(q_vec, dtype=np.float32)[None]).to(dev))
+            return (torch.full((1, max(k, 1)), -1, dtype=torch.int64, device=dev),
+                    torch.zeros((1, max(k, 1)), dtype=torch.float64, device=dev),
+                    torch.zeros((1,), dtype=torch.int32, device=dev), torch.zeros((1,), dtype=torch.int32, device=dev))
+        q = ops.f32_to_bf16(unit_rows(self._stage_query(q_vec, dev)))
         mask = col.mask(where)
-        scores, rows, counts, _ = ops.dense_topk_certified(col.matrix(), q, pool, row_mask=mask,
-                                                           workspace=col.workspace(1, pool), algo=col.algo_for(mask))
+        fn = ops.dense_topk_certified if certified else ops.dense_topk
+        scores, rows, counts, flags = fn(col.matrix(), q, pool, row_mask=mask, workspace=col.workspace(1, pool),
+                                         algo=col.algo_for(mask), cert_eps=ops.dense_cert_eps(col.dim, 1.0005, col.max_row_norm))
         if self.use_mmr:
             cand = ops.gather_rows(col.matrix(), rows)
             rows, scores, counts = ops.mmr_select(cand, scores, rows, counts, min(k, pool), self.mmr_lambda)
@@ -98,7 +110,7 @@ class HybridRetriever:
             rows, scores = rows[:, :k], scores[:, :k]
             counts = torch.clamp(counts, max=k)
         gids = torch.where(rows >= 0, col.gids[rows.clamp(min=0)], rows)
-        return gids.contiguous(), scores.contiguous(), counts.contiguous()
+        return gids.contiguous(), scores.contiguous(), counts.contiguous(), flags
 
     def _bm25_search_device(self, query: str, where, k: int):
         if not query.strip() or self.bm25_store.count() == 0:
@@ -107,14 +119,14 @@ class HybridRetriever:
         if got is None:
             return None
         ix, sc, docs, cnt = got
-        rows = torch.from_numpy(ix.rows).to(docs.device)
-        gids = torch.where(docs >= 0, self.bm25_store._gids[rows[docs.clamp(min=0)]], docs)
+        store_rows = docs.clamp(min=0) if ix.rows_dev is None else ix.rows_dev[docs.clamp(min=0)]
+        gids = torch.where(docs >= 0, self.bm25_store._gids[store_rows], docs)
         return gids.contiguous(), sc, cnt
 
     # -- reference-shaped helpers (kept for callers that use them directly) -------------------
     def _vector_search(self, *, query: str, where: Optional[Mapping[str, object]], k: int) -> List[Mapping[str, object]]:
         q_vec = np.asarray(self.embedder.encode_queries([query])[0], dtype=np.float32)
-        gids, sims, cnt = [t.cpu().numpy() for t in self._vector_search_device(q_vec, where, k)]
+        gids, sims, cnt = [t.cpu().numpy() for t in self._vector_search_device(q_vec, where, k)[:3]]
         col = self.vector_store._ensure_collection()
         out = []
         for j in range(int(cnt[0])):
@@ -127,6 +139,17 @@ class HybridRetriever:
     def _bm25_search(self, *, query: str, where: Optional[Mapping[str, object]], k: int) -> List[Mapping[str, object]]:
         return self.bm25_store.search(query=query, where=where, top_k=k)
 
+    def _read_back(self, tensors):
+        """Device results -> pinned host buffers (cached per shape), asynchronous copies, one wait."""
+        cache = getattr(self, "_pin_out", None)
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        if cache is None or cache[0] != key:
+            cache = self._pin_out = (key, [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in tensors])
+        for h, t in zip(cache[1], tensors):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(tensors[0].device).synchronize()
+        return [h.numpy() for h in cache[1]]
+
     # -- the entry point -----------------------------------------------------------------------------
     def retrieve(self, *, question: str, filters: Optional[Mapping[str, object]] = None, top_k: int = 8,
                  hybrid: bool = True) -> List[Dict[str, object]]:
@@ -136,12 +159,21 @@ class HybridRetriever:
 
         q_vec = np.asarray(self.embedder.encode_queries([question])[0], dtype=np.float32)
         k_vec = self.k_vector if hybrid else max(top_k, self.k_vector)
-        vec = self._vector_search_device(q_vec, chroma_where, k_vec)
+        # every kernel of the call is enqueued without a host synchronisation; results and the dense
+        # certificate flag come back in ONE read-back into pinned buffers kept on the retriever
+        *vec, flags = self._vector_search_device(q_vec, chroma_where, k_vec, certified=False)
         bm = self._bm25_search_device(question, bm_where, self.k_bm25) if hybrid else None
-        ids, fused, vdist, bmsc, cnt = ops.hybrid_fuse(
-            vec, bm, top_k=top_k, rrf_k=self.rrf_k,
-            w_vec=self.weight_vector if hybrid else 1.0, w_bm=self.weight_bm25)
-        ids, fused, vdist, bmsc, cnt = (t.cpu().numpy() for t in (ids, fused, vdist, bmsc, cnt))
+        dev_out = ops.hybrid_fuse(tuple(vec), bm, top_k=top_k, rrf_k=self.rrf_k,
+                                  w_vec=self.weight_vector if hybrid else 1.0, w_bm=self.weight_bm25)
+        host = self._read_back((*dev_out, flags))
+        if int(host[5][0]) != 0:
+            # thousands of exact duplicates around rank k: the fp32 pass could not certify its pool;
+            # the exhaustive float64 scan serves this query (rare; one more round trip)
+            *vec, _ = self._vector_search_device(q_vec, chroma_where, k_vec, certified=True)
+            dev_out = ops.hybrid_fuse(tuple(vec), bm, top_k=top_k, rrf_k=self.rrf_k,
+                                      w_vec=self.weight_vector if hybrid else 1.0, w_bm=self.weight_bm25)
+            host = self._read_back((*dev_out, flags))
+        ids, fused, vdist, bmsc, cnt = host[:5]
 
         col = self.vector_store._ensure_collection()
         entries = self.bm25_store._entries

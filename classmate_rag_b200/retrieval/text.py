@@ -48,8 +48,11 @@ _detect = None
 
 
 def detect_lang_tag(text: str) -> str:
-    """'en' or 'it'.  Uses langdetect (seeded, as the reference does) when it is installed;
-    otherwise a stopword vote between the two lists, English on ties or empty input."""
+    """'en' or 'it'.  Uses langdetect (seeded, as the reference does,
+    rag/utils/lang_detect.py:10-27) when it is installed.  Without it the reference cannot even
+    be imported; here the tag comes from a stopword vote between the two lists (English on ties
+    or empty input) and a RuntimeWarning says so once, because the vote can pick another stopword
+    list than langdetect would for a text that carries no metadata language."""
     global _detect
     if _detect is None:
         try:
@@ -58,6 +61,10 @@ def detect_lang_tag(text: str) -> str:
             _detect = detect
         except Exception:
             _detect = False
+            import warnings
+            warnings.warn("langdetect is not installed: classmate_rag_b200 decides 'en' / 'it' by a stopword vote, which "
+                          "can differ from the reference's langdetect for texts without a metadata language",
+                          RuntimeWarning, stacklevel=2)
     if _detect:
         try:
             lang = _detect(text or "")

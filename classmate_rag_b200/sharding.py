@@ -94,6 +94,9 @@ class ShardComm:
                 self.peer_generation += 1
             except Exception as exc:  # no symmetric memory on this build / topology
                 self.peer_memory, self.peer, self.peer_error = False, None, repr(exc)
+                import warnings
+                warnings.warn(f"peer-memory shard exchange unavailable ({exc!r}): using the NCCL all-gather "
+                              "(set CMRAG_P2P=0 to silence)", RuntimeWarning, stacklevel=2)
         return self.peer
 
     def _merge(self, scores, ids, counts):
