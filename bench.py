@@ -442,7 +442,7 @@ def main():
 
     # ---- queries -----------------------------------------------------------
     n_steps = a.warmup + a.steps
-    nq = a.batch * n_steps
+    nq = max(a.batch, 128 if world == 1 else a.batch) * n_steps   # enough fresh queries for the batch sweep too
     q_f32, planted = synth.dense_queries(a.rows, a.dim, nq, dev)
     terms = synth.lexical_queries(nq, VOCAB)
     q_bf16 = ops.f32_to_bf16(q_f32)
@@ -623,8 +623,33 @@ def main():
                    "runs step s; a batch with an uncertified query is re-run on the exhaustive scan before it is handed out"}
     # sanity on the last batch: the planted row is the dense top-1 unless MMR/RRF reorder it out of the top-10
     ids_last = last[0]
-    planted_last = planted[(n_steps - 1) * a.batch:].numpy()
+    planted_last = planted[(n_steps - 1) * a.batch:n_steps * a.batch].numpy()
     hit = float(np.mean([planted_last[i] in ids_last[i] for i in range(a.batch)]))
+
+    # ---- other batch sizes, same measurement as `value` (resident inputs, graph replay, CUDA events) ----
+    batch_sweep = {}
+    for bsz in sorted({32, 64, 128} - {a.batch}):
+        if bsz * n_steps > nq or world > 1:
+            continue
+        gb = GraphedSearch(eng, p, bsz, max_terms=16)
+        sets = []
+        for s in range(n_steps):
+            qt, qp = lexical.pack_queries(terms[s * bsz:(s + 1) * bsz])
+            sets.append((qt.to(dev), qp.to(dev)))
+        for s in range(a.warmup):
+            gb.launch_resident(q_res[s * bsz:(s + 1) * bsz], *sets[s])
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(gb.stream)
+        for s in range(a.warmup, n_steps):
+            gb.launch_resident(q_res[s * bsz:(s + 1) * bsz], *sets[s])
+        b1.record(gb.stream)
+        barrier()
+        ms_b = max_over_ranks(b0.elapsed_time(b1)) / a.steps
+        batch_sweep[str(bsz)] = {"qps": bsz * 1e3 / ms_b, "ms_per_step": ms_b,
+                                 "uncertified_last_step": int(gb.flags.sum().item())}
+        del gb, sets
+    torch.cuda.empty_cache()
 
     # ---- single-query latency (B=1), end to end: host clock and CUDA events -----------------
     g1 = GraphedSearch(eng, p, 1, max_terms=16)
@@ -713,7 +738,7 @@ def main():
                                    if overlap_on else "off (CMRAG_OVERLAP=0): the retrievers run one after the other"),
                        "stage_times": "roofline.avg_launch_ms / bm25.avg_ms_per_step: each retriever alone, in a serial step"},
            "roofline": roofline, "e2e": e2e, "latency": latency, "gpu_launches": launches_per_step * a.steps,
-           "clocks": clock_info, "planted_top1_in_top10": hit, "c2": c2, "dropin": dropin,
+           "clocks": clock_info, "planted_top1_in_top10": hit, "batch_sweep": batch_sweep, "c2": c2, "dropin": dropin,
            "parity_check": parity, "result_digest": digest, "uncertified_queries_last_step": last_flags,
            "exchange": exchange,
            "chroma_hnsw_recall_at_10": None,

@@ -35,6 +35,7 @@
 #include <stdlib.h>
 
 #include "bm25_head.cuh"
+#include "lex_slice.cuh"
 #include "topk.cuh"
 
 namespace cmr {
@@ -148,8 +149,8 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
   // per-tile chain.
   const bool one_chunk = (qhi - qlo) <= BM_MAXQ;
   long long tk_base = 0;
-  const uint32_t* tk_skip = nullptr;
-  u32 pre0 = 0, pre1 = 0;  // skip entries of the tile about to be processed
+  int tk_term = -1, tk_row = -1;   // sparse token of this thread: its term and its skip-table row (-1: bisection)
+  u32 pre0 = 0, pre1 = 0;  // slice (relative to tk_base) of the tile about to be processed
   if (one_chunk && tid < qhi - qlo) {
     const int t = q_terms[qlo + tid];
     double w = 0.0;
@@ -159,11 +160,9 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
       w = ix.idf[t];
       if (ix.dense_slot != nullptr) slot = ix.dense_slot[t];
       if (slot < 0) {
-        tk_skip = ix.tile_skip + (size_t)t * (ix.n_tiles + 1);
-        if (first_tile < ix.n_tiles) {
-          pre0 = tk_skip[first_tile];
-          pre1 = tk_skip[first_tile + 1];
-        }
+        tk_term = t;
+        tk_row = lex_skip_row(ix, t);
+        if (first_tile < ix.n_tiles) lex_slice(ix, t, tk_row, first_tile, &pre0, &pre1);
       }
     }
     s_w[tid] = w;
@@ -189,10 +188,8 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
           s_lo[tid] = tk_base + pre0;   // dense / unknown tokens: an empty slice (0, 0)
           s_hi[tid] = tk_base + pre1;
           const int next = tile + (int)gridDim.y;
-          if (tk_skip != nullptr && next < ix.n_tiles) {  // in flight during this tile's passes
-            pre0 = tk_skip[next];
-            pre1 = tk_skip[next + 1];
-          }
+          if (tk_term >= 0 && next < ix.n_tiles)   // in flight during this tile's passes
+            lex_slice(ix, tk_term, tk_row, next, &pre0, &pre1);
         }
       } else if (tid < m) {
         const int t = q_terms[c0 + tid];
@@ -201,9 +198,10 @@ bm25_tile_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* _
         int slot = -1;
         if (t >= 0 && t < ix.n_terms) {  // unknown token: empty slice
           const long long base = ix.term_ptr[t];
-          const uint32_t* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
-          lo = base + sk[0];
-          hi = base + sk[1];
+          u32 a = 0, z = 0;
+          lex_slice(ix, t, lex_skip_row(ix, t), tile, &a, &z);
+          lo = base + a;
+          hi = base + z;
           w = ix.idf[t];
           if (ix.dense_slot != nullptr) slot = ix.dense_slot[t];
         }
@@ -465,7 +463,8 @@ static int check_index(const cmr_lex_index* ix) {
                 "index needs packed or wide postings");
   CMR_CHECK_ARG(ix->n_tiles >= 1 && (long long)ix->n_tiles * ix->tile_docs >= ix->n_docs, "n_tiles inconsistent with n_docs/tile_docs");
   CMR_CHECK_ARG(ix->n_terms >= 0, "n_terms negative");
-  CMR_CHECK_ARG(ix->n_terms == 0 || (ix->term_ptr && ix->tile_skip && ix->idf), "null index arrays");
+  CMR_CHECK_ARG(ix->n_terms == 0 || (ix->term_ptr && ix->idf && (ix->tile_skip || ix->skip_row)), "null index arrays");
+  CMR_CHECK_ARG(ix->skip_row == nullptr || ix->post_doc != nullptr, "skip_row needs post_doc (bisection of the short lists)");
   CMR_CHECK_ARG(ix->n_dense >= 0 && (ix->n_dense == 0 || (ix->dense_imp && ix->dense_slot)), "dense columns inconsistent");
   return CMR_OK;
 }

@@ -58,6 +58,7 @@
 #include <stdlib.h>
 
 #include "bm25_head.cuh"
+#include "lex_slice.cuh"
 #include "mma_common.cuh"
 
 namespace cmr {
@@ -66,10 +67,12 @@ constexpr int BX_M = 128;                     // documents per item (UMMA M, TME
 constexpr int BX_N = 32;                      // queries per block (UMMA N, TMEM columns)
 constexpr int BX_K = 64;                      // head terms: one 128-byte swizzle span of fp16
 constexpr int BX_STAGES = 8;                  // ring of head_mat boxes (128 KB in flight per SM)
-constexpr int BX_ACC = 8;                     // TMEM accumulators (8 x 32 columns)
+constexpr int BX_ACC = 16;                    // TMEM accumulators (16 x 32 columns = all of TMEM); see the work-order note
 constexpr int BX_A_BYTES = BX_M * BX_K * 2;   // 16 KiB
 constexpr int BX_Q_BYTES = BX_N * BX_K * 2;   // 4 KiB
-constexpr int BX_EPI_WARPS = 8;
+constexpr int BX_MAX_QB = 4;                  // blocks of 32 queries served by one pass over head_mat
+constexpr int BX_EPI_GROUPS = 3;              // epilogue warp groups (4 warps each) on alternating items
+constexpr int BX_EPI_WARPS = 4 * BX_EPI_GROUPS;
 constexpr int BX_THREADS = (2 + BX_EPI_WARPS) * 32;
 constexpr int BX_S_BYTES = 32 * BX_N * 4;     // one epilogue warp's 32 documents x 32 queries fp32 tile
 constexpr int BX_CAP = 256;                   // words per bucket of 32 documents; word 0 = entry count
@@ -90,9 +93,11 @@ constexpr int BX_F_LONG = 2, BX_F_NEG = 4, BX_F_BUCKET = 8, BX_F_LIST = 16, BX_F
 // |approx - exact| <= BX_RHO * exact + BX_ABS for non-negative contributions: every contribution is
 // rounded to fp16 once (2^-11 relative; below the fp16 normal range 2^-25 absolute), products with
 // the integer counts are exact, at most 64 + 16 fp32 additions (2^-23 relative each, the tensor
-// pipe may truncate) -> 2^-11 + 80 * 2^-23 < 2^-11 * 1.03; 1.0625 leaves a margin.
+// pipe may truncate) -> 2^-11 + 80 * 2^-23 < 2^-11 * 1.03; 1.0625 leaves a margin.  The sparse
+// contributions are summed in 2^-16 fixed point: exact for fp16 values >= 2^-6, up to 2^-17 of
+// rounding each below that (at most BX_MAXT of them), which BX_ABS covers.
 constexpr double BX_RHO = 1.0625 / 2048.0;
-constexpr double BX_ABS = 4e-6;
+constexpr double BX_ABS = 1.3e-4;
 
 struct __align__(16) BxPair {
   int term;
@@ -177,8 +182,13 @@ constexpr int BXB_THREADS = 256;
 constexpr int BXB_U = 4;   // postings in flight per thread
 
 __global__ void __launch_bounds__(BXB_THREADS)
-bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const int* __restrict__ n_pairs_p, int q_base,
-                    u32* __restrict__ buckets, int* __restrict__ flags) {
+bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs_all, const int* __restrict__ n_pairs_all,
+                    int q_base0, u32* __restrict__ buckets_all, size_t bucket_stride, int* __restrict__ flags) {
+  // grid (index tile, query block of the group)
+  const BxPair* pairs = pairs_all + (size_t)blockIdx.y * BX_MAX_PAIRS;
+  const int* n_pairs_p = n_pairs_all + blockIdx.y;
+  const int q_base = q_base0 + (int)blockIdx.y * BX_N;
+  u32* buckets = buckets_all + (size_t)blockIdx.y * bucket_stride;
   __shared__ long long s_lo[BX_MAX_PAIRS];
   __shared__ int s_off[BX_MAX_PAIRS + 1];
   __shared__ double s_w[BX_MAX_PAIRS];
@@ -192,8 +202,8 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const in
   if (tid == 0) s_off[0] = 0;
   for (int p = tid; p < np; p += BXB_THREADS) {
     const BxPair pr = pairs[p];
-    const u32* sk = ix.tile_skip + (size_t)pr.term * (ix.n_tiles + 1) + tile;
-    const u32 a = sk[0], z = sk[1];
+    u32 a = 0, z = 0;
+    lex_slice(ix, pr.term, lex_skip_row(ix, pr.term), tile, &a, &z);
     s_lo[p] = ix.term_ptr[pr.term] + a;
     s_off[p + 1] = (int)(z - a);
     s_w[p] = pr.w;
@@ -216,26 +226,33 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs, const in
   }
   __syncthreads();
   const int total = s_off[np];
-  for (int i0 = tid; i0 < total; i0 += BXB_U * BXB_THREADS) {
+  // A warp takes chunks of 32 * BXB_U consecutive postings of the concatenated slices: one bisection
+  // for the chunk's first posting, then every lane walks forward from there (slices are ~50 postings).
+  constexpr int CH = 32 * BXB_U;
+  for (int base = warp * CH; base < total; base += (BXB_THREADS / 32) * CH) {
+    int p = 0;
+    {
+      int hi = np;   // the pair whose slice holds posting `base`: largest p with s_off[p] <= base
+      while (hi - p > 1) {
+        const int mid = (p + hi) >> 1;
+        if (s_off[mid] <= base) p = mid;
+        else hi = mid;
+      }
+    }
     int pr_of[BXB_U];
     u32 pk[BXB_U];
 #pragma unroll
-    for (int u = 0; u < BXB_U; ++u) {   // the pair whose slice holds posting i: largest p with s_off[p] <= i
-      const int i = i0 + u * BXB_THREADS;
-      int lo = 0, hi = np;
+    for (int u = 0; u < BXB_U; ++u) {
+      const int i = base + u * 32 + lane;
       if (i < total) {
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (s_off[mid] <= i) lo = mid;
-          else hi = mid;
-        }
-        pk[u] = ldg_stream_word(ix.post_pack + s_lo[lo] + (i - s_off[lo]));
+        while (s_off[p + 1] <= i) ++p;
+        pk[u] = ldg_stream_word(ix.post_pack + s_lo[p] + (i - s_off[p]));
       }
-      pr_of[u] = lo;
+      pr_of[u] = p;
     }
 #pragma unroll
     for (int u = 0; u < BXB_U; ++u) {
-      if (i0 + u * BXB_THREADS >= total) break;
+      if (base + u * 32 + lane >= total) break;
       const u32 local = pk[u] & 0xFFFFu;
       const int q = s_q[pr_of[u]];
       const __half h = __double2half(__dmul_rn(s_w[pr_of[u]], __ldg(ix.imp_table + (pk[u] >> 16))));
@@ -254,23 +271,36 @@ struct BxParams {
   long long n_docs;
   int n_items;          // tiles of 128 documents this launch visits
   int stride;           // SAMPLE: visited tile = item * stride (full tiles only); MAIN: 1
-  int n_queries;        // queries of this block (<= 32)
-  const u32* buckets;   // [ceil(n_docs / 32) rounded up to whole index tiles][BX_CAP]
-  float* gmax;          // SAMPLE: [32][gridDim.x * BX_GROUPS_PER_CTA] maxima of every group, per query
-  const float* thr;     // MAIN: [32] admission bounds
-  u64* cand;            // MAIN: [gridDim.x][32][cap] keys (orderable fp32 score, ~document)
-  int* cnt;             // MAIN: [gridDim.x][32] entries appended (may exceed cap)
+  int n_qb;             // blocks of 32 queries in this group (MAIN: all in one pass; SAMPLE: blockIdx.y picks one)
+  int n_queries;        // queries of the group (<= 32 * n_qb)
+  const u32* buckets;   // [n_qb][bucket_stride words]: per block [ceil(n_docs / 32) up to whole index tiles][BX_CAP]
+  size_t bucket_stride;
+  float* gmax;          // SAMPLE: [32 * n_qb][gridDim.x * BX_GROUPS_PER_CTA] maxima of every group, per query
+  const float* thr;     // MAIN: [32 * n_qb] admission bounds
+  u64* cand;            // MAIN: [gridDim.x][32 * n_qb][cap] keys (orderable fp32 score, ~document)
+  int* cnt;             // MAIN: [gridDim.x][32 * n_qb] entries appended (may exceed cap)
   int cap;
 };
 
-// shared memory (offsets from the 1024-byte aligned base): ring, query tile, epilogue tiles, control
+// shared memory (offsets from the 1024-byte aligned base): ring, query tiles, epilogue tiles, control
 constexpr u32 BX_OFF_Q = BX_STAGES * BX_A_BYTES;
-constexpr u32 BX_OFF_S = BX_OFF_Q + BX_Q_BYTES;
+constexpr u32 BX_OFF_S = BX_OFF_Q + BX_MAX_QB * BX_Q_BYTES;
 constexpr u32 BX_OFF_BAR = BX_OFF_S + BX_EPI_WARPS * BX_S_BYTES;
-// barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +192+8a, qfull +256; TMEM base +264; list counters +272
-constexpr u32 BX_OFF_CNT = BX_OFF_BAR + 272;
-constexpr size_t BX_SMEM = 1024 + BX_OFF_CNT + BX_N * 4;
+// barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +256+8a, qfull +384; TMEM base +392
+constexpr u32 BX_BAR_TFULL = 128, BX_BAR_TEMPTY = 256, BX_BAR_QFULL = 384, BX_BAR_TMEM = 392;
+static_assert(BX_STAGES <= 8 && BX_ACC <= 16, "barrier slots");
+constexpr u32 BX_OFF_THR = BX_OFF_BAR + 400;                       // [32 * BX_MAX_QB] admission bounds
+constexpr u32 BX_OFF_CNT = BX_OFF_THR + BX_MAX_QB * BX_N * 4;      // [32 * BX_MAX_QB] list counters
+constexpr size_t BX_SMEM = 1024 + BX_OFF_CNT + BX_MAX_QB * BX_N * 4;
 
+// Work order shared by the three roles.  A CTA owns items first, first + step, ...; item number li
+// (0, 1, ...) is served for the query blocks qb = 0 .. nqb-1 in turn, use u = li * nqb + qb of the
+// accumulator ring (accumulator u % BX_ACC, phase (u / BX_ACC) & 1).  Epilogue group g serves the
+// items with li % BX_EPI_GROUPS == g.  A parity wait must never be a whole phase behind: a warp that
+// waits for use u has seen the commit of its previous use u', and the commit of u - BX_ACC (the use
+// before u on the same accumulator) precedes it only if u' >= u - BX_ACC.  Consecutive uses of a
+// warp are at most (BX_EPI_GROUPS - 1) * BX_MAX_QB + 1 apart, hence the assert.
+static_assert((BX_EPI_GROUPS - 1) * BX_MAX_QB + 1 <= BX_ACC, "accumulator ring too shallow for the epilogue groups");
 template <int MODE>
 __global__ void __launch_bounds__(BX_THREADS, 1)
 bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_rows,
@@ -280,13 +310,20 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const u32 base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* gen = smem_raw + (base - raw);
   const u32 bars = base + BX_OFF_BAR;
-  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(gen + BX_OFF_BAR + 264);
+  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(gen + BX_OFF_BAR + BX_BAR_TMEM);
+  float* s_thr = reinterpret_cast<float*>(gen + BX_OFF_THR);
   int* s_cnt = reinterpret_cast<int*>(gen + BX_OFF_CNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // SAMPLE: one query block per CTA row of the grid; MAIN: every block of the group, head_mat read once
+  const int nqb = MODE == BX_SAMPLE ? 1 : p.n_qb;
+  const int qb0 = MODE == BX_SAMPLE ? (int)blockIdx.y : 0;
 
   for (int i = threadIdx.x; i < BX_EPI_WARPS * BX_S_BYTES / 16; i += BX_THREADS)
     reinterpret_cast<float4*>(gen + BX_OFF_S)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (threadIdx.x < BX_N) s_cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < BX_MAX_QB * BX_N; i += BX_THREADS) {
+    s_cnt[i] = 0;
+    s_thr[i] = (MODE == BX_MAIN && i < p.n_queries) ? p.thr[i] : INFINITY;
+  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
@@ -295,14 +332,14 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(bars + 64 + 8 * s, 1);
     }
     for (int a = 0; a < BX_ACC; ++a) {
-      mbar_init(bars + 128 + 8 * a, 1);
-      mbar_init(bars + 192 + 8 * a, 4);  // one arrival per epilogue warp of the accumulator's group
+      mbar_init(bars + BX_BAR_TFULL + 8 * a, 1);
+      mbar_init(bars + BX_BAR_TEMPTY + 8 * a, 4);  // one arrival per epilogue warp of the group that drains it
     }
-    mbar_init(bars + 256, 1);
+    mbar_init(bars + BX_BAR_QFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the allocating warp also frees
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 264),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BX_BAR_TMEM),
                  "r"((u32)(BX_ACC * BX_N))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -316,8 +353,9 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      mbar_expect_tx(bars + 256, BX_Q_BYTES);
-      tma_load_2d(base + BX_OFF_Q, &tm_q, bars + 256, 0, 0, TMA_EVICT_LAST);
+      mbar_expect_tx(bars + BX_BAR_QFULL, (u32)(nqb * BX_Q_BYTES));
+      for (int qb = 0; qb < nqb; ++qb)
+        tma_load_2d(base + BX_OFF_Q + qb * BX_Q_BYTES, &tm_q, bars + BX_BAR_QFULL, 0, (qb0 + qb) * BX_N, TMA_EVICT_LAST);
       u32 s = 0, ph = 0;
       for (int it = first; it < p.n_items; it += step) {
         mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
@@ -330,53 +368,70 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      mbar_wait(bars + 256, 0);
+      mbar_wait(bars + BX_BAR_QFULL, 0);
       tc_fence_after();
-      const unsigned long long dq = umma_desc_sw128(base + BX_OFF_Q);
-      u32 s = 0, ph = 0, li = 0;
-      for (int it = first; it < p.n_items; it += step, ++li) {
-        const u32 acc = li % BX_ACC, aph = (li / BX_ACC) & 1u;
-        mbar_wait(bars + 192 + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
-        tc_fence_after();
-        mbar_wait(bars + 8 * s, ph);                // TMA bytes have landed
+      u32 s = 0, ph = 0, u = 0;
+      for (int it = first; it < p.n_items; it += step) {
+        mbar_wait(bars + 8 * s, ph);                  // TMA bytes have landed
         tc_fence_after();
         const unsigned long long da = umma_desc_sw128(base + s * BX_A_BYTES);
+        for (int qb = 0; qb < nqb; ++qb, ++u) {
+          const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
+          mbar_wait(bars + BX_BAR_TEMPTY + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
+          tc_fence_after();
+          const unsigned long long dq = umma_desc_sw128(base + BX_OFF_Q + qb * BX_Q_BYTES);
 #pragma unroll
-        for (int k = 0; k < BX_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
-          tc_mma_bf16(tmem_base + acc * BX_N, da + 2ull * k, dq + 2ull * k, BX_IDESC, k != 0);
-        tc_commit(bars + 64 + 8 * s);        // frees the ring slot when these MMAs retire
-        tc_commit(bars + 128 + 8 * acc);     // accumulator complete
+          for (int k = 0; k < BX_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
+            tc_mma_bf16(tmem_base + acc * BX_N, da + 2ull * k, dq + 2ull * k, BX_IDESC, k != 0);
+          tc_commit(bars + BX_BAR_TFULL + 8 * acc);     // accumulator complete
+        }
+        tc_commit(bars + 64 + 8 * s);          // frees the ring slot when these MMAs retire
         if (++s == BX_STAGES) { s = 0; ph ^= 1u; }
       }
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. +31; group g takes items li = g, g+2, ... =====
+    // ===== epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. +31 =====
     const int e = warp - 2, lq = warp & 3, g = e >> 2;
-    float* S = reinterpret_cast<float*>(gen + BX_OFF_S + e * BX_S_BYTES);
-    float4* S4 = reinterpret_cast<float4*>(S) + lane * 8;
-    float bnd[32], gm[32];
+    // The warp's 32 documents x 32 queries tile of sparse contributions is FIXED POINT (2^-16): shared
+    // memory has a native integer atomic add, a float one is a compare-and-swap loop.
+    int* S = reinterpret_cast<int*>(gen + BX_OFF_S + e * BX_S_BYTES);
+    int4* S4 = reinterpret_cast<int4*>(S) + lane * 8;
+    float gm[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      bnd[j] = INFINITY;
-      gm[j] = -INFINITY;
-      if (MODE == BX_MAIN && j < p.n_queries) bnd[j] = p.thr[j];
-    }
+    for (int j = 0; j < 32; ++j) gm[j] = -INFINITY;
+    // this warp's uses, in order: items li = g, g + BX_EPI_GROUPS, ..., each for the blocks 0 .. nqb-1
+    const long long it_step = (long long)BX_EPI_GROUPS * step;
+    auto bucket_at = [&](long long it, int qb) -> const u32* {
+      return p.buckets + (size_t)(qb0 + qb) * p.bucket_stride + ((size_t)it * p.stride * 4 + lq) * BX_CAP;
+    };
+    long long it = (long long)first + (long long)g * step;   // current use
+    int qb = 0;
     u32 li = (u32)g;
-    long long it = (long long)first + (long long)li * step;
-    u32 w0 = 0, w1 = 0;
+    long long it1 = it, it2;                                  // the next two uses
+    int qb1 = qb, qb2;
+    if (++qb1 == nqb) { qb1 = 0; it1 += it_step; }
+    it2 = it1;
+    qb2 = qb1;
+    if (++qb2 == nqb) { qb2 = 0; it2 += it_step; }
+    // bucket words of the next two uses are in flight while the current one is processed
+    u32 w0 = 0, w1 = 0, x0 = 0, x1 = 0;
     if (it < p.n_items) {
-      const u32* bp = p.buckets + ((size_t)it * p.stride * 4 + lq) * BX_CAP;
+      const u32* bp = bucket_at(it, qb);
       w0 = ldg_stream_word(bp + lane);
       w1 = ldg_stream_word(bp + 32 + lane);
     }
-    for (; it < p.n_items; li += 2, it += 2ll * step) {
+    if (it1 < p.n_items) {
+      const u32* bp = bucket_at(it1, qb1);
+      x0 = ldg_stream_word(bp + lane);
+      x1 = ldg_stream_word(bp + 32 + lane);
+    }
+    while (it < p.n_items) {
+      const u32* bp = bucket_at(it, qb);
       const long long tile = it * p.stride;
-      const u32* bp = p.buckets + ((size_t)tile * 4 + lq) * BX_CAP;
-      const long long nit = it + 2ll * step;
       u32 n0 = 0, n1 = 0;
-      if (nit < p.n_items) {   // the next item's bucket is in flight while this one is processed
-        const u32* nb = p.buckets + ((size_t)nit * p.stride * 4 + lq) * BX_CAP;
+      if (it2 < p.n_items) {
+        const u32* nb = bucket_at(it2, qb2);
         n0 = ldg_stream_word(nb + lane);
         n1 = ldg_stream_word(nb + 32 + lane);
       }
@@ -387,60 +442,74 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         auto apply = [&](u32 w) {
           const u32 r = w & 31u, q = (w >> 5) & 31u;
           const float val = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
-          atomicAdd(S + r * 32 + ((((q >> 2) ^ (r & 7u))) << 2) + (q & 3u), val);
+          atomicAdd(S + r * 32 + ((((q >> 2) ^ (r & 7u))) << 2) + (q & 3u), __float2int_rn(val * 65536.f));
         };
         if (lane >= 1 && lane - 1 < cnt) apply(w0);
         if (31 + lane < cnt) apply(w1);
-        for (int x = 63 + lane; x < cnt; x += 32) apply(bp[1 + x]);
+        if (cnt > 63)
+          for (int x = 63 + lane; x < cnt; x += 32) apply(bp[1 + x]);
       }
       __syncwarp();
       // ---- accumulator -> registers; release it at once ----
-      const u32 acc = li % BX_ACC, aph = (li / BX_ACC) & 1u;
-      mbar_wait(bars + 128 + 8 * acc, aph);
+      const u32 u = li * (u32)nqb + (u32)qb;
+      const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
+      mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
       tc_fence_after();
       float v[32];
       tmem_ld32(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, v);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 192 + 8 * acc);
+      if (lane == 0) mbar_arrive(bars + BX_BAR_TEMPTY + 8 * acc);
       // ---- add this document's row of the tile (16-byte chunks XOR-swizzled by the row) and clear it ----
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float4* pp = S4 + (c ^ (lane & 7));
-        const float4 s4 = *pp;
-        *pp = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[4 * c] += s4.x;
-        v[4 * c + 1] += s4.y;
-        v[4 * c + 2] += s4.z;
-        v[4 * c + 3] += s4.w;
+        int4* pp = S4 + (c ^ (lane & 7));
+        const int4 s4 = *pp;
+        *pp = make_int4(0, 0, 0, 0);
+        v[4 * c] = fmaf(__int2float_rn(s4.x), 1.0f / 65536.f, v[4 * c]);
+        v[4 * c + 1] = fmaf(__int2float_rn(s4.y), 1.0f / 65536.f, v[4 * c + 1]);
+        v[4 * c + 2] = fmaf(__int2float_rn(s4.z), 1.0f / 65536.f, v[4 * c + 2]);
+        v[4 * c + 3] = fmaf(__int2float_rn(s4.w), 1.0f / 65536.f, v[4 * c + 3]);
       }
       __syncwarp();
       if (MODE == BX_SAMPLE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) gm[j] = fmaxf(gm[j], v[j]);
       } else {
+        const float4* b4 = reinterpret_cast<const float4*>(s_thr + qb * BX_N);   // broadcast reads
         bool any = false;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) any |= v[j] >= bnd[j];
+        for (int c = 0; c < 8; ++c) {
+          const float4 bb = b4[c];
+          any |= (v[4 * c] >= bb.x) | (v[4 * c + 1] >= bb.y) | (v[4 * c + 2] >= bb.z) | (v[4 * c + 3] >= bb.w);
+        }
         if (any) {
           // Rare (about 16 * KP documents per query over the whole pass).
           const long long row = tile * BX_M + lq * 32 + lane;
           if (row < p.n_docs) {
             u32 hits = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hits |= (v[j] >= bnd[j] ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) hits |= (v[j] >= s_thr[qb * BX_N + j] ? 1u : 0u) << j;
+            const int nq_all = nqb * BX_N;
             while (hits) {
               const int j = __ffs(hits) - 1;
               hits &= hits - 1;
-              const int slot = atomicAdd(&s_cnt[j], 1);
+              const int qg = qb * BX_N + j;
+              const int slot = atomicAdd(&s_cnt[qg], 1);
               if (slot < p.cap)
-                p.cand[((size_t)blockIdx.x * BX_N + j) * p.cap + slot] = make_key(pick32(v, j), (u32)row);
+                p.cand[((size_t)blockIdx.x * nq_all + qg) * p.cap + slot] = make_key(pick32(v, j), (u32)row);
             }
           }
         }
       }
-      w0 = n0;
-      w1 = n1;
+      w0 = x0;
+      w1 = x1;
+      x0 = n0;
+      x1 = n1;
+      if (++qb == nqb) { qb = 0; it += it_step; li += BX_EPI_GROUPS; }
+      it1 = it2;
+      qb1 = qb2;
+      if (++qb2 == nqb) { qb2 = 0; it2 += it_step; }
     }
     if (MODE == BX_SAMPLE) {
       // group maxima: the documents an epilogue warp saw form one group (a warp that saw none
@@ -457,13 +526,14 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 16));
         if (lane == j) mine = m;
       }
-      p.gmax[(size_t)lane * n_groups + (size_t)blockIdx.x * BX_GROUPS_PER_CTA + e] = mine;
+      p.gmax[(size_t)(qb0 * BX_N + lane) * n_groups + (size_t)blockIdx.x * BX_GROUPS_PER_CTA + e] = mine;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (MODE == BX_MAIN && threadIdx.x < BX_N) p.cnt[(size_t)blockIdx.x * BX_N + threadIdx.x] = s_cnt[threadIdx.x];
+  if (MODE == BX_MAIN)
+    for (int i = threadIdx.x; i < nqb * BX_N; i += BX_THREADS) p.cnt[(size_t)blockIdx.x * nqb * BX_N + i] = s_cnt[i];
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)(BX_ACC * BX_N))
@@ -492,7 +562,19 @@ bm25x_bound_kernel(const float* __restrict__ gmax, int n_groups, int kp, int n_q
   }
   u32* v = s_vals[warp];
   const float* src = gmax + (size_t)q * n_groups;
-  for (int g = lane; g < n_groups; g += 32) v[g] = f32_orderable(src[g]);
+  for (int g0 = lane; g0 < n_groups; g0 += 32 * 8) {   // 8 independent loads in flight per lane
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + 32 * u;
+      x[u] = g < n_groups ? src[g] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + 32 * u;
+      if (g < n_groups) v[g] = f32_orderable(x[u]);
+    }
+  }
   __syncwarp();
   u32 prefix = 0;
   for (int bit = 31; bit >= 0; --bit) {
@@ -510,7 +592,7 @@ bm25x_bound_kernel(const float* __restrict__ gmax, int n_groups, int kp, int n_q
 template <int KPL>
 __global__ void __launch_bounds__(FIN_THREADS)
 bm25x_finalize_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* __restrict__ q_ptr, int q_base,
-                      const u64* __restrict__ cand, const int* __restrict__ cnt, int n_lists, int cap, int cap_total,
+                      const u64* __restrict__ cand, const int* __restrict__ cnt, int n_lists, int q_stride, int cap, int cap_total,
                       const float* __restrict__ thr, long long row_offset, int k, double* __restrict__ out_scores,
                       long long* __restrict__ out_ids, int* __restrict__ out_counts, int* __restrict__ out_flags) {
   constexpr int KP = 32 * KPL;
@@ -529,7 +611,7 @@ bm25x_finalize_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const i
     return;
   }
   int n_total, over;
-  cand_collect_select<KP>(cand, cnt, n_lists, BX_N, cap, cap_total, ql, s_keys, s_out, s_surv, s_ctl, &n_total, &over);
+  cand_collect_select<KP>(cand, cnt, n_lists, q_stride, cap, cap_total, ql, s_keys, s_out, s_surv, s_ctl, &n_total, &over);
   if (tid == 0) {
     int n = 0;
     for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
@@ -549,10 +631,9 @@ bm25x_finalize_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const i
       const int t = s_tok[j];
       const u32 row = key_row(s_out[c]);
       const u32 tile = row / (u32)ix.tile_docs, local = row - tile * (u32)ix.tile_docs;
-      const u32* sk = ix.tile_skip + (size_t)t * (ix.n_tiles + 1) + tile;
       const long long tbase = ix.term_ptr[t];
-      u32 lo = sk[0];
-      const u32 end = sk[1];
+      u32 lo = 0, end = 0;
+      lex_slice(ix, t, lex_skip_row(ix, t), (int)tile, &lo, &end);
       u32 hi = end;
       while (lo < hi) {
         const u32 mid = (lo + hi) >> 1;
@@ -614,7 +695,8 @@ bm25x_finalize_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const i
 // ---- host side ------------------------------------------------------------------------
 struct BxPlan {
   int kpl, kp, cap, cap_total;
-  int n_blocks, n_items, n_sample, stride, grid_main, grid_sample, n_groups, n_b;
+  int n_blocks, n_items, n_sample, stride, grid_main, grid_sample, n_groups, n_b, group_qb;
+  size_t bucket_stride;
   size_t off_qmat, off_pairs, off_npairs, off_thr, off_gmax, off_cand, off_cnt, off_buckets, total;
   size_t smem_fin;
 };
@@ -649,11 +731,14 @@ static void bx_plan(const cmr_lex_index& ix, int n_queries, int k, int sms, BxPl
   p->off_qmat = off;    off += up((size_t)p->n_blocks * BX_N * BX_K * 2);
   p->off_pairs = off;   off += up((size_t)p->n_blocks * BX_MAX_PAIRS * sizeof(BxPair));
   p->off_npairs = off;  off += up((size_t)p->n_blocks * 4);
-  p->off_thr = off;     off += up(32 * 4);
-  p->off_gmax = off;    off += up((size_t)p->n_groups * 32 * 4);
-  p->off_cand = off;    off += up((size_t)p->grid_main * BX_N * p->cap * 8);
-  p->off_cnt = off;     off += up((size_t)p->grid_main * BX_N * 4);
-  p->off_buckets = off; off += up((size_t)ix.n_tiles * p->n_b * BX_CAP * 4);
+  p->group_qb = p->n_blocks < BX_MAX_QB ? p->n_blocks : BX_MAX_QB;   // query blocks served by one pass
+  p->bucket_stride = (size_t)ix.n_tiles * p->n_b * BX_CAP;
+  const size_t gq = (size_t)p->group_qb * BX_N;
+  p->off_thr = off;     off += up(gq * 4);
+  p->off_gmax = off;    off += up((size_t)p->n_groups * gq * 4);
+  p->off_cand = off;    off += up((size_t)p->grid_main * gq * p->cap * 8);
+  p->off_cnt = off;     off += up((size_t)p->grid_main * gq * 4);
+  p->off_buckets = off; off += up((size_t)p->group_qb * p->bucket_stride * 4);
   p->total = off;
   p->smem_fin = (size_t)p->cap_total * 8 + (size_t)p->kp * 16 + (size_t)4 * p->kp * 8 + (size_t)p->kp * BX_MAXT * 8 + 16;
 }
@@ -724,17 +809,21 @@ int bm25_head_topk(const cmr_lex_index& ix, const int* q_terms, const int* q_ptr
   if (rc != CMR_OK) return rc;
   bm25x_prep_kernel<<<p.n_blocks, BX_N * 16, 0, st>>>(ix, q_terms, q_ptr, n_queries, qmat, pairs, n_pairs, out_flags);
 
-  for (int blk = 0; blk < p.n_blocks; ++blk) {
-    const int q_base = blk * BX_N;
-    const int nq = n_queries - q_base < BX_N ? n_queries - q_base : BX_N;
-    rc = make_tmap(&tm_q, qmat + (size_t)blk * BX_N * BX_K, BX_N, BX_K, BX_N, true);
+  // groups of up to BX_MAX_QB blocks of 32 queries: head_mat streams once per group
+  for (int blk0 = 0; blk0 < p.n_blocks; blk0 += p.group_qb) {
+    const int n_qb = p.n_blocks - blk0 < p.group_qb ? p.n_blocks - blk0 : p.group_qb;
+    const int q_base = blk0 * BX_N;
+    const int nq = n_queries - q_base < n_qb * BX_N ? n_queries - q_base : n_qb * BX_N;
+    rc = make_tmap(&tm_q, qmat + (size_t)blk0 * BX_N * BX_K, (long long)n_qb * BX_N, BX_K, BX_N, true);
     if (rc != CMR_OK) return rc;
-    bm25x_bucket_kernel<<<ix.n_tiles, BXB_THREADS, 0, st>>>(ix, pairs + (size_t)blk * BX_MAX_PAIRS, n_pairs + blk,
-                                                               q_base, buckets, out_flags);
+    bm25x_bucket_kernel<<<dim3(ix.n_tiles, n_qb), BXB_THREADS, 0, st>>>(ix, pairs + (size_t)blk0 * BX_MAX_PAIRS, n_pairs + blk0,
+                                                                        q_base, buckets, p.bucket_stride, out_flags);
     BxParams kp{};
     kp.n_docs = ix.n_docs;
+    kp.n_qb = n_qb;
     kp.n_queries = nq;
     kp.buckets = buckets;
+    kp.bucket_stride = p.bucket_stride;
     kp.gmax = gmax;
     kp.thr = thr;
     kp.cand = cand;
@@ -743,28 +832,29 @@ int bm25_head_topk(const cmr_lex_index& ix, const int* q_terms, const int* q_ptr
     if (p.n_sample > 0) {
       kp.n_items = p.n_sample;
       kp.stride = p.stride;
-      bm25x_mma_kernel<BX_SAMPLE><<<p.grid_sample, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
+      bm25x_mma_kernel<BX_SAMPLE><<<dim3(p.grid_sample, n_qb), BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
     }
     bm25x_bound_kernel<<<(nq + BXT_WARPS - 1) / BXT_WARPS, BXT_WARPS * 32, 0, st>>>(gmax, p.n_sample > 0 ? p.n_groups : 0,
                                                                                    p.kp, nq, thr);
     kp.n_items = p.n_items;
     kp.stride = 1;
     bm25x_mma_kernel<BX_MAIN><<<p.grid_main, BX_THREADS, BX_SMEM, st>>>(tm_q, tm_rows, kp);
+    const int q_stride = n_qb * BX_N;
     switch (p.kpl) {
       case 1:
         bm25x_finalize_kernel<1><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
-                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
-                                                                     out_ids, out_counts, out_flags);
+                                                                     q_stride, p.cap, p.cap_total, thr, row_offset, k,
+                                                                     out_scores, out_ids, out_counts, out_flags);
         break;
       case 2:
         bm25x_finalize_kernel<2><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
-                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
-                                                                     out_ids, out_counts, out_flags);
+                                                                     q_stride, p.cap, p.cap_total, thr, row_offset, k,
+                                                                     out_scores, out_ids, out_counts, out_flags);
         break;
       default:
         bm25x_finalize_kernel<4><<<nq, FIN_THREADS, p.smem_fin, st>>>(ix, q_terms, q_ptr, q_base, cand, cnt, p.grid_main,
-                                                                     p.cap, p.cap_total, thr, row_offset, k, out_scores,
-                                                                     out_ids, out_counts, out_flags);
+                                                                     q_stride, p.cap, p.cap_total, thr, row_offset, k,
+                                                                     out_scores, out_ids, out_counts, out_flags);
         break;
     }
   }

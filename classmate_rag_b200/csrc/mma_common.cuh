@@ -123,21 +123,30 @@ __device__ __forceinline__ void cand_collect_select(const u64* __restrict__ cand
   }
   for (int i = tid; i < KP; i += FIN_THREADS) s_out[i] = 0ull;
   __syncthreads();
-  // one warp per CTA list: claim a range of the shared buffer, copy the keys
-  for (int l = warp; l < n_lists; l += FIN_THREADS / 32) {
-    const int have = cnt[(size_t)l * n_queries + qi];
-    if (have == 0) continue;  // warp-uniform
+  // Every list's length is read in one round trip (thread l owns list l), each list claims a
+  // range of the shared buffer, then one warp per list copies its keys: two dependent global
+  // round trips in all, whatever the number of lists.
+  for (int l0 = 0; l0 < n_lists; l0 += FIN_THREADS) {
+    const int l = l0 + tid;
+    int have = 0;
+    if (l < n_lists) have = cnt[(size_t)l * n_queries + qi];
     const int take = have < cap ? have : cap;
+    if (have > cap) s_over = 1;
     int base = 0;
-    if (lane == 0) {
-      base = atomicAdd(&s_total, take);
-      if (have > cap) s_over = 1;
-    }
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    const u64* src = cand + ((size_t)l * n_queries + qi) * cap;
-    for (int i = lane; i < take; i += 32) {
-      if (base + i < cap_total) s_keys[base + i] = src[i];
-      else s_over = 1;
+    if (take > 0) base = atomicAdd(&s_total, take);
+    // hand (base, take) of the 32 lists of this warp's lanes to the whole warp, list by list
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, take > 0);
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int b2 = __shfl_sync(0xFFFFFFFFu, base, src_lane);
+      const int t2 = __shfl_sync(0xFFFFFFFFu, take, src_lane);
+      const int l2 = l0 + (tid & ~31) + src_lane;
+      const u64* src = cand + ((size_t)l2 * n_queries + qi) * cap;
+      for (int i = lane; i < t2; i += 32) {
+        if (b2 + i < cap_total) s_keys[b2 + i] = src[i];
+        else s_over = 1;
+      }
     }
   }
   __syncthreads();

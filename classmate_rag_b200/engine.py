@@ -121,8 +121,20 @@ class HybridEngine:
         ws = self._dense_ws.get(key)
         if ws is None:
             ws = self._dense_ws[key] = ops.DenseWorkspace(n, d, b, k, self.device)
-        out = ops.dense_topk(self.emb, q_bf16, k, row_mask=row_mask, row_offset=self.row_offset,
-                             cert_eps=self._cert_eps(d), workspace=ws, algo=algo)
+        if algo == "wide":
+            # the widest over-selection one pass certifies (top-120, KP = 128), cut back to k: serves
+            # queries whose top k sits inside a cluster of exact duplicates (tools/dup_heavy.py)
+            kw = max(k, ops.WIDE_K)
+            wkey = (n, d, b, kw)
+            wws = self._dense_ws.get(wkey)
+            if wws is None:
+                wws = self._dense_ws[wkey] = ops.DenseWorkspace(n, d, b, kw, self.device)
+            s_w, i_w, c_w, f_w = ops.dense_topk(self.emb, q_bf16, kw, row_mask=row_mask, row_offset=self.row_offset,
+                                                cert_eps=self._cert_eps(d), workspace=wws)
+            out = (s_w[:, :k].contiguous(), i_w[:, :k].contiguous(), torch.clamp(c_w, max=k), f_w)
+        else:
+            out = ops.dense_topk(self.emb, q_bf16, k, row_mask=row_mask, row_offset=self.row_offset,
+                                 cert_eps=self._cert_eps(d), workspace=ws, algo=algo)
         if self.comm is not None:
             out = self.comm.merge_topk(*out)
         return out
@@ -161,8 +173,9 @@ class HybridEngine:
         """Returns device tensors (ids i64 [B,top_k], fused f64, vector_distance f64
         (NaN = None), bm25_score f64 (NaN = None), counts i32 [B]); nothing is
         synchronised.  ``self.last_dense_flags`` (int32 [B], device) is non-zero for queries
-        whose dense pool could not be certified: re-run those with ``dense_algo="exact"`` (the
-        exhaustive float64 scan; GraphedSearch.result() does).  ``stage_events``: a list that
+        whose dense pool could not be certified: re-run those with ``dense_algo="wide"`` (the
+        same kernels over-selecting 128 candidates) and, if still flagged, ``"exact"`` (the
+        exhaustive float64 scan); GraphedSearch.result() does.  ``stage_events``: a list that
         receives timing events at the stage boundaries (start, dense done, MMR done, BM25
         done, fused) -- single-shard path only."""
         def mark():
@@ -358,21 +371,24 @@ class GraphedSearch:
         for h, t in zip((self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt), out):
             h.copy_(t, non_blocking=True)
 
-    def _rerun_exact(self):
-        """A query of the batch could not be certified by the fp32 pass (thousands of exact
-        duplicates around rank k): the batch is run again, eagerly, with the exhaustive float64
-        scan as the dense stage (same inputs -- they are still in the static buffers -- same
-        exchange on every rank, since the merged flags are identical everywhere)."""
-        self.reruns += 1
-        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
-            q_bf16 = ops.f32_to_bf16(self.q_f32)
-            out = self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
-                                     self.q_ptr if self.hybrid else None, self.p, dense_algo="exact")
-            self._copy_out(out)
-            self.h_flags.copy_(self.engine.last_dense_flags, non_blocking=True)
-            self.stream.synchronize()
-        if int(self.h_flags.sum()) != 0:
-            raise RuntimeError("the exhaustive dense scan returned an uncertified result")
+    def _rerun_certified(self):
+        """A query of the batch could not be certified by the fp32 pass (a cluster of exact duplicates
+        around rank k): the batch is run again, eagerly, with the widest over-selection, and if that
+        still leaves a flag, with the exhaustive float64 scan as the dense stage (same inputs -- they are
+        still in the static buffers -- same exchange on every rank, since the merged flags are identical
+        everywhere)."""
+        for algo in ("wide", "exact"):
+            self.reruns += 1
+            with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+                q_bf16 = ops.f32_to_bf16(self.q_f32)
+                out = self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
+                                         self.q_ptr if self.hybrid else None, self.p, dense_algo=algo)
+                self._copy_out(out)
+                self.h_flags.copy_(self.engine.last_dense_flags, non_blocking=True)
+                self.stream.synchronize()
+            if int(self.h_flags.sum()) == 0:
+                return
+        raise RuntimeError("the exhaustive dense scan returned an uncertified result")
 
     def launch_resident(self, q_f32: torch.Tensor, q_terms: Optional[torch.Tensor] = None,
                         q_ptr: Optional[torch.Tensor] = None):
@@ -406,13 +422,13 @@ class GraphedSearch:
 
     def result(self):
         """Wait for the last launch() of THIS object and hand back its pinned result buffers.
-        Fails loudly when a rank never arrived at the peer exchange; re-runs the batch on the
-        exhaustive scan when the dense certificate failed for one of its queries."""
+        Fails loudly when a rank never arrived at the peer exchange; re-runs the batch (wider
+        over-selection, then the exhaustive scan) when the dense certificate failed for a query."""
         self.done.synchronize()
         if int(self.h_timeout[0]) != 0:
             raise RuntimeError("shard exchange timed out: a rank did not deliver its message (results are invalid)")
         if int(self.h_flags.sum()) != 0:
-            self._rerun_exact()
+            self._rerun_certified()
         return self.h_ids.numpy(), self.h_fused.numpy(), self.h_vd.numpy(), self.h_bm.numpy(), self.h_cnt.numpy()
 
     def __call__(self, q_f32: np.ndarray, term_lists=None):

@@ -24,6 +24,7 @@ DEFAULT_TILE_DOCS = 2048   # 16 documents per thread of a 128-thread CTA (csrc/b
 DENSE_DENSITY = 0.125    # terms in at least this share of the documents get a factor column
 DENSE_MAX_TERMS = 64     # 8 B x n_docs each
 HEAD_TERMS = 64          # columns of the fp16 head matrix (one 128-byte row per document; csrc/bm25_mma.cu)
+SKIP_BUDGET_BYTES = 1 << 30   # skip-table rows ((n_tiles + 1) x 4 B each) go to the most frequent terms within this
 
 
 class LexIndexStruct(C.Structure):
@@ -32,7 +33,7 @@ class LexIndexStruct(C.Structure):
         ("term_ptr", C.c_void_p), ("tile_skip", C.c_void_p), ("post_pack", C.c_void_p), ("imp_table", C.c_void_p),
         ("post_doc", C.c_void_p), ("post_imp", C.c_void_p), ("post_tf", C.c_void_p), ("doc_len", C.c_void_p),
         ("idf", C.c_void_p), ("dense_imp", C.c_void_p), ("dense_slot", C.c_void_p),
-        ("head_mat", C.c_void_p), ("head_slot", C.c_void_p),
+        ("head_mat", C.c_void_p), ("head_slot", C.c_void_p), ("skip_row", C.c_void_p),
         ("n_docs", C.c_int64), ("n_terms", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
         ("n_codes", C.c_int32), ("n_dense", C.c_int32), ("n_head", C.c_int32),
         ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
@@ -61,7 +62,7 @@ def idf_table(df: np.ndarray, n_docs: int, vocab_order: np.ndarray, epsilon: flo
 @dataclass
 class LexicalIndex:
     term_ptr: torch.Tensor      # int64 [V+1]
-    tile_skip: torch.Tensor     # int32 (uint32 bits) [V, n_tiles+1]
+    tile_skip: torch.Tensor     # int32 (uint32 bits) [n_skip_rows, n_tiles+1]: rows of the most frequent terms
     post_doc: torch.Tensor      # int32 [P]
     post_imp: Optional[torch.Tensor]   # float64 [P] (wide format only)
     post_tf: torch.Tensor       # int16 (uint16 bits) [P]
@@ -84,6 +85,7 @@ class LexicalIndex:
     head_mat: Optional[torch.Tensor] = None    # float16 [N, 64]: fp16(idf * factor) of the head terms, 0 where absent
     head_slot: Optional[torch.Tensor] = None   # int32 [V]: column of the term in head_mat or -1
     head_terms: Optional[np.ndarray] = field(default=None, repr=False)   # term id of each head column
+    skip_row: Optional[torch.Tensor] = None    # int32 [V]: row of the term in tile_skip or -1 (bisection on post_doc)
     idf_host: np.ndarray = field(default=None, repr=False)
     df_host: np.ndarray = field(default=None, repr=False)        # corpus-wide df
     shard_df_host: np.ndarray = field(default=None, repr=False)  # postings per term in THIS shard
@@ -104,7 +106,7 @@ class LexicalIndex:
                 self.term_ptr.data_ptr(), self.tile_skip.data_ptr(), opt(self.post_pack), opt(self.imp_table),
                 self.post_doc.data_ptr(), opt(self.post_imp), self.post_tf.data_ptr(), self.doc_len.data_ptr(),
                 self.idf.data_ptr(), opt(self.dense_imp), opt(self.dense_slot),
-                opt(self.head_mat), opt(self.head_slot),
+                opt(self.head_mat), opt(self.head_slot), opt(self.skip_row),
                 self.n_docs, self.n_terms, self.tile_docs, self.n_tiles,
                 0 if self.imp_table is None else int(self.imp_table.numel()),
                 0 if self.dense_imp is None else int(self.dense_imp.shape[0]),
@@ -167,7 +169,8 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
                         stats: Optional[GlobalStats] = None, fmt: str = "auto",
                         k1: float = BM25_K1, b: float = BM25_B, epsilon: float = BM25_EPS,
                         dense_density: Optional[float] = DENSE_DENSITY,
-                        dense_max_terms: int = DENSE_MAX_TERMS, head_terms: int = HEAD_TERMS) -> LexicalIndex:
+                        dense_max_terms: int = DENSE_MAX_TERMS, head_terms: int = HEAD_TERMS,
+                        skip_budget_bytes: int = SKIP_BUDGET_BYTES) -> LexicalIndex:
     """Build the CSR index of the documents ``tokens[doc_ptr[i]:doc_ptr[i+1]]``.
 
     ``stats`` (optional) supplies corpus-wide df / N / total tokens when this
@@ -175,7 +178,10 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
     terms present in at least that share of the documents also get a dense
     float64 factor column, swept instead of scattered by the kernel.  ``head_terms`` (0 = off):
     the terms with the longest posting lists in this shard, at most 64, get a column of the fp16
-    head matrix the batched kernels score on the tensor cores (packed postings only)."""
+    head matrix the batched kernels score on the tensor cores (packed postings only).
+    ``skip_budget_bytes``: the skip table (posting offset of every tile start) gets rows for the
+    terms with the longest lists in this shard, as many as fit; the rest (short lists) are
+    bisected by the kernels, so the table does not grow with the vocabulary."""
     if device is None:
         device = tokens.device
     doc_ptr = doc_ptr.to(device).long()
@@ -203,11 +209,25 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
         uniq = torch.zeros(0, dtype=torch.int64, device=device)
         counts = term = doc = uniq
     term_ptr = torch.searchsorted(term, torch.arange(n_terms + 1, device=device))
-    # tile skip table: posting offset (relative to the term) where each tile starts
-    bounds = (torch.arange(n_terms, device=device)[:, None] * max(n_docs, 1)
-              + torch.clamp(torch.arange(n_tiles + 1, device=device) * tile_docs, max=max(n_docs, 1))[None, :])
-    skip = torch.searchsorted(uniq, bounds.reshape(-1)).reshape(n_terms, n_tiles + 1) - term_ptr[:-1, None]
-    del bounds
+    # tile skip table: posting offset (relative to the term) where each tile starts -- one row per
+    # term for the most frequent terms (within the budget), none for the rest
+    shard_df_all = (term_ptr[1:] - term_ptr[:-1])
+    max_rows = max(1, int(skip_budget_bytes) // ((n_tiles + 1) * 4))
+    n_listed = int((shard_df_all > 0).sum())
+    if n_listed <= max_rows:
+        row_terms = torch.nonzero(shard_df_all > 0).flatten()
+    else:
+        row_terms = torch.argsort(shard_df_all, descending=True, stable=True)[:max_rows].sort().values
+    skip_row = torch.full((n_terms,), -1, dtype=torch.int32, device=device)
+    skip_row[row_terms] = torch.arange(row_terms.numel(), dtype=torch.int32, device=device)
+    tile_starts = torch.clamp(torch.arange(n_tiles + 1, device=device) * tile_docs, max=max(n_docs, 1))
+    skip = torch.zeros((max(1, row_terms.numel()), n_tiles + 1), dtype=torch.int64, device=device)
+    for lo_r in range(0, row_terms.numel(), 4096):      # bounded temporaries for large vocabularies
+        rt = row_terms[lo_r:lo_r + 4096]
+        bounds = rt[:, None] * max(n_docs, 1) + tile_starts[None, :]
+        skip[lo_r:lo_r + rt.numel()] = (torch.searchsorted(uniq, bounds.reshape(-1)).reshape(rt.numel(), n_tiles + 1)
+                                        - term_ptr[rt][:, None])
+        del bounds
     if tile_docs > 65536:
         raise ValueError("tile_docs must be <= 65536")
     if fmt not in ("auto", "packed", "wide"):
@@ -282,7 +302,7 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
         post_doc=doc.to(torch.int32).contiguous(), post_imp=None if imp is None else imp.contiguous(),
         post_pack=post_pack, imp_table=imp_table, pair_tf=pair_tf, pair_dl=pair_dl,
         dense_imp=dense_imp, dense_slot=dense_slot, dense_terms=dense_terms,
-        head_mat=head_mat, head_slot=head_slot, head_terms=head_ids,
+        head_mat=head_mat, head_slot=head_slot, head_terms=head_ids, skip_row=skip_row,
         post_tf=tf16.contiguous(), doc_len=doc_len.to(torch.int32).contiguous(),
         idf=torch.from_numpy(idf_host).to(device), n_docs=n_docs, n_terms=n_terms, tile_docs=tile_docs,
         n_tiles=n_tiles, avgdl=float(avgdl), k1=k1, b=b, idf_host=idf_host, df_host=stats.df,
@@ -305,7 +325,7 @@ def pack_queries(queries: Sequence[Sequence[int]]):
 # BM25Okapi rebuild of the reference, rag/retrieval/bm25.py:220-248, rag/pipeline/rag.py:532)
 # --------------------------------------------------------------------------
 _SNAPSHOT_TENSORS = ("term_ptr", "tile_skip", "post_doc", "post_imp", "post_tf", "doc_len", "idf", "post_pack",
-                     "imp_table", "pair_tf", "pair_dl", "dense_imp", "dense_slot", "head_mat", "head_slot")
+                     "imp_table", "pair_tf", "pair_dl", "dense_imp", "dense_slot", "head_mat", "head_slot", "skip_row")
 _SNAPSHOT_VERSION = 1
 
 

@@ -343,16 +343,33 @@ def shard_merge(gathered: torch.Tensor, pool: int, kb: int, dim: int):
     return d_s, d_i, d_c, d_f, rows, b_s, b_i, b_c
 
 
+WIDE_K = _lib.CMR_MAX_K   # the widest over-selection one pass can certify (KP = 128)
+
+
 def dense_topk_certified(emb: torch.Tensor, queries: torch.Tensor, k: int, *, row_mask: Optional[torch.Tensor] = None,
                          row_offset: int = 0, cert_eps: Optional[float] = None,
                          workspace: Optional[DenseWorkspace] = None, algo: str = "auto"):
-    """dense_topk, then the queries whose result could not be certified are re-run on the
-    exhaustive float64 scan and patched in place.  Synchronises (it reads the flags)."""
+    """dense_topk, then the queries whose result could not be certified are served by a ladder and
+    patched in place: (1) the same fast kernels with the widest over-selection (top-120, KP = 128:
+    certifies through clusters of ~100 exact duplicates around rank k -- duplicated course chunks --
+    for the price of one more pass over the matrix); (2) what is still flagged goes to the exhaustive
+    float64 scan, which ranks on the exact score of every row.  Synchronises (it reads the flags)."""
     scores, ids, counts, flags = dense_topk(emb, queries, k, row_mask=row_mask, row_offset=row_offset,
                                             cert_eps=cert_eps, workspace=workspace, algo=algo)
     bad = torch.nonzero(flags).flatten()
     if bad.numel():
         q = queries[None, :] if queries.dim() == 1 else queries
+        if k < WIDE_K and algo != "exact":
+            qb = q[bad].contiguous()
+            s2, i2, c2, f2 = dense_topk(emb, qb, WIDE_K, row_mask=row_mask, row_offset=row_offset, cert_eps=cert_eps,
+                                        algo=algo)
+            ok = torch.nonzero(f2 == 0).flatten()
+            if ok.numel():
+                dst = bad[ok]
+                scores[dst], ids[dst] = s2[ok, :k], i2[ok, :k]
+                counts[dst], flags[dst] = torch.clamp(c2[ok], max=k), f2[ok]
+            bad = bad[torch.nonzero(f2).flatten()]
+    if bad.numel():
         s2, i2, c2, f2 = dense_topk(emb, q[bad].contiguous(), k, row_mask=row_mask, row_offset=row_offset,
                                     algo="exact")
         scores[bad], ids[bad], counts[bad], flags[bad] = s2, i2, c2, f2

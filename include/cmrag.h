@@ -119,8 +119,9 @@ int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t str
  *     (rag/retrieval/bm25.py:175-212).
  *
  * The inverted index is a term-major CSR over the shard's documents, postings
- * of a term sorted by document, plus a skip table that gives, per term, the
- * posting offset at which every tile of `tile_docs` documents starts.
+ * of a term sorted by document, plus a skip table that gives, for the frequent
+ * terms, the posting offset at which every tile of `tile_docs` documents starts
+ * (rare terms: bisection on the documents of their short lists).
  * Scores are accumulated in float64 in query-token order with rank_bm25's own
  * operation order (idf * factor rounded, then added; no fma) (the per-posting factor is an exact float64, stored either per
  * posting or once per distinct (tf, doc_len) pair), so they are bit-identical to the reference arithmetic and
@@ -129,7 +130,8 @@ int cmr_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cmr_stream_t str
  * ---------------------------------------------------------------------- */
 typedef struct cmr_lex_index {
   const int64_t* term_ptr;   /* [n_terms + 1] posting offsets                          */
-  const uint32_t* tile_skip; /* [n_terms, n_tiles + 1] offsets relative to term_ptr[t]  */
+  const uint32_t* tile_skip; /* [n_skip_rows, n_tiles + 1] posting offset (relative to term_ptr[t]) at
+                                which every tile starts, one row per term that owns one        */
   /* packed postings (preferred, 4 B each): (code << 16) | (doc - tile_lo); code indexes
    * imp_table, the float64 BM25 factor of that posting's (tf, doc_len) pair.            */
   const uint32_t* post_pack; /* [P] or NULL                                             */
@@ -153,6 +155,11 @@ typedef struct cmr_lex_index {
    * (the query side is the count of each head term in the query).                        */
   const uint16_t* head_mat;  /* [n_docs, 64] fp16 bits or NULL                          */
   const int32_t* head_slot;  /* [n_terms] column of the term in head_mat, -1 = none; NULL without head_mat */
+  /* skip_row [n_terms]: row of the term in tile_skip, or -1: the term (a short list) has no
+   * row and its tile slices are found by bisection on post_doc (which must then be present).
+   * NULL = tile_skip has a row for every term.  The builder gives rows to the most frequent
+   * terms within a memory budget, so the table does not grow with the vocabulary.         */
+  const int32_t* skip_row;
   int64_t n_docs;
   int32_t n_terms;
   int32_t tile_docs;         /* multiple of 512, <= 65536                               */

@@ -119,10 +119,12 @@ def test_bm25_dense_columns_do_not_change_results(density, max_terms):
 @pytest.mark.parametrize("n_docs,vocab,k,tile,nq", [(20000, 300, 8, 2048, 12), (5002, 60, 24, 512, 40),
                                                     (40000, 3000, 10, 2048, 70), (777, 40, 8, 512, 9),
                                                     (130, 25, 10, 512, 33), (3000, 50, 100, 1024, 16),
-                                                    (66000, 30000, 10, 2048, 32)])
+                                                    (66000, 30000, 10, 2048, 32), (25000, 500, 10, 2048, 130),
+                                                    (9000, 200, 100, 1024, 100)])
 def test_bm25_head_path_equals_oracle_and_exact_kernel(n_docs, vocab, k, tile, nq):
     """CMR_BM25_HEAD (with its exact re-run of uncertified queries) returns the oracle's bytes: ragged sizes, more
-    than one block of 32 queries, tiny indexes without an admission bound, k = 100 (KP = 128), queries it
+    than one block of 32 queries (groups of up to 4 blocks share one pass over the head matrix; 130 queries =
+    a full group + a single block), tiny indexes without an admission bound, k = 100 (KP = 128), queries it
     must hand back (empty, unknown-only, > 16 tokens), repeated tokens."""
     from classmate_rag_b200 import lexical, ops
     rng = np.random.default_rng(n_docs)

@@ -4,6 +4,8 @@ cubin (same build).  usage: ncu_lines.py report.ncu-rep object.o kernel_substrin
 import collections, csv, re, subprocess, sys, tempfile, os
 rep, obj, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+kregex = sys.argv[5] if len(sys.argv) > 5 else None
+lskip = sys.argv[6] if len(sys.argv) > 6 else '0'
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith('.cubin')][0]
@@ -20,7 +22,7 @@ for l in dis:
         cur_line = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r'\s*/\*([0-9a-f]{4,6})\*/\s+(\S.*?);', l)
     if m and cur_line: line_of[int(m.group(1), 16)] = cur_line
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'] + (['-k', 'regex:' + kregex, '--launch-skip', lskip, '--launch-count', '1'] if kregex else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ia, iex, isamp = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
