@@ -66,12 +66,18 @@ namespace cmr {
 constexpr int BX_M = 128;                     // documents per item (UMMA M, TMEM lanes)
 constexpr int BX_N = 32;                      // queries per block (UMMA N, TMEM columns)
 constexpr int BX_K = 64;                      // head terms: one 128-byte swizzle span of fp16
-constexpr int BX_STAGES = 8;                  // ring of head_mat boxes (128 KB in flight per SM)
+#ifndef CMR_BX_STAGES
+#define CMR_BX_STAGES 8
+#endif
+constexpr int BX_STAGES = CMR_BX_STAGES;      // ring of head_mat boxes (128 KB in flight per SM)
 constexpr int BX_ACC = 16;                    // TMEM accumulators (16 x 32 columns = all of TMEM); see the work-order note
 constexpr int BX_A_BYTES = BX_M * BX_K * 2;   // 16 KiB
 constexpr int BX_Q_BYTES = BX_N * BX_K * 2;   // 4 KiB
 constexpr int BX_MAX_QB = 4;                  // blocks of 32 queries served by one pass over head_mat
-constexpr int BX_EPI_GROUPS = 3;              // epilogue warp groups (4 warps each) on alternating items
+#ifndef CMR_BX_EPI_GROUPS
+#define CMR_BX_EPI_GROUPS 3
+#endif
+constexpr int BX_EPI_GROUPS = CMR_BX_EPI_GROUPS;   // epilogue warp groups (4 warps each) on alternating items
 constexpr int BX_EPI_WARPS = 4 * BX_EPI_GROUPS;
 constexpr int BX_THREADS = (2 + BX_EPI_WARPS) * 32;
 constexpr int BX_S_BYTES = 32 * BX_N * 4;     // one epilogue warp's 32 documents x 32 queries fp32 tile
@@ -80,7 +86,7 @@ constexpr int BX_MAXT = 16;                   // tokens per query served here
 constexpr int BX_MAX_PAIRS = BX_N * BX_MAXT;  // (query, sparse term) pairs per block
 constexpr int BX_SAMPLE = 0, BX_MAIN = 1;
 constexpr int BX_SAMPLE_STRIDE = 16;
-constexpr int BX_GROUPS_PER_CTA = BX_EPI_WARPS;       // SAMPLE: group maxima each CTA hands to the bound kernel (one per epilogue warp)
+constexpr int BX_GROUPS_PER_CTA = 4;                  // SAMPLE: group maxima each CTA hands to the bound kernel (one per TMEM lane quarter)
 constexpr int BX_LIST_CAP = 256;              // candidate slots per (CTA, query)
 constexpr int BX_CAP_PER_KP = 128;            // candidates finalize can collect per query = 128 * KP
 constexpr int BX_MAX_TILE_DOCS = 2048;        // bucket kernel: tile_docs / 32 buckets of BX_CAP words in shared memory
@@ -189,50 +195,85 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs_all, cons
   const int* n_pairs_p = n_pairs_all + blockIdx.y;
   const int q_base = q_base0 + (int)blockIdx.y * BX_N;
   u32* buckets = buckets_all + (size_t)blockIdx.y * bucket_stride;
+  // the pairs that have postings in this tile, compacted: slice start, running end offset, idf, query
   __shared__ long long s_lo[BX_MAX_PAIRS];
   __shared__ int s_off[BX_MAX_PAIRS + 1];
   __shared__ double s_w[BX_MAX_PAIRS];
   __shared__ int s_q[BX_MAX_PAIRS];
   __shared__ int s_cnt[BX_MAX_TILE_DOCS / 32];
+  __shared__ int s_warp_sum[BXB_THREADS / 32], s_warp_live[BXB_THREADS / 32];
+  __shared__ int s_next, s_np;
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_b = ix.tile_docs / 32;
   const int np = *n_pairs_p;
   u32* rows = buckets + (size_t)tile * n_b * BX_CAP;
   for (int b = tid; b < n_b; b += BXB_THREADS) s_cnt[b] = 0;
-  if (tid == 0) s_off[0] = 0;
-  for (int p = tid; p < np; p += BXB_THREADS) {
-    const BxPair pr = pairs[p];
+  if (tid == 0) {
+    s_off[0] = 0;
+    s_next = 0;
+  }
+  // Slices of up to BXB_THREADS pairs per round: every thread looks one up (two dependent loads),
+  // then a block scan hands the non-empty ones their place in the compact list.
+  int carry = 0, live = 0;   // postings / non-empty pairs of the rounds so far (uniform)
+  for (int p0 = 0; p0 < np; p0 += BXB_THREADS) {
+    const int p = p0 + tid;
     u32 a = 0, z = 0;
-    lex_slice(ix, pr.term, lex_skip_row(ix, pr.term), tile, &a, &z);
-    s_lo[p] = ix.term_ptr[pr.term] + a;
-    s_off[p + 1] = (int)(z - a);
-    s_w[p] = pr.w;
-    s_q[p] = pr.q;
-  }
-  __syncthreads();
-  if (warp == 0) {  // inclusive scan of the slice lengths
-    int carry = 0;
-    for (int base = 0; base < np; base += 32) {
-      const int i = base + lane;
-      int v = i < np ? s_off[i + 1] : 0;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int o = __shfl_up_sync(0xFFFFFFFFu, v, off);
-        if (lane >= off) v += o;
-      }
-      if (i < np) s_off[i + 1] = carry + v;
-      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+    BxPair pr;
+    pr.term = 0;
+    pr.q = 0;
+    pr.w = 0.0;
+    if (p < np) {
+      pr = pairs[p];
+      lex_slice(ix, pr.term, lex_skip_row(ix, pr.term), tile, &a, &z);
     }
+    const int len = (int)(z - a);
+    int incl = len;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    const unsigned nz = __ballot_sync(0xFFFFFFFFu, len > 0);
+    if (lane == 31) s_warp_sum[warp] = incl;
+    if (lane == 0) s_warp_live[warp] = __popc(nz);
+    __syncthreads();
+    int sum_before = carry, live_before = live, sum_all = carry, live_all = live;
+#pragma unroll
+    for (int w = 0; w < BXB_THREADS / 32; ++w) {
+      if (w < warp) {
+        sum_before += s_warp_sum[w];
+        live_before += s_warp_live[w];
+      }
+      sum_all += s_warp_sum[w];
+      live_all += s_warp_live[w];
+    }
+    if (len > 0) {
+      const int ci = live_before + __popc(nz & ((1u << lane) - 1u));
+      s_lo[ci] = ix.term_ptr[pr.term] + a;
+      s_off[ci + 1] = sum_before + incl;
+      s_w[ci] = pr.w;
+      s_q[ci] = pr.q;
+    }
+    carry = sum_all;
+    live = live_all;
+    __syncthreads();   // s_warp_* are rewritten by the next round
   }
+  if (tid == 0) s_np = live;
   __syncthreads();
-  const int total = s_off[np];
-  // A warp takes chunks of 32 * BXB_U consecutive postings of the concatenated slices: one bisection
-  // for the chunk's first posting, then every lane walks forward from there (slices are ~50 postings).
+  const int npc = s_np;
+  const int total = s_off[npc];
+  // A warp takes chunks of 32 * BXB_U consecutive postings of the concatenated slices (handed out
+  // by a counter, so no warp idles while another has a chunk left): one bisection for the chunk's
+  // first posting, then every lane walks forward over the (non-empty) slices from there.
   constexpr int CH = 32 * BXB_U;
-  for (int base = warp * CH; base < total; base += (BXB_THREADS / 32) * CH) {
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_next, 1) * CH;
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) break;
     int p = 0;
     {
-      int hi = np;   // the pair whose slice holds posting `base`: largest p with s_off[p] <= base
+      int hi = npc;   // the pair whose slice holds posting `base`: largest p with s_off[p] <= base
       while (hi - p > 1) {
         const int mid = (p + hi) >> 1;
         if (s_off[mid] <= base) p = mid;
@@ -241,9 +282,11 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs_all, cons
     }
     int pr_of[BXB_U];
     u32 pk[BXB_U];
+    double imp[BXB_U];
 #pragma unroll
     for (int u = 0; u < BXB_U; ++u) {
       const int i = base + u * 32 + lane;
+      pk[u] = 0;
       if (i < total) {
         while (s_off[p + 1] <= i) ++p;
         pk[u] = ldg_stream_word(ix.post_pack + s_lo[p] + (i - s_off[p]));
@@ -251,11 +294,13 @@ bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs_all, cons
       pr_of[u] = p;
     }
 #pragma unroll
+    for (int u = 0; u < BXB_U; ++u) imp[u] = __ldg(ix.imp_table + (pk[u] >> 16));   // all gathers in flight together
+#pragma unroll
     for (int u = 0; u < BXB_U; ++u) {
       if (base + u * 32 + lane >= total) break;
       const u32 local = pk[u] & 0xFFFFu;
       const int q = s_q[pr_of[u]];
-      const __half h = __double2half(__dmul_rn(s_w[pr_of[u]], __ldg(ix.imp_table + (pk[u] >> 16))));
+      const __half h = __double2half(__dmul_rn(s_w[pr_of[u]], imp[u]));
       const int b = (int)(local >> 5);
       const int slot = atomicAdd(&s_cnt[b], 1) + 1;
       if (slot < BX_CAP) rows[b * BX_CAP + slot] = (local & 31u) | ((u32)q << 5) | ((u32)__half_as_ushort(h) << 16);
@@ -435,7 +480,17 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         n0 = ldg_stream_word(nb + lane);
         n1 = ldg_stream_word(nb + 32 + lane);
       }
-      // ---- scatter the bucket's sparse contributions into the warp's tile ----
+      // ---- accumulator + sparse contributions.  When the accumulator is already complete (the epilogue
+      // is the bottleneck: several query blocks per item) its TMEM read is issued first and the scatter
+      // hides the latency; when it is not (one block: the kernel waits for HBM) the scatter fills the wait.
+      const u32 u = li * (u32)nqb + (u32)qb;
+      const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
+      u32 vr[32];
+      const bool early = __all_sync(0xFFFFFFFFu, mbar_test(bars + BX_BAR_TFULL + 8 * acc, aph));
+      if (early) {
+        tc_fence_after();
+        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, vr);
+      }
       int cnt = (int)__shfl_sync(0xFFFFFFFFu, w0, 0);
       cnt = cnt < BX_CAP - 1 ? cnt : BX_CAP - 1;
       {
@@ -449,40 +504,49 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (cnt > 63)
           for (int x = 63 + lane; x < cnt; x += 32) apply(bp[1 + x]);
       }
+      if (!early) {
+        mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
+        tc_fence_after();
+        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, vr);
+      }
+      float4 bb[8];   // the block's admission bounds (broadcast reads), in flight with the rest
+      if (MODE == BX_MAIN) {
+        const float4* b4 = reinterpret_cast<const float4*>(s_thr + qb * BX_N);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bb[c] = b4[c];
+      }
       __syncwarp();
-      // ---- accumulator -> registers; release it at once ----
-      const u32 u = li * (u32)nqb + (u32)qb;
-      const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
-      mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
-      tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, v);
+      // ---- accumulator in registers: release it at once ----
+      tmem_ld32_wait(vr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + BX_BAR_TEMPTY + 8 * acc);
+      float v[32];
       // ---- add this document's row of the tile (16-byte chunks XOR-swizzled by the row) and clear it ----
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         int4* pp = S4 + (c ^ (lane & 7));
         const int4 s4 = *pp;
         *pp = make_int4(0, 0, 0, 0);
-        v[4 * c] = fmaf(__int2float_rn(s4.x), 1.0f / 65536.f, v[4 * c]);
-        v[4 * c + 1] = fmaf(__int2float_rn(s4.y), 1.0f / 65536.f, v[4 * c + 1]);
-        v[4 * c + 2] = fmaf(__int2float_rn(s4.z), 1.0f / 65536.f, v[4 * c + 2]);
-        v[4 * c + 3] = fmaf(__int2float_rn(s4.w), 1.0f / 65536.f, v[4 * c + 3]);
+        v[4 * c] = fmaf(__int2float_rn(s4.x), 1.0f / 65536.f, __uint_as_float(vr[4 * c]));
+        v[4 * c + 1] = fmaf(__int2float_rn(s4.y), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 1]));
+        v[4 * c + 2] = fmaf(__int2float_rn(s4.z), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 2]));
+        v[4 * c + 3] = fmaf(__int2float_rn(s4.w), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 3]));
       }
       __syncwarp();
       if (MODE == BX_SAMPLE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) gm[j] = fmaxf(gm[j], v[j]);
       } else {
-        const float4* b4 = reinterpret_cast<const float4*>(s_thr + qb * BX_N);   // broadcast reads
-        bool any = false;
+        bool any0 = false, any1 = false, any2 = false, any3 = false;   // four short chains instead of one long one
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 bb = b4[c];
-          any |= (v[4 * c] >= bb.x) | (v[4 * c + 1] >= bb.y) | (v[4 * c + 2] >= bb.z) | (v[4 * c + 3] >= bb.w);
+          any0 |= v[4 * c] >= bb[c].x;
+          any1 |= v[4 * c + 1] >= bb[c].y;
+          any2 |= v[4 * c + 2] >= bb[c].z;
+          any3 |= v[4 * c + 3] >= bb[c].w;
         }
+        const bool any = (any0 | any1) | (any2 | any3);
         if (any) {
           // Rare (about 16 * KP documents per query over the whole pass).
           const long long row = tile * BX_M + lq * 32 + lane;
@@ -514,7 +578,6 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (MODE == BX_SAMPLE) {
       // group maxima: the documents an epilogue warp saw form one group (a warp that saw none
       // reports -inf, a valid maximum of nothing); lane j publishes query j's
-      const int n_groups = (int)gridDim.x * BX_GROUPS_PER_CTA;
       float mine = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -526,12 +589,24 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 16));
         if (lane == j) mine = m;
       }
-      p.gmax[(size_t)(qb0 * BX_N + lane) * n_groups + (size_t)blockIdx.x * BX_GROUPS_PER_CTA + e] = mine;
+      // the warp's tile is free now: park the 32 maxima there for the cross-group reduction below
+      reinterpret_cast<float*>(S)[lane] = mine;
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (MODE == BX_SAMPLE && warp >= 2 && warp < 6) {
+    // one group of documents per TMEM lane quarter: everything the CTA's epilogue warps of that quarter saw
+    // (a quarter that saw nothing reports -inf, a valid maximum of nothing); lane j publishes query j's
+    const int e = warp - 2;
+    float m = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < BX_EPI_GROUPS; ++g)
+      m = fmaxf(m, reinterpret_cast<const float*>(gen + BX_OFF_S + (e + 4 * g) * BX_S_BYTES)[lane]);
+    const int n_groups = (int)gridDim.x * BX_GROUPS_PER_CTA;
+    p.gmax[(size_t)(qb0 * BX_N + lane) * n_groups + (size_t)blockIdx.x * BX_GROUPS_PER_CTA + e] = m;
+  }
   if (MODE == BX_MAIN)
     for (int i = threadIdx.x; i < nqb * BX_N; i += BX_THREADS) p.cnt[(size_t)blockIdx.x * nqb * BX_N + i] = s_cnt[i];
   if (warp == 1) {

@@ -37,6 +37,20 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// one non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(u32 bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap* map, u32 bar, int c0, int c1,
                                             unsigned long long hint) {
   asm volatile(
@@ -86,6 +100,31 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load split in two: issue (the 32 registers are written asynchronously) and wait (takes the
+// registers as in/out operands, so nothing that uses them can be scheduled ahead of it).  Independent
+// work placed between the two overlaps the TMEM read latency.
+__device__ __forceinline__ void tmem_ld32_issue(u32 taddr, u32 (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(u32 (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // v[j] for a run-time j: registers cannot be indexed, a dense switch becomes one indirect branch
 __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
   switch (j) {
@@ -123,31 +162,29 @@ __device__ __forceinline__ void cand_collect_select(const u64* __restrict__ cand
   }
   for (int i = tid; i < KP; i += FIN_THREADS) s_out[i] = 0ull;
   __syncthreads();
-  // Every list's length is read in one round trip (thread l owns list l), each list claims a
-  // range of the shared buffer, then one warp per list copies its keys: two dependent global
-  // round trips in all, whatever the number of lists.
+  // Every list's length is read in one round trip (thread l owns list l) and claims its range of the
+  // shared buffer; then the warps copy the lists (warp w: lists w, w + 32, ...), all loads independent:
+  // two dependent global round trips in all, whatever the number of lists.
+  __shared__ int s_base[FIN_THREADS], s_take[FIN_THREADS];
   for (int l0 = 0; l0 < n_lists; l0 += FIN_THREADS) {
     const int l = l0 + tid;
     int have = 0;
     if (l < n_lists) have = cnt[(size_t)l * n_queries + qi];
     const int take = have < cap ? have : cap;
     if (have > cap) s_over = 1;
-    int base = 0;
-    if (take > 0) base = atomicAdd(&s_total, take);
-    // hand (base, take) of the 32 lists of this warp's lanes to the whole warp, list by list
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, take > 0);
-    while (todo) {
-      const int src_lane = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int b2 = __shfl_sync(0xFFFFFFFFu, base, src_lane);
-      const int t2 = __shfl_sync(0xFFFFFFFFu, take, src_lane);
-      const int l2 = l0 + (tid & ~31) + src_lane;
-      const u64* src = cand + ((size_t)l2 * n_queries + qi) * cap;
+    s_take[tid] = take;
+    s_base[tid] = take > 0 ? atomicAdd(&s_total, take) : 0;
+    __syncthreads();
+    const int n_here = n_lists - l0 < FIN_THREADS ? n_lists - l0 : FIN_THREADS;
+    for (int j = warp; j < n_here; j += FIN_THREADS / 32) {
+      const int t2 = s_take[j], b2 = s_base[j];
+      const u64* src = cand + ((size_t)(l0 + j) * n_queries + qi) * cap;
       for (int i = lane; i < t2; i += 32) {
         if (b2 + i < cap_total) s_keys[b2 + i] = src[i];
         else s_over = 1;
       }
     }
+    __syncthreads();
   }
   __syncthreads();
   *n_total = s_total;

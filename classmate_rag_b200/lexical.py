@@ -42,20 +42,25 @@ class LexIndexStruct(C.Structure):
 
 def idf_table(df: np.ndarray, n_docs: int, vocab_order: np.ndarray, epsilon: float = BM25_EPS):
     """rank_bm25 idf with the epsilon floor.  ``vocab_order``: term ids with
-    df > 0 in first-appearance order (the order the running sum is taken in)."""
+    df > 0 in first-appearance order (the order the running sum is taken in).
+
+    Bit-identical to rank_bm25's Python loop without being one: the logarithms are libm's
+    (``math.log`` mapped over the values -- NumPy's vectorised log may differ in the last bit),
+    the subtraction is the same IEEE operation in NumPy, and the running sum is
+    ``np.cumsum`` (a sequential left-to-right scan, unlike ``np.sum``'s pairwise tree)."""
     idf = np.zeros(df.shape[0], dtype=np.float64)
-    idf_sum = 0.0
-    negative = []
-    for t in vocab_order.tolist():
-        n_t = int(df[t])
-        v = math.log(n_docs - n_t + 0.5) - math.log(n_t + 0.5)
-        idf[t] = v
-        idf_sum += v
-        if v < 0:
-            negative.append(t)
-    average_idf = idf_sum / max(1, len(vocab_order))
-    if negative:
-        idf[np.asarray(negative, dtype=np.int64)] = epsilon * average_idf
+    order = np.asarray(vocab_order, dtype=np.int64)
+    if order.size == 0:
+        return idf, 0.0
+    n_t = df[order].astype(np.float64)
+    log_a = np.fromiter(map(math.log, (float(n_docs) - n_t + 0.5).tolist()), dtype=np.float64, count=order.size)
+    log_b = np.fromiter(map(math.log, (n_t + 0.5).tolist()), dtype=np.float64, count=order.size)
+    v = log_a - log_b
+    idf[order] = v
+    average_idf = float(np.cumsum(v)[-1]) / max(1, order.size)
+    neg = order[v < 0]
+    if neg.size:
+        idf[neg] = epsilon * average_idf
     return idf, average_idf
 
 

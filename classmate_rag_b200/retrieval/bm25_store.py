@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from .. import _lib, lexical, ops
-from .filters import MetaColumns, bm25_clauses
+from .filters import SIMPLE_FIELDS, MetaColumns, bm25_clauses
 from .ids import REGISTRY
 from .text import detect_lang_tag, tokenize
 
@@ -91,32 +91,66 @@ class _FilteredView:
         self.rows_dev = None
         self.buffers: Dict[Tuple[int, int], ops.TopkBuffers] = {}
         self.mask = mask
+        import os
+        import time
+        prof = os.environ.get("CMRAG_PROFILE_FILTER") == "1"
+        marks = []
+
+        def mark(name):
+            if prof:
+                torch.cuda.synchronize(dev)
+                marks.append((name, time.perf_counter()))
+        mark("start")
         keep = mask.bool()
         n_terms, n_post = lex.n_terms, lex.n_postings
         doc_len = (doc_ptr[1:] - doc_ptr[:-1])
-        # one read-back for the scalars: subset size and its token total
-        n_sub, total = [int(x) for x in torch.stack([keep.sum(), (doc_len * keep).sum()]).tolist()]
-        self.n_docs = n_sub
         # df of the subset: postings whose document passes the filter (segmented sum over the CSR)
         hit = keep.index_select(0, lex.post_doc).to(torch.int32 if n_post < 2 ** 31 else torch.int64)
         cs = torch.zeros(n_post + 1, dtype=hit.dtype, device=dev)
         torch.cumsum(hit, 0, out=cs[1:])
-        df = (cs[lex.term_ptr[1:]] - cs[lex.term_ptr[:-1]]).to(torch.int64)
-        del hit, cs
-        # rank_bm25 sums idf in dict order = first appearance of each term over the subset's token stream
-        n_tok = int(tokens.numel())
-        first = torch.full((max(n_terms, 1),), n_tok, dtype=torch.int64, device=dev)
-        if n_tok:
-            tok_keep = torch.repeat_interleave(keep, doc_len)
-            pos = torch.where(tok_keep, torch.arange(n_tok, device=dev), torch.full((), n_tok, dtype=torch.int64, device=dev))
-            first.scatter_reduce_(0, tokens.long(), pos, reduce="amin")
-        order = torch.argsort(first, stable=True)
+        before = cs[lex.term_ptr[:-1]]
+        df = (cs[lex.term_ptr[1:]] - before).to(torch.int64)
+        del hit
+        mark("masked df")
+        # rank_bm25 sums idf in dict order = first appearance of each term in the subset's token stream:
+        # the term's first posting whose document passes (postings are in document order), then its first
+        # position inside that document.  V-sized work instead of a pass over every token of the corpus.
+        seen = torch.nonzero(df > 0).flatten()
+        order = seen
+        if seen.numel():
+            first_post = torch.searchsorted(cs, (before[seen] + 1).contiguous()) - 1   # cs[j + 1] is the first to reach before + 1
+            mark("  first postings")
+            d_first = lex.post_doc[first_post].long()
+            starts, lens = doc_ptr[d_first], doc_len[d_first]
+            l_max = int(lens.max())
+            pos_in_doc = torch.empty(seen.numel(), dtype=torch.int64, device=dev)
+            ar = torch.arange(l_max, device=dev)
+            n_tok = int(tokens.numel())
+            for lo_c in range(0, seen.numel(), 65536):          # bounded temporaries for large vocabularies
+                sl = slice(lo_c, lo_c + 65536)
+                idx = (starts[sl, None] + ar[None, :]).clamp_(max=max(n_tok - 1, 0))
+                eq = (tokens[idx] == seen[sl, None]) & (ar[None, :] < lens[sl, None])
+                pos_in_doc[sl] = torch.where(eq, ar[None, :], l_max).amin(dim=1)
+            mark("  positions in documents")
+            order = seen[torch.argsort(d_first * (l_max + 1) + pos_in_doc, stable=True)]
+        del cs
+        mark("first appearances")
+        # one read-back: subset size, its token total, df, the vocabulary order
+        n_sub_t = torch.stack([keep.sum(), (doc_len * keep).sum()])
+        n_sub, total = [int(x) for x in n_sub_t.tolist()]
+        self.n_docs = n_sub
         df_h = df.cpu().numpy().astype(np.int64)
-        n_seen = int((df_h > 0).sum())
-        idf_host, _ = lexical.idf_table(df_h, n_sub, order[:n_seen].cpu().numpy())
+        order_h = order.cpu().numpy()
+        mark("read-back")
+        idf_host, _ = lexical.idf_table(df_h, n_sub, order_h)
         avgdl = (total / n_sub) if n_sub > 0 else 0.0
         imp = (lexical.bm25_factor(lex.pair_tf, lex.pair_dl, avgdl, lex.k1, lex.b) if avgdl > 0
                else torch.zeros_like(lex.imp_table))
+        mark("idf + factor table")
+        if prof:
+            import sys
+            print("[_FilteredView] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms" for a, b in zip(marks, marks[1:])),
+                  file=sys.stderr, flush=True)
         self.lex = dataclasses.replace(lex, idf=torch.from_numpy(idf_host).to(dev), imp_table=imp, avgdl=float(avgdl),
                                        dense_imp=None, dense_slot=None, dense_terms=None, head_mat=None, head_slot=None,
                                        head_terms=None, idf_host=idf_host, df_host=df_h, _struct=None)
@@ -183,6 +217,8 @@ class BM25Store:
         self._dev_tokens = (doc_ptr, tokens, ptr)
         self._columns = MetaColumns(dev)
         self._columns.reset([self._entries[c].metadata for c in self._id_list])
+        self._columns.prepare([("get", f) for f in SIMPLE_FIELDS])   # dictionary-code the filterable fields now,
+        # while the build walks every entry anyway: the first filtered search then pays no O(n) Python loop
         self._gids = torch.tensor([REGISTRY.intern(c) for c in self._id_list], dtype=torch.int64, device=dev)
         self._full = _DeviceIndex(range(len(self._id_list)), doc_ptr, tokens, len(vocab), ptr, dev)
         self._subsets.clear()

@@ -136,20 +136,18 @@ class MetaColumns:
         self._metas = metas
         self._keys, self._dicts, self._host_cols, self._dev = [], {}, {}, None
 
-    def _ensure(self, key: Hashable) -> int:
-        if key in self._host_cols:
-            return self._keys.index(key)
+    def _code_rows(self, key: Hashable, lo: int, hi: int, codes: Dict[Any, int]) -> np.ndarray:
+        """Codes of rows [lo, hi) for one column (grows ``codes`` with the values it meets)."""
         kind, name = key
-        n = len(self._metas)
-        col = np.full(n, -1, dtype=np.int32)
-        codes: Dict[Any, int] = {}
+        col = np.full(hi - lo, -1, dtype=np.int32)
+        metas = self._metas
         if kind == "tag":
-            for i, m in enumerate(self._metas):
-                col[i] = 1 if name in (m.get("tags") or []) else 0
-            codes = {True: 1}
+            for i in range(lo, hi):
+                col[i - lo] = 1 if name in (metas[i].get("tags") or []) else 0
+            codes.setdefault(True, 1)
         else:
-            for i, m in enumerate(self._metas):
-                v = m.get(name)
+            for i in range(lo, hi):
+                v = metas[i].get(name)
                 if v is None:
                     continue
                 try:
@@ -158,12 +156,37 @@ class MetaColumns:
                         c = codes[v] = len(codes)
                 except TypeError:  # unhashable metadata value: can never equal a filter scalar
                     c = -3
-                col[i] = c
+                col[i - lo] = c
+        return col
+
+    def _ensure(self, key: Hashable) -> int:
+        if key in self._host_cols:
+            return self._keys.index(key)
+        codes: Dict[Any, int] = {}
+        col = self._code_rows(key, 0, len(self._metas), codes)
         self._keys.append(key)
         self._dicts[key] = codes
         self._host_cols[key] = col
         self._dev = None
         return len(self._keys) - 1
+
+    def extend(self, metas: Sequence[Mapping[str, Any]], n_old: int) -> None:
+        """Rows were APPENDED to the metadata list (rows [0, n_old) unchanged): every column built
+        so far grows by the codes of the new rows only, so a store that is filled batch by batch
+        never re-codes what it already has."""
+        self._metas = metas
+        n = len(metas)
+        if n == n_old:
+            return
+        for key in self._keys:
+            self._host_cols[key] = np.concatenate([self._host_cols[key][:n_old],
+                                                   self._code_rows(key, n_old, n, self._dicts[key])])
+        self._dev = None
+
+    def prepare(self, keys: Sequence[Hashable]) -> None:
+        """Build the columns of these keys now (index build time) instead of at their first use."""
+        for key in keys:
+            self._ensure(key)
 
     def mask(self, clauses: Sequence[Clause], alive: Optional[torch.Tensor] = None) -> torch.Tensor:
         """uint8 [n] device mask of the rows satisfying every clause (and alive)."""

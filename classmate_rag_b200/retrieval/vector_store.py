@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from .filters import MetaColumns, chroma_clauses
+from .filters import SIMPLE_FIELDS, MetaColumns, chroma_clauses
 from .ids import REGISTRY
 
 _COLLECTIONS: Dict[tuple, "_Collection"] = {}   # (persist_dir, name) -> live collection of this process
@@ -122,9 +122,15 @@ class _Collection:
             self.row_of[cid] = lo + j
         self.ids.extend(ids)
         self.documents.extend(documents)
+        n_meta_old = len(self.metadatas)
         self.metadatas.extend(dict(m or {}) for m in metadatas)
         self.n_rows += n
-        self.columns.reset(self.metadatas)
+        if n_meta_old == lo and self.columns._metas is self.metadatas:
+            self.columns.extend(self.metadatas, n_meta_old)      # appended rows only
+        else:
+            self.columns.reset(self.metadatas)
+        self.columns.prepare([("meta", f) for f in SIMPLE_FIELDS])   # the reference's filterable fields are coded
+        # at upsert time (Chroma indexes metadata at upsert too): the first filtered query pays no O(rows) loop
         self.version += 1
 
     def compact(self) -> None:

@@ -140,6 +140,24 @@ def test_bm25_head_path_equals_oracle_and_exact_kernel(n_docs, vocab, k, tile, n
         assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
 
 
+@pytest.mark.parametrize("rows", [0, 3, 40])
+def test_bm25_skip_table_budget_does_not_change_results(rows):
+    """The skip table holds rows for the most frequent terms only (a memory budget); every other term's tile
+    slices are bisected on post_doc.  No row at all, three rows, forty rows: same bytes from both kernels."""
+    n_docs, vocab = 30000, 900
+    docs, doc_ptr, tokens, v = zipf_corpus(seed=202, n_docs=n_docs, vocab=vocab, mean_len=18)
+    n_tiles = (n_docs + 2047) // 2048
+    budget = max(1, rows) * (n_tiles + 1) * 4
+    queries = zipf_queries(13, 20, vocab) + [[vocab - 1, vocab - 2, 0], [5, vocab - 7, vocab - 7], list(range(200, 230))]
+    for algo in ("exact", "head"):
+        ix = _run(docs, doc_ptr, tokens, v, queries, 10, 2048, algo=algo, skip_budget_bytes=budget)
+        assert ix.tile_skip.shape[0] == max(1, rows) and int((ix.skip_row >= 0).sum()) == max(1, rows)
+    _run(docs, doc_ptr, tokens, v, queries[:3], 10, 2048, algo="exact", skip_budget_bytes=budget)
+    rng = np.random.default_rng(3)
+    _run(docs, doc_ptr, tokens, v, queries, 10, 2048, mask=(rng.random(n_docs) < 0.5).astype(np.uint8),
+         skip_budget_bytes=budget)
+
+
 def test_bm25_head_path_certifies_normal_queries():
     """Without the re-run (head_nofallback) the flags say which queries were certified; every certified query is
     bit-exact, and on a Zipf corpus with 6-token queries (nearly) all of them are."""
