@@ -830,6 +830,16 @@ def run_c5(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     emb = synth.dense_corpus(a.rows, a.dim, dev)     # replicated (3 GB); the triangle's row blocks are dealt round-robin
+    # 5 % near-duplicates (normalize(c_j + 0.05 * noise)) + 1 % exact duplicates, same on every rank
+    g = torch.Generator(device="cpu").manual_seed(0xD0B)
+    perm = torch.randperm(a.rows, generator=g)
+    n_near, n_exact = a.rows // 20, a.rows // 100
+    src = perm[: n_near + n_exact].to(dev)
+    dst = perm[n_near + n_exact: 2 * (n_near + n_exact)].to(dev)
+    noise = torch.randn((n_near, a.dim), generator=torch.Generator(device=dev).manual_seed(0xD0C), device=dev) / a.dim ** 0.5
+    emb[dst[:n_near]] = torch.nn.functional.normalize(emb[src[:n_near]].float() + 0.05 * noise, dim=1).to(torch.bfloat16)
+    emb[dst[n_near:]] = emb[src[n_near:]]
+    del noise
     times = []
     keep = None
     for i in range(a.warmup + a.steps):
@@ -837,7 +847,7 @@ def run_c5(a):
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        keep = neardup.neardup_keep_mask(emb, 0.95, rank=rank, world=world) if world > 1 else neardup.neardup_keep_mask(emb, 0.95)
+        keep = neardup.neardup_keep_mask(emb, 0.95, group=True if world > 1 else None)
         torch.cuda.synchronize()
         if i >= a.warmup:
             times.append(time.perf_counter() - t0)
