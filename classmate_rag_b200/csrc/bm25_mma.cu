@@ -70,7 +70,7 @@ constexpr int BX_K = 64;                      // head terms: one 128-byte swizzl
 #define CMR_BX_STAGES 8
 #endif
 constexpr int BX_STAGES = CMR_BX_STAGES;      // ring of head_mat boxes (128 KB in flight per SM)
-constexpr int BX_ACC = 16;                    // TMEM accumulators (16 x 32 columns = all of TMEM); see the work-order note
+constexpr int BX_ACC = 16;                    // barrier slots for the TMEM accumulators (512 / (32 * query blocks) are in use)
 constexpr int BX_A_BYTES = BX_M * BX_K * 2;   // 16 KiB
 constexpr int BX_Q_BYTES = BX_N * BX_K * 2;   // 4 KiB
 constexpr int BX_MAX_QB = 4;                  // blocks of 32 queries served by one pass over head_mat
@@ -90,8 +90,8 @@ constexpr int BX_GROUPS_PER_CTA = 4;                  // SAMPLE: group maxima ea
 constexpr int BX_LIST_CAP = 256;              // candidate slots per (CTA, query)
 constexpr int BX_CAP_PER_KP = 128;            // candidates finalize can collect per query = 128 * KP
 constexpr int BX_MAX_TILE_DOCS = 2048;        // bucket kernel: tile_docs / 32 buckets of BX_CAP words in shared memory
-// kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), both K-major, N >> 3, M >> 4
-constexpr u32 BX_IDESC = (1u << 4) | ((u32)(BX_N >> 3) << 17) | ((u32)(BX_M >> 4) << 24);
+// kind::f16 instruction descriptor (built in the kernel: N depends on the query blocks of the pass): D = f32
+// (bit 4), A = B = fp16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 
 // reasons a query is handed back to the exact kernels (bit 0 = CMR_FLAG_UNCERTIFIED is always set with them)
 constexpr int BX_F_LONG = 2, BX_F_NEG = 4, BX_F_BUCKET = 8, BX_F_LIST = 16, BX_F_CERT = 32;
@@ -339,13 +339,16 @@ constexpr u32 BX_OFF_CNT = BX_OFF_THR + BX_MAX_QB * BX_N * 4;      // [32 * BX_M
 constexpr size_t BX_SMEM = 1024 + BX_OFF_CNT + BX_MAX_QB * BX_N * 4;
 
 // Work order shared by the three roles.  A CTA owns items first, first + step, ...; item number li
-// (0, 1, ...) is served for the query blocks qb = 0 .. nqb-1 in turn, use u = li * nqb + qb of the
-// accumulator ring (accumulator u % BX_ACC, phase (u / BX_ACC) & 1).  Epilogue group g serves the
-// items with li % BX_EPI_GROUPS == g.  A parity wait must never be a whole phase behind: a warp that
-// waits for use u has seen the commit of its previous use u', and the commit of u - BX_ACC (the use
-// before u on the same accumulator) precedes it only if u' >= u - BX_ACC.  Consecutive uses of a
-// warp are at most (BX_EPI_GROUPS - 1) * BX_MAX_QB + 1 apart, hence the assert.
-static_assert((BX_EPI_GROUPS - 1) * BX_MAX_QB + 1 <= BX_ACC, "accumulator ring too shallow for the epilogue groups");
+// (0, 1, ...) gets ONE accumulator of 32 * nqb TMEM columns (accumulator li % n_acc, phase (li / n_acc) & 1,
+// n_acc = 512 / (32 * nqb)): the MMAs of an item cover all its query blocks at once (UMMA N = 32 * nqb).
+// A tcgen05.mma of this shape costs ~150 cycles of latency whatever its N and the 4 MMAs of a K = 64 chain
+// accumulate into the same columns, i.e. serially -- with one chain per (item, block) the issuing thread, not
+// HBM or the epilogue, bounded the kernel (a 128-column head matrix doubled its time).  Epilogue group g
+// serves the items with li % BX_EPI_GROUPS == g, block by block (use = (item, block): the block's 32 columns).
+// A parity wait must never be a whole phase behind: a warp that waits for item li has seen the commit of its
+// previous item li - BX_EPI_GROUPS, and the commit of li - n_acc (the item before li on the same accumulator)
+// precedes that one only if BX_EPI_GROUPS <= n_acc; n_acc >= 4, hence the assert.
+static_assert(BX_EPI_GROUPS <= 512 / (BX_N * BX_MAX_QB), "accumulator ring too shallow for the epilogue groups");
 template <int MODE>
 __global__ void __launch_bounds__(BX_THREADS, 1)
 bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_rows,
@@ -378,14 +381,14 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     for (int a = 0; a < BX_ACC; ++a) {
       mbar_init(bars + BX_BAR_TFULL + 8 * a, 1);
-      mbar_init(bars + BX_BAR_TEMPTY + 8 * a, 4);  // one arrival per epilogue warp of the group that drains it
+      mbar_init(bars + BX_BAR_TEMPTY + 8 * a, 4u * (u32)nqb);  // the 4 warps of the draining group, once per block
     }
     mbar_init(bars + BX_BAR_QFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the allocating warp also frees
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BX_BAR_TMEM),
-                 "r"((u32)(BX_ACC * BX_N))
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -415,22 +418,21 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ===== MMA issuer =====
       mbar_wait(bars + BX_BAR_QFULL, 0);
       tc_fence_after();
-      u32 s = 0, ph = 0, u = 0;
-      for (int it = first; it < p.n_items; it += step) {
-        mbar_wait(bars + 8 * s, ph);                  // TMA bytes have landed
+      const unsigned long long dq = umma_desc_sw128(base + BX_OFF_Q);   // the blocks' count tiles are contiguous: N rows
+      const u32 idesc = (1u << 4) | ((u32)((BX_N * nqb) >> 3) << 17) | ((u32)(BX_M >> 4) << 24);
+      const u32 n_acc = (u32)(512 / (BX_N * nqb));
+      u32 s = 0, ph = 0, li = 0;
+      for (int it = first; it < p.n_items; it += step, ++li) {
+        const u32 acc = li % n_acc, aph = (li / n_acc) & 1u;
+        mbar_wait(bars + BX_BAR_TEMPTY + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
+        mbar_wait(bars + 8 * s, ph);                          // TMA bytes have landed
         tc_fence_after();
         const unsigned long long da = umma_desc_sw128(base + s * BX_A_BYTES);
-        for (int qb = 0; qb < nqb; ++qb, ++u) {
-          const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
-          mbar_wait(bars + BX_BAR_TEMPTY + 8 * acc, aph ^ 1u);  // the epilogue has drained this accumulator
-          tc_fence_after();
-          const unsigned long long dq = umma_desc_sw128(base + BX_OFF_Q + qb * BX_Q_BYTES);
 #pragma unroll
-          for (int k = 0; k < BX_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
-            tc_mma_bf16(tmem_base + acc * BX_N, da + 2ull * k, dq + 2ull * k, BX_IDESC, k != 0);
-          tc_commit(bars + BX_BAR_TFULL + 8 * acc);     // accumulator complete
-        }
-        tc_commit(bars + 64 + 8 * s);          // frees the ring slot when these MMAs retire
+        for (int k = 0; k < BX_K / 16; ++k)  // +32 bytes per K = 16 step inside the swizzle span
+          tc_mma_bf16(tmem_base + acc * (u32)(BX_N * nqb), da + 2ull * k, dq + 2ull * k, idesc, k != 0);
+        tc_commit(bars + 64 + 8 * s);                 // frees the ring slot when these MMAs retire
+        tc_commit(bars + BX_BAR_TFULL + 8 * acc);     // accumulator complete
         if (++s == BX_STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -483,13 +485,14 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ---- accumulator + sparse contributions.  When the accumulator is already complete (the epilogue
       // is the bottleneck: several query blocks per item) its TMEM read is issued first and the scatter
       // hides the latency; when it is not (one block: the kernel waits for HBM) the scatter fills the wait.
-      const u32 u = li * (u32)nqb + (u32)qb;
-      const u32 acc = u % BX_ACC, aph = (u / BX_ACC) & 1u;
+      const u32 n_acc = (u32)(512 / (BX_N * nqb));
+      const u32 acc = li % n_acc, aph = (li / n_acc) & 1u;
+      const u32 tcol = acc * (u32)(BX_N * nqb) + (u32)(qb * BX_N);   // this block's 32 columns of the item's accumulator
       u32 vr[32];
       const bool early = __all_sync(0xFFFFFFFFu, mbar_test(bars + BX_BAR_TFULL + 8 * acc, aph));
       if (early) {
         tc_fence_after();
-        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, vr);
+        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + tcol, vr);
       }
       int cnt = (int)__shfl_sync(0xFFFFFFFFu, w0, 0);
       cnt = cnt < BX_CAP - 1 ? cnt : BX_CAP - 1;
@@ -507,7 +510,7 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (!early) {
         mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
         tc_fence_after();
-        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + acc * BX_N, vr);
+        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + tcol, vr);
       }
       float4 bb[8];   // the block's admission bounds (broadcast reads), in flight with the rest
       if (MODE == BX_MAIN) {
@@ -611,7 +614,7 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int i = threadIdx.x; i < nqb * BX_N; i += BX_THREADS) p.cnt[(size_t)blockIdx.x * nqb * BX_N + i] = s_cnt[i];
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)(BX_ACC * BX_N))
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                  : "memory");
   }
 }
