@@ -381,7 +381,7 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     for (int a = 0; a < BX_ACC; ++a) {
       mbar_init(bars + BX_BAR_TFULL + 8 * a, 1);
-      mbar_init(bars + BX_BAR_TEMPTY + 8 * a, 4u * (u32)nqb);  // the 4 warps of the draining group, once per block
+      mbar_init(bars + BX_BAR_TEMPTY + 8 * a, 4);  // one arrival per epilogue warp of the group that drains the item
     }
     mbar_init(bars + BX_BAR_QFULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -447,113 +447,117 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     float gm[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) gm[j] = -INFINITY;
-    // this warp's uses, in order: items li = g, g + BX_EPI_GROUPS, ..., each for the blocks 0 .. nqb-1
+    // this warp's items: li = g, g + BX_EPI_GROUPS, ...; an item is served block by block (a "use")
     const long long it_step = (long long)BX_EPI_GROUPS * step;
-    auto bucket_at = [&](long long it, int qb) -> const u32* {
-      return p.buckets + (size_t)(qb0 + qb) * p.bucket_stride + ((size_t)it * p.stride * 4 + lq) * BX_CAP;
+    const u32 n_acc = (u32)(512 / (BX_N * nqb));
+    const size_t bstride = p.bucket_stride;
+    // the item's bucket of this lane quarter, per block: blocks are bucket_stride words apart
+    auto bucket_of = [&](long long it) -> const u32* {
+      return p.buckets + (size_t)qb0 * bstride + ((size_t)it * p.stride * 4 + lq) * BX_CAP;
     };
-    long long it = (long long)first + (long long)g * step;   // current use
-    int qb = 0;
-    u32 li = (u32)g;
-    long long it1 = it, it2;                                  // the next two uses
-    int qb1 = qb, qb2;
-    if (++qb1 == nqb) { qb1 = 0; it1 += it_step; }
-    it2 = it1;
-    qb2 = qb1;
-    if (++qb2 == nqb) { qb2 = 0; it2 += it_step; }
-    // bucket words of the next two uses are in flight while the current one is processed
-    u32 w0 = 0, w1 = 0, x0 = 0, x1 = 0;
+    // the first 64 words (count + 63 entries) of the buckets of every block of an item, one item ahead
+    u32 w0[BX_MAX_QB], w1[BX_MAX_QB];
+#pragma unroll
+    for (int qb = 0; qb < BX_MAX_QB; ++qb) w0[qb] = w1[qb] = 0;
+    long long it = (long long)first + (long long)g * step;
     if (it < p.n_items) {
-      const u32* bp = bucket_at(it, qb);
-      w0 = ldg_stream_word(bp + lane);
-      w1 = ldg_stream_word(bp + 32 + lane);
+      const u32* bp = bucket_of(it);
+#pragma unroll
+      for (int qb = 0; qb < BX_MAX_QB; ++qb)
+        if (qb < nqb) {
+          w0[qb] = ldg_stream_word(bp + qb * bstride + lane);
+          w1[qb] = ldg_stream_word(bp + qb * bstride + 32 + lane);
+        }
     }
-    if (it1 < p.n_items) {
-      const u32* bp = bucket_at(it1, qb1);
-      x0 = ldg_stream_word(bp + lane);
-      x1 = ldg_stream_word(bp + 32 + lane);
-    }
-    while (it < p.n_items) {
-      const u32* bp = bucket_at(it, qb);
-      const long long tile = it * p.stride;
-      u32 n0 = 0, n1 = 0;
-      if (it2 < p.n_items) {
-        const u32* nb = bucket_at(it2, qb2);
-        n0 = ldg_stream_word(nb + lane);
-        n1 = ldg_stream_word(nb + 32 + lane);
-      }
-      // ---- accumulator + sparse contributions.  When the accumulator is already complete (the epilogue
-      // is the bottleneck: several query blocks per item) its TMEM read is issued first and the scatter
-      // hides the latency; when it is not (one block: the kernel waits for HBM) the scatter fills the wait.
-      const u32 n_acc = (u32)(512 / (BX_N * nqb));
+    for (u32 li = (u32)g; it < p.n_items; it += it_step, li += BX_EPI_GROUPS) {
+      const u32* bp = bucket_of(it);
+      const long long row = it * p.stride * BX_M + lq * 32 + lane;   // this thread's document
       const u32 acc = li % n_acc, aph = (li / n_acc) & 1u;
-      const u32 tcol = acc * (u32)(BX_N * nqb) + (u32)(qb * BX_N);   // this block's 32 columns of the item's accumulator
-      u32 vr[32];
-      const bool early = __all_sync(0xFFFFFFFFu, mbar_test(bars + BX_BAR_TFULL + 8 * acc, aph));
-      if (early) {
-        tc_fence_after();
-        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + tcol, vr);
-      }
-      int cnt = (int)__shfl_sync(0xFFFFFFFFu, w0, 0);
-      cnt = cnt < BX_CAP - 1 ? cnt : BX_CAP - 1;
+      const u32 tbase = tmem_base + ((u32)(lq * 32) << 16) + acc * (u32)(BX_N * nqb);
+      // the next item's bucket words are in flight while this item is processed
+      u32 n0[BX_MAX_QB], n1[BX_MAX_QB];
       {
-        auto apply = [&](u32 w) {
-          const u32 r = w & 31u, q = (w >> 5) & 31u;
-          const float val = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
-          atomicAdd(S + r * 32 + ((((q >> 2) ^ (r & 7u))) << 2) + (q & 3u), __float2int_rn(val * 65536.f));
-        };
-        if (lane >= 1 && lane - 1 < cnt) apply(w0);
-        if (31 + lane < cnt) apply(w1);
-        if (cnt > 63)
-          for (int x = 63 + lane; x < cnt; x += 32) apply(bp[1 + x]);
-      }
-      if (!early) {
-        mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
-        tc_fence_after();
-        tmem_ld32_issue(tmem_base + ((u32)(lq * 32) << 16) + tcol, vr);
-      }
-      float4 bb[8];   // the block's admission bounds (broadcast reads), in flight with the rest
-      if (MODE == BX_MAIN) {
-        const float4* b4 = reinterpret_cast<const float4*>(s_thr + qb * BX_N);
+        const bool more = it + it_step < p.n_items;
+        const u32* nb = bucket_of(it + it_step);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) bb[c] = b4[c];
+        for (int qb = 0; qb < BX_MAX_QB; ++qb) {
+          n0[qb] = n1[qb] = 0;
+          if (more && qb < nqb) {
+            n0[qb] = ldg_stream_word(nb + qb * bstride + lane);
+            n1[qb] = ldg_stream_word(nb + qb * bstride + 32 + lane);
+          }
+        }
       }
-      __syncwarp();
-      // ---- accumulator in registers: release it at once ----
-      tmem_ld32_wait(vr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BX_BAR_TEMPTY + 8 * acc);
-      float v[32];
-      // ---- add this document's row of the tile (16-byte chunks XOR-swizzled by the row) and clear it ----
+      // When the accumulator is already complete (several query blocks per item: the epilogue is the
+      // bottleneck) every block's TMEM read is issued before its scatter, which hides the read latency;
+      // when it is not (one block: the kernel waits for HBM) the first scatter fills the wait.
+      bool ready = __all_sync(0xFFFFFFFFu, mbar_test(bars + BX_BAR_TFULL + 8 * acc, aph));
+      if (ready) tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        int4* pp = S4 + (c ^ (lane & 7));
-        const int4 s4 = *pp;
-        *pp = make_int4(0, 0, 0, 0);
-        v[4 * c] = fmaf(__int2float_rn(s4.x), 1.0f / 65536.f, __uint_as_float(vr[4 * c]));
-        v[4 * c + 1] = fmaf(__int2float_rn(s4.y), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 1]));
-        v[4 * c + 2] = fmaf(__int2float_rn(s4.z), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 2]));
-        v[4 * c + 3] = fmaf(__int2float_rn(s4.w), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 3]));
-      }
-      __syncwarp();
-      if (MODE == BX_SAMPLE) {
+      for (int qb = 0; qb < BX_MAX_QB; ++qb) {
+        if (qb >= nqb) break;
+        u32 vr[32];
+        if (ready) tmem_ld32_issue(tbase + (u32)(qb * BX_N), vr);
+        // ---- scatter the bucket's sparse contributions into the warp's tile ----
+        int cnt = (int)__shfl_sync(0xFFFFFFFFu, w0[qb], 0);
+        cnt = cnt < BX_CAP - 1 ? cnt : BX_CAP - 1;
+        {
+          auto apply = [&](u32 w) {
+            const u32 r = w & 31u, q = (w >> 5) & 31u;
+            const float val = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+            atomicAdd(S + r * 32 + ((((q >> 2) ^ (r & 7u))) << 2) + (q & 3u), __float2int_rn(val * 65536.f));
+          };
+          if (lane >= 1 && lane - 1 < cnt) apply(w0[qb]);
+          if (31 + lane < cnt) apply(w1[qb]);
+          if (cnt > 63)
+            for (int x = 63 + lane; x < cnt; x += 32) apply(bp[qb * bstride + 1 + x]);
+        }
+        if (!ready) {
+          mbar_wait(bars + BX_BAR_TFULL + 8 * acc, aph);
+          tc_fence_after();
+          ready = true;
+          tmem_ld32_issue(tbase + (u32)(qb * BX_N), vr);
+        }
+        float4 bb[8];   // the block's admission bounds (broadcast reads), in flight with the rest
+        if (MODE == BX_MAIN) {
+          const float4* b4 = reinterpret_cast<const float4*>(s_thr + qb * BX_N);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gm[j] = fmaxf(gm[j], v[j]);
-      } else {
-        bool any0 = false, any1 = false, any2 = false, any3 = false;   // four short chains instead of one long one
+          for (int c = 0; c < 8; ++c) bb[c] = b4[c];
+        }
+        __syncwarp();
+        tmem_ld32_wait(vr);
+        if (qb == nqb - 1) {   // the item's accumulator is in registers (this warp's share): release it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + BX_BAR_TEMPTY + 8 * acc);
+        }
+        float v[32];
+        // ---- add this document's row of the tile (16-byte chunks XOR-swizzled by the row) and clear it ----
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          any0 |= v[4 * c] >= bb[c].x;
-          any1 |= v[4 * c + 1] >= bb[c].y;
-          any2 |= v[4 * c + 2] >= bb[c].z;
-          any3 |= v[4 * c + 3] >= bb[c].w;
+          int4* pp = S4 + (c ^ (lane & 7));
+          const int4 s4 = *pp;
+          *pp = make_int4(0, 0, 0, 0);
+          v[4 * c] = fmaf(__int2float_rn(s4.x), 1.0f / 65536.f, __uint_as_float(vr[4 * c]));
+          v[4 * c + 1] = fmaf(__int2float_rn(s4.y), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 1]));
+          v[4 * c + 2] = fmaf(__int2float_rn(s4.z), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 2]));
+          v[4 * c + 3] = fmaf(__int2float_rn(s4.w), 1.0f / 65536.f, __uint_as_float(vr[4 * c + 3]));
         }
-        const bool any = (any0 | any1) | (any2 | any3);
-        if (any) {
-          // Rare (about 16 * KP documents per query over the whole pass).
-          const long long row = tile * BX_M + lq * 32 + lane;
-          if (row < p.n_docs) {
+        __syncwarp();
+        if (MODE == BX_SAMPLE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gm[j] = fmaxf(gm[j], v[j]);
+        } else {
+          bool any0 = false, any1 = false, any2 = false, any3 = false;   // four short chains instead of one long one
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            any0 |= v[4 * c] >= bb[c].x;
+            any1 |= v[4 * c + 1] >= bb[c].y;
+            any2 |= v[4 * c + 2] >= bb[c].z;
+            any3 |= v[4 * c + 3] >= bb[c].w;
+          }
+          if (((any0 | any1) | (any2 | any3)) && row < p.n_docs) {
+            // Rare (about 16 * KP documents per query over the whole pass).
             u32 hits = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) hits |= (v[j] >= s_thr[qb * BX_N + j] ? 1u : 0u) << j;
@@ -569,14 +573,11 @@ bm25x_mma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
       }
-      w0 = x0;
-      w1 = x1;
-      x0 = n0;
-      x1 = n1;
-      if (++qb == nqb) { qb = 0; it += it_step; li += BX_EPI_GROUPS; }
-      it1 = it2;
-      qb1 = qb2;
-      if (++qb2 == nqb) { qb2 = 0; it2 += it_step; }
+#pragma unroll
+      for (int qb = 0; qb < BX_MAX_QB; ++qb) {
+        w0[qb] = n0[qb];
+        w1[qb] = n1[qb];
+      }
     }
     if (MODE == BX_SAMPLE) {
       // group maxima: the documents an epilogue warp saw form one group (a warp that saw none
