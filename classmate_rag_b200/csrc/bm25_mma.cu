@@ -184,8 +184,14 @@ bm25x_prep_kernel(cmr_lex_index ix, const int* __restrict__ q_terms, const int* 
 // Slots are handed out by shared-memory counters; the entries go straight to the bucket rows in
 // global memory (all writers of a row are this CTA, within microseconds: L2 merges the sectors).
 // ---------------------------------------------------------------------------------------
-constexpr int BXB_THREADS = 256;
-constexpr int BXB_U = 4;   // postings in flight per thread
+#ifndef CMR_BXB_U
+#define CMR_BXB_U 4
+#endif
+#ifndef CMR_BXB_THREADS
+#define CMR_BXB_THREADS 256
+#endif
+constexpr int BXB_THREADS = CMR_BXB_THREADS;
+constexpr int BXB_U = CMR_BXB_U;   // postings in flight per thread
 
 __global__ void __launch_bounds__(BXB_THREADS)
 bm25x_bucket_kernel(cmr_lex_index ix, const BxPair* __restrict__ pairs_all, const int* __restrict__ n_pairs_all,
