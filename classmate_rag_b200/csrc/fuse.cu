@@ -288,6 +288,8 @@ struct ShardP2P {
   int n_parts, my_rank;
   unsigned long long slot_stride;        // bytes between the slots of two source ranks
   unsigned long long parity_stride;      // bytes between the two buffers used on alternating steps
+  const unsigned long long* peer_rows;   // pull form: device array [n_parts] of every rank's row matrix, or null
+  const long long* peer_row_lo;          // pull form: device array [n_parts], global id of every rank's first row
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
@@ -383,7 +385,9 @@ shard_merge_kernel(const unsigned char* gathered /* peers store into it until th
                    const unsigned int* __restrict__ wait_flags, const unsigned int* __restrict__ wait_state,
                    unsigned long long parity_stride, int* __restrict__ timeout_flag,
                    int n_parts, int n_queries, int pool, int kb,
-                   int dim, double* __restrict__ d_scores, long long* __restrict__ d_ids,
+                   int dim, int msg_dim /* row width the messages were packed with: dim, or 0 when rows are pulled */,
+                   const unsigned long long* __restrict__ peer_rows, const long long* __restrict__ peer_row_lo,
+                   double* __restrict__ d_scores, long long* __restrict__ d_ids,
                    int* __restrict__ d_counts, int* __restrict__ d_flags, uint4* __restrict__ d_rows,
                    double* __restrict__ b_scores, long long* __restrict__ b_ids, int* __restrict__ b_counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -393,7 +397,7 @@ shard_merge_kernel(const unsigned char* gathered /* peers store into it until th
   int* s_src = reinterpret_cast<int*>(s_i + (n_d > n_b ? n_d : n_b));  // [pool] entry feeding each output slot
   __shared__ int s_total, s_flag;
   const int qi = blockIdx.x, tid = threadIdx.x;
-  const size_t mb = shard_msg_bytes(pool, kb, dim);
+  const size_t mb = shard_msg_bytes(pool, kb, msg_dim);
   if (wait_flags != nullptr) {
     // peer-memory exchange: wait until every rank has published this step's message
     const unsigned int epoch = wait_state[0];
@@ -467,17 +471,45 @@ shard_merge_kernel(const unsigned char* gathered /* peers store into it until th
     }
     __syncthreads();
     if (pass == 0 && dim > 0 && d_rows != nullptr) {
-      const int dim_vec = dim / 8;
-      for (int e = tid; e < pool * dim_vec; e += SHARD_THREADS) {
-        const int r = e / dim_vec, v = e - r * dim_vec;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        const int src = s_src[r];
-        if (src >= 0) {
-          const int g = src / pool, rr = src - g * pool;
-          const uint4* rows = reinterpret_cast<const uint4*>(msg_of(g) + (size_t)16 * pool + (size_t)16 * kb + 16);
-          val = rows[(size_t)rr * dim_vec + v];
+      const int dim_vec = dim / 8, total = pool * dim_vec;
+      if (peer_rows != nullptr) {
+        // pull: every row of the merged pool lives in its source rank's matrix (mapped here).  The loads
+        // cross NVLink (microseconds each), so a thread keeps PULL_U of them in flight before storing.
+        constexpr int PULL_U = 12;
+        for (int e0 = tid; e0 < total; e0 += SHARD_THREADS * PULL_U) {
+          uint4 val[PULL_U];
+#pragma unroll
+          for (int u = 0; u < PULL_U; ++u) {
+            const int e = e0 + u * SHARD_THREADS;
+            val[u] = make_uint4(0, 0, 0, 0);
+            if (e < total) {
+              const int r = e / dim_vec, v = e - r * dim_vec;
+              const int src = s_src[r];
+              if (src >= 0) {
+                const int g = src / pool;
+                const long long local = s_i[src] - peer_row_lo[g];
+                val[u] = reinterpret_cast<const uint4*>(peer_rows[g])[(size_t)local * dim_vec + v];
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PULL_U; ++u) {
+            const int e = e0 + u * SHARD_THREADS;
+            if (e < total) d_rows[(size_t)qi * total + e] = val[u];
+          }
         }
-        d_rows[((size_t)qi * pool + r) * dim_vec + v] = val;
+      } else {
+        for (int e = tid; e < total; e += SHARD_THREADS) {
+          const int r = e / dim_vec, v = e - r * dim_vec;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          const int src = s_src[r];
+          if (src >= 0) {
+            const int g = src / pool, rr = src - g * pool;
+            const uint4* rows = reinterpret_cast<const uint4*>(msg_of(g) + (size_t)16 * pool + (size_t)16 * kb + 16);
+            val = rows[(size_t)rr * dim_vec + v];
+          }
+          d_rows[(size_t)qi * total + e] = val;
+        }
       }
       __syncthreads();
     }
@@ -684,7 +716,8 @@ extern "C" int cmr_shard_pack(const double* dense_scores, const int64_t* dense_i
 
 static int launch_shard_merge(const void* gathered, size_t slot_stride, const unsigned int* wait_flags,
                               const unsigned int* wait_state, unsigned long long parity_stride, int* timeout_flag,
-                              int n_parts, int n_queries, int pool, int kb, int dim, double* dense_scores,
+                              int n_parts, int n_queries, int pool, int kb, int dim, int msg_dim,
+                              const unsigned long long* peer_rows, const long long* peer_row_lo, double* dense_scores,
                               int64_t* dense_ids, int32_t* dense_counts, int32_t* dense_flags, uint16_t* dense_rows,
                               double* bm_scores, int64_t* bm_ids, int32_t* bm_counts, cmr_stream_t stream) {
   CMR_CHECK_ARG(n_parts >= 1 && n_queries > 0 && pool > 0 && kb >= 0 && dim >= 0 && dim % 8 == 0, "bad shard message shape");
@@ -696,8 +729,8 @@ static int launch_shard_merge(const void* gathered, size_t slot_stride, const un
   CMR_CHECK_ARG(smem <= 48 * 1024, "too many shards x list entries for one merge (%d)", n);
   shard_merge_kernel<<<n_queries, SHARD_THREADS, smem, (cudaStream_t)stream>>>(
       (const unsigned char*)gathered, slot_stride, wait_flags, wait_state, parity_stride, timeout_flag, n_parts,
-      n_queries, pool, kb, dim, dense_scores, (long long*)dense_ids, dense_counts, dense_flags,
-      reinterpret_cast<uint4*>(dense_rows), bm_scores, (long long*)bm_ids, bm_counts);
+      n_queries, pool, kb, dim, msg_dim, peer_rows, peer_row_lo, dense_scores, (long long*)dense_ids, dense_counts,
+      dense_flags, reinterpret_cast<uint4*>(dense_rows), bm_scores, (long long*)bm_ids, bm_counts);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }
@@ -711,8 +744,8 @@ extern "C" int cmr_shard_merge(const void* gathered, int n_parts, int n_queries,
     return CMR_EINVAL;
   }
   return launch_shard_merge(gathered, (size_t)n_queries * shard_msg_bytes(pool, kb, dim), nullptr, nullptr, 0, nullptr,
-                            n_parts, n_queries, pool, kb, dim, dense_scores, dense_ids, dense_counts, dense_flags,
-                            dense_rows, bm_scores, bm_ids, bm_counts, stream);
+                            n_parts, n_queries, pool, kb, dim, dim, nullptr, nullptr, dense_scores, dense_ids,
+                            dense_counts, dense_flags, dense_rows, bm_scores, bm_ids, bm_counts, stream);
 }
 
 extern "C" int cmr_shard_exchange_pack(const double* dense_scores, const int64_t* dense_ids,
@@ -726,11 +759,13 @@ extern "C" int cmr_shard_exchange_pack(const double* dense_scores, const int64_t
   CMR_CHECK_ARG(dim == 0 || n_rows == 0 || emb, "null embedding matrix");
   CMR_CHECK_ARG(x->peer_recv && x->peer_flags && x->state && x->n_parts >= 1 && x->my_rank >= 0 &&
                     x->my_rank < x->n_parts, "incomplete peer-exchange descriptor");
+  CMR_CHECK_ARG((x->peer_rows == nullptr) == (x->peer_row_lo == nullptr), "peer_rows and peer_row_lo go together");
+  if (x->peer_rows != nullptr) dim = 0;   // pull form: the merge reads rows from their owners, none travel
   CMR_CHECK_ARG((size_t)n_queries * shard_msg_bytes(pool, kb, dim) <= x->slot_stride && x->slot_stride % 16 == 0 &&
                     x->parity_stride >= x->slot_stride * (size_t)x->n_parts && x->parity_stride % 16 == 0,
                 "peer receive buffer too small for this message");
   ShardP2P p{(const unsigned long long*)x->peer_recv, (const unsigned long long*)x->peer_flags, (unsigned int*)x->state,
-             x->n_parts, x->my_rank, x->slot_stride, x->parity_stride};
+             x->n_parts, x->my_rank, x->slot_stride, x->parity_stride, nullptr, nullptr};
   shard_pack_kernel<true><<<n_queries, SHARD_THREADS, 0, (cudaStream_t)stream>>>(
       dense_scores, (const long long*)dense_ids, dense_counts, dense_flags, pool, bm_scores, (const long long*)bm_ids,
       bm_counts, kb, reinterpret_cast<const uint4*>(emb), n_rows, dim, row_offset, nullptr, p);
@@ -744,7 +779,10 @@ extern "C" int cmr_shard_exchange_merge(const void* local_recv, const uint32_t* 
                                         int32_t* dense_flags, uint16_t* dense_rows, double* bm_scores,
                                         int64_t* bm_ids, int32_t* bm_counts, cmr_stream_t stream) {
   CMR_CHECK_ARG(local_recv && local_flags && x && x->state && timeout_flag, "null pointer argument");
+  CMR_CHECK_ARG((x->peer_rows == nullptr) == (x->peer_row_lo == nullptr), "peer_rows and peer_row_lo go together");
   return launch_shard_merge(local_recv, (size_t)x->slot_stride, local_flags, (const unsigned int*)x->state,
-                            x->parity_stride, timeout_flag, x->n_parts, n_queries, pool, kb, dim, dense_scores,
-                            dense_ids, dense_counts, dense_flags, dense_rows, bm_scores, bm_ids, bm_counts, stream);
+                            x->parity_stride, timeout_flag, x->n_parts, n_queries, pool, kb, dim,
+                            x->peer_rows != nullptr ? 0 : dim, (const unsigned long long*)x->peer_rows,
+                            (const long long*)x->peer_row_lo, dense_scores, dense_ids, dense_counts, dense_flags,
+                            dense_rows, bm_scores, bm_ids, bm_counts, stream);
 }

@@ -233,13 +233,15 @@ class HybridEngine:
         dim = self.emb.shape[1] if p.use_mmr else 0
         kb = p.k_bm25 if hybrid else 0
         b = q_bf16.shape[0]
-        peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim))
+        peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim), self.emb, self.row_offset)
         if peer is not None:
             # stores into every rank's receive buffer over NVLink + flags: no collective launch
-            ops.shard_exchange_pack(dense, bm_local, self.emb if p.use_mmr else None, peer.struct,
-                                    row_offset=self.row_offset)
+            # with every shard's matrix in shared memory (sharding.shared_rows) no rows travel: the
+            # merge pulls the merged pool's rows from their owners
+            px = peer.struct_for(self.emb)
+            ops.shard_exchange_pack(dense, bm_local, self.emb if p.use_mmr else None, px, row_offset=self.row_offset)
             d_s, d_i, d_c, d_f, rows, g_bs, g_bi, g_bc = ops.shard_exchange_merge(
-                peer.recv, peer.flags, peer.struct, peer.timeout, b, pool, kb, dim)
+                peer.recv, peer.flags, px, peer.timeout, b, pool, kb, dim)
             self.last_exchange_timeout = peer.timeout   # int32 [1], device: non-zero = a rank never arrived
         else:
             msg = ops.shard_pack(dense, bm_local, self.emb if p.use_mmr else None, row_offset=self.row_offset)

@@ -380,7 +380,7 @@ class ShardP2PStruct(ctypes.Structure):
     """Mirror of ``cmr_shard_p2p`` (include/cmrag.h)."""
     _fields_ = [("peer_recv", ctypes.c_void_p), ("peer_flags", ctypes.c_void_p), ("state", ctypes.c_void_p),
                 ("n_parts", ctypes.c_int32), ("my_rank", ctypes.c_int32), ("slot_stride", ctypes.c_uint64),
-                ("parity_stride", ctypes.c_uint64)]
+                ("parity_stride", ctypes.c_uint64), ("peer_rows", ctypes.c_void_p), ("peer_row_lo", ctypes.c_void_p)]
 
 
 def shard_exchange_pack(dense, bm, emb: Optional[torch.Tensor], x: "ShardP2PStruct", *, row_offset: int = 0) -> None:

@@ -15,6 +15,7 @@ The reference has no distributed code; this is new.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import numpy as np
@@ -30,6 +31,34 @@ def shard_range(n: int, rank: int, world: int, align: int = 16) -> Tuple[int, in
     per = (per + align - 1) // align * align
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+# bf16 row matrices allocated by shared_rows(): data_ptr -> (symmetric-memory handle, base tensor)
+_SHARED_ROWS: dict = {}
+
+
+def shared_rows(n_rows: int, dim: int, device, group=None) -> torch.Tensor:
+    """A bf16 [n_rows, dim] matrix every rank of the box can read (torch symmetric memory: one
+    cudaMalloc per rank, handles exchanged once).  With every shard's matrix allocated this way
+    the peer exchange carries no embedding rows: the merge reads the merged pool's rows from
+    their owners over NVLink (``cmr_shard_p2p.peer_rows``).  Collective: every rank calls it;
+    ``n_rows`` may differ per rank (the allocation is the maximum).  Raises when symmetric
+    memory is unavailable -- callers fall back to an ordinary tensor, whose rows then travel
+    inside the messages."""
+    import torch.distributed._symmetric_memory as symm_mem
+    group = group if group is not None else dist.group.WORLD
+    most = torch.tensor([int(n_rows)], dtype=torch.int64, device=device)
+    dist.all_reduce(most, op=dist.ReduceOp.MAX, group=group)
+    with torch.cuda.device(device):
+        base = symm_mem.empty((max(int(most.item()), 1), dim), dtype=torch.bfloat16, device=device)
+        handle = symm_mem.rendezvous(base, group)
+    _SHARED_ROWS[base.data_ptr()] = (handle, base)
+    return base[:n_rows]
+
+
+def _shared_row_pointers(emb: Optional[torch.Tensor]):
+    ent = None if emb is None else _SHARED_ROWS.get(emb.data_ptr())
+    return None if ent is None else [int(p) for p in ent[0].buffer_ptrs]
 
 
 class PeerExchange:
@@ -58,8 +87,37 @@ class PeerExchange:
         self.timeout = torch.zeros(1, dtype=torch.int32, device=device)
         self.struct = ops.ShardP2PStruct(self.peer_recv.data_ptr(), self.peer_flags.data_ptr(), self.state.data_ptr(),
                                          world, rank, self.slot, self.parity)
+        self.pull_rows = False
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)     # every rank's buffers are zeroed before anyone stores into them
+
+    def attach_rows(self, emb: Optional[torch.Tensor], row_offset: int) -> bool:
+        """Collective.  If EVERY rank's matrix came from shared_rows(), the exchange switches to its
+        pull form (no rows in the messages); otherwise nothing changes."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        ptrs = _shared_row_pointers(emb)
+        dev = self.state.device
+        info = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+        info[rank, 0] = 1 if ptrs is not None and len(ptrs) == world else 0
+        info[rank, 1] = int(row_offset)
+        dist.all_reduce(info, group=self.group)
+        if int(info[:, 0].min()) == 0:
+            return False
+        from . import ops
+        self.peer_rows = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.peer_row_lo = info[:, 1].contiguous()
+        s = self.struct
+        self.struct_pull = ops.ShardP2PStruct(s.peer_recv, s.peer_flags, s.state, s.n_parts, s.my_rank, s.slot_stride,
+                                              s.parity_stride, self.peer_rows.data_ptr(), self.peer_row_lo.data_ptr())
+        self._pull_ptr = emb.data_ptr()
+        self.pull_rows = True
+        return True
+
+    def struct_for(self, emb: Optional[torch.Tensor]):
+        """The descriptor a step over ``emb`` uses: the pull form only for the matrix it was set up with."""
+        if self.pull_rows and emb is not None and emb.data_ptr() == self._pull_ptr:
+            return self.struct_pull
+        return self.struct
 
 
 class ShardComm:
@@ -73,7 +131,6 @@ class ShardComm:
         # peer-memory exchange: on by default with NCCL (CMRAG_P2P=0 turns it off); any failure
         # to set it up falls back to the NCCL all-gather of the same messages
         if peer_memory is None:
-            import os
             peer_memory = os.environ.get("CMRAG_P2P", "1") != "0" and dist.get_backend(group) == "nccl"
         self.peer_memory = bool(peer_memory)
         self.peer: Optional[PeerExchange] = None
@@ -81,9 +138,12 @@ class ShardComm:
         self.peer_generation = 0
         self.min_slot_bytes = 16 << 20
 
-    def peer_exchange(self, device, slot_bytes: int) -> Optional[PeerExchange]:
+    def peer_exchange(self, device, slot_bytes: int, rows: Optional[torch.Tensor] = None,
+                      row_offset: int = 0) -> Optional[PeerExchange]:
         """The PeerExchange big enough for ``slot_bytes`` per rank (collective on first use /
-        growth: every rank calls it with the same size), or None when unavailable."""
+        growth: every rank calls it with the same size), or None when unavailable.  ``rows``:
+        this rank's matrix; if every rank's is a shared_rows() allocation the exchange pulls the
+        pool rows from their owners instead of shipping them."""
         if not self.peer_memory:
             return None
         if self.peer is None or self.peer.slot < slot_bytes:
@@ -92,6 +152,8 @@ class ShardComm:
                 # CUDA graphs captured before hold the old addresses (see GraphedSearch.launch)
                 self.peer = PeerExchange(self.group, device, max(int(slot_bytes), self.min_slot_bytes))
                 self.peer_generation += 1
+                if os.environ.get("CMRAG_PULL_ROWS", "1") != "0":
+                    self.peer.attach_rows(rows, row_offset)
             except Exception as exc:  # no symmetric memory on this build / topology
                 self.peer_memory, self.peer, self.peer_error = False, None, repr(exc)
                 import warnings

@@ -328,6 +328,12 @@ typedef struct cmr_shard_p2p {
   int32_t n_parts, my_rank;
   uint64_t slot_stride;        /* bytes reserved per source rank  (>= n_queries * msg bytes)      */
   uint64_t parity_stride;      /* bytes between the two alternating buffers (>= n_parts * slot)   */
+  /* optional "pull" form: when every rank's bf16 row matrix is itself mapped into all ranks, the
+   * messages carry no rows (they are packed as if dim = 0) and cmr_shard_exchange_merge reads
+   * the rows of the merged pool -- pool rows per query instead of n_parts * pool -- straight
+   * from their owners over NVLink.  The matrices must not change while a step is in flight. */
+  const uint64_t* peer_rows;   /* device array [n_parts]: address of every rank's row matrix, or NULL */
+  const int64_t* peer_row_lo;  /* device array [n_parts]: global id of every rank's first row      */
 } cmr_shard_p2p;
 
 int cmr_shard_exchange_pack(const double* dense_scores, const int64_t* dense_ids, const int32_t* dense_counts,

@@ -1,6 +1,6 @@
 """Multi-GPU check of the sharded hot path (run under torchrun, one rank per GPU):
-peer-memory exchange == NCCL all-gather exchange == unsharded search, bit for bit, eager and
-from a CUDA graph.  Prints "shard_check ok" on rank 0."""
+peer-memory exchange (rows inside the messages, and rows pulled from their owners' shared
+matrices) == NCCL all-gather exchange == unsharded search, bit for bit, eager and from a CUDA graph.  Prints "shard_check ok" on rank 0."""
 import os
 import sys
 
@@ -38,15 +38,18 @@ def main():
                                           n_docs_total=n, token_offset=t_lo)
     sh_lex = lexical.build_lexical_index(doc_ptr[lo:hi + 1] - doc_ptr[lo], tokens[t_lo:t_hi], vocab, stats=gstats)
     results = {}
-    for name, peer in (("nccl", False), ("peer", True)):
+    shared = sharding.shared_rows(hi - lo, d, dev)      # this shard's rows, readable by every rank
+    shared.copy_(emb[lo:hi])
+    for name, peer in (("nccl", False), ("peer", True), ("peer_pull", True)):
         comm = sharding.ShardComm(peer_memory=peer)
-        eng = HybridEngine(emb[lo:hi].contiguous(), sh_lex, row_offset=lo, comm=comm)
+        eng = HybridEngine(shared if name == "peer_pull" else emb[lo:hi].contiguous(), sh_lex, row_offset=lo, comm=comm)
         for it in range(3):      # several steps: epochs / parity buffers of the peer exchange
             got = [t.clone() for t in eng.search(qb, qt, qp, p)]
         torch.cuda.synchronize()
         if peer:
             assert comm.peer is not None, f"peer memory unavailable: {comm.peer_error}"
             assert int(comm.peer.timeout.item()) == 0
+            assert comm.peer.pull_rows == (name == "peer_pull"), name
         for a, b in zip(got, want):
             assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes(), name
         gs = GraphedSearch(eng, p, nq, max_terms=16)
