@@ -29,8 +29,76 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ emb, long long n_ro
     out[(size_t)i * dim_vec + v] = mine ? emb[(size_t)local * dim_vec + v] : make_uint4(0, 0, 0, 0);
 }
 
-constexpr int MMR_THREADS = 1024;
+constexpr int MMR_THREADS = 512;
 constexpr int MMR_MAX_POOL = 64;
+constexpr int MMR_T = 4;   // a warp computes a 4 x 4 block of the similarity matrix at a time
+
+// 4 x 4 block of exact float64 dots, rows (i0..i0+3) x (j0..j0+3), in warp_exact_dot's pinned order for every
+// pair (lane l owns the 16-byte vectors l, l+32, ...; elements in order; halving tree).  float -> double
+// conversion is the slow instruction here (16 lanes per clock and SM, the DFMA pipe does 64): a block
+// converts every element once for 4 pairs instead of once per pair.  Rows beyond n_rows are clamped (their
+// results are not used).  Lane 0 ends up with the 16 sums.
+__device__ __forceinline__ void warp_exact_dot_block(const uint16_t* __restrict__ rows, int dim, int n_rows, int i0,
+                                                     int j0, int lane, double (&acc)[MMR_T][MMR_T]) {
+  const int nvec = dim >> 3;
+  const uint4* ra[MMR_T];
+  const uint4* rb[MMR_T];
+#pragma unroll
+  for (int t = 0; t < MMR_T; ++t) {
+    const int i = i0 + t < n_rows ? i0 + t : n_rows - 1, j = j0 + t < n_rows ? j0 + t : n_rows - 1;
+    ra[t] = reinterpret_cast<const uint4*>(rows + (size_t)i * dim);
+    rb[t] = reinterpret_cast<const uint4*>(rows + (size_t)j * dim);
+  }
+#pragma unroll
+  for (int r = 0; r < MMR_T; ++r)
+#pragma unroll
+    for (int c = 0; c < MMR_T; ++c) acc[r][c] = 0.0;
+  for (int v = lane; v < nvec; v += 32) {
+    u32 wa[MMR_T][4], wb[MMR_T][4];
+#pragma unroll
+    for (int t = 0; t < MMR_T; ++t) {
+      const uint4 x = ra[t][v], y = rb[t][v];
+      wa[t][0] = x.x, wa[t][1] = x.y, wa[t][2] = x.z, wa[t][3] = x.w;
+      wb[t][0] = y.x, wb[t][1] = y.y, wb[t][2] = y.z, wb[t][3] = y.w;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double a[MMR_T], b[MMR_T];
+#pragma unroll
+        for (int t = 0; t < MMR_T; ++t) {
+          a[t] = (double)(h ? bf16hi(wa[t][w]) : bf16lo(wa[t][w]));
+          b[t] = (double)(h ? bf16hi(wb[t][w]) : bf16lo(wb[t][w]));
+        }
+#pragma unroll
+        for (int r = 0; r < MMR_T; ++r)
+#pragma unroll
+          for (int c = 0; c < MMR_T; ++c) acc[r][c] = __fma_rn(a[r], b[c], acc[r][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < MMR_T; ++r)
+#pragma unroll
+      for (int c = 0; c < MMR_T; ++c) acc[r][c] = __dadd_rn(acc[r][c], __shfl_down_sync(0xFFFFFFFFu, acc[r][c], off));
+}
+
+// Index of the largest score among the lanes with `valid` (lowest index on equal scores), or -1: three
+// warp-wide integer reductions on an order-preserving key instead of a shuffle tree of float64 compares.
+__device__ __forceinline__ int warp_argbest(double score, int idx, bool valid) {
+  const long long bits = __double_as_longlong(score + 0.0);   // + 0.0: -0.0 and 0.0 compare equal
+  const unsigned long long key = (unsigned long long)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ll));
+  const u32 hi = (u32)(key >> 32), lo = (u32)key;
+  const u32 mhi = __reduce_max_sync(0xFFFFFFFFu, valid ? hi : 0u);
+  bool c = valid && hi == mhi;
+  const u32 mlo = __reduce_max_sync(0xFFFFFFFFu, c ? lo : 0u);
+  c = c && lo == mlo;
+  const u32 mi = __reduce_min_sync(0xFFFFFFFFu, c ? (u32)idx : 0xFFFFFFFFu);
+  return mi == 0xFFFFFFFFu ? -1 : (int)mi;
+}
 
 // One CTA per query.  cand_rows [B][pool][dim] bf16, cand_sims [B][pool] (exact
 // q.c, i.e. the scores cmr_dense_topk returned), cand_ids [B][pool].
@@ -38,7 +106,8 @@ __global__ void __launch_bounds__(MMR_THREADS)
 mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restrict__ cand_sims,
                   const long long* __restrict__ cand_ids, const int* __restrict__ cand_counts, int pool,
                   int dim, int k, double lambda, long long* __restrict__ out_ids,
-                  double* __restrict__ out_sims, int* __restrict__ out_counts) {
+                  double* __restrict__ out_sims, int* __restrict__ out_counts, int stage_rows) {
+  extern __shared__ __align__(16) unsigned char mmr_dyn[];   // the pool's rows when they fit (stage_rows)
   __shared__ double s_cc[MMR_MAX_POOL * MMR_MAX_POOL];
   __shared__ double s_q[MMR_MAX_POOL];
   __shared__ int s_sel[MMR_MAX_POOL];
@@ -47,72 +116,83 @@ mmr_select_kernel(const uint16_t* __restrict__ cand_rows, const double* __restri
   if (n > pool) n = pool;
   const uint16_t* rows = cand_rows + (size_t)qi * pool * dim;
   for (int i = tid; i < n; i += MMR_THREADS) s_q[i] = cand_sims[(size_t)qi * pool + i];
-  // pairwise similarities (symmetric: the pinned order multiplies elementwise)
-  const int n_pairs = n * (n - 1) / 2;
-  for (int p = warp; p < n_pairs; p += MMR_THREADS / 32) {
-    int i = 0, rem = p;
-    while (rem >= n - 1 - i) {  // row i holds pairs (i, i+1..n-1)
-      rem -= n - 1 - i;
-      ++i;
+  if (stage_rows) {
+    // every row is read by n - 1 pairs: bring the pool in once, the dots then run at shared-memory latency
+    const uint4* src = reinterpret_cast<const uint4*>(rows);
+    uint4* dst = reinterpret_cast<uint4*>(mmr_dyn);
+    for (int e = tid; e < n * (dim >> 3); e += MMR_THREADS) dst[e] = src[e];
+    rows = reinterpret_cast<const uint16_t*>(mmr_dyn);
+    __syncthreads();
+  }
+  // pairwise similarities (symmetric: the pinned order multiplies elementwise), one 4 x 4 block of the
+  // upper triangle per warp and turn
+  const int nb = (n + MMR_T - 1) / MMR_T, n_blocks = nb * (nb + 1) / 2;
+  for (int p = warp; p < n_blocks; p += MMR_THREADS / 32) {
+    int bi = 0, rem = p;
+    while (rem >= nb - bi) {  // block row bi holds blocks (bi, bi..nb-1)
+      rem -= nb - bi;
+      ++bi;
     }
-    const int j = i + 1 + rem;
-    const double s = warp_exact_dot(rows + (size_t)i * dim, rows + (size_t)j * dim, dim, lane);
+    const int bj = bi + rem;
+    double acc[MMR_T][MMR_T];
+    warp_exact_dot_block(rows, dim, n, bi * MMR_T, bj * MMR_T, lane, acc);
     if (lane == 0) {
-      s_cc[i * MMR_MAX_POOL + j] = s;
-      s_cc[j * MMR_MAX_POOL + i] = s;
+#pragma unroll
+      for (int r = 0; r < MMR_T; ++r)
+#pragma unroll
+        for (int c = 0; c < MMR_T; ++c) {
+          const int i = bi * MMR_T + r, j = bj * MMR_T + c;
+          if (i < j && j < n) {
+            s_cc[i * MMR_MAX_POOL + j] = acc[r][c];
+            s_cc[j * MMR_MAX_POOL + i] = acc[r][c];
+          }
+        }
     }
   }
   __syncthreads();
   if (warp == 0) {
-    // greedy selection by one warp: lane l scores candidates l and l+32, the best
+    // greedy selection by one warp: lane l owns candidates l and l+32 and keeps, for each, the running
+    // maximum of its similarity to the items selected so far (one shared-memory read per pick); the best
     // (score desc, index asc -- the reference's strict '>' over ascending i) wins
     const int target = k < n ? k : n;
     int n_sel = 0;
-    unsigned long long remaining = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    const int i0 = lane, i1 = lane + 32;
+    bool live0 = i0 < n, live1 = i1 < n;
+    const double q0 = live0 ? s_q[i0] : 0.0, q1 = live1 ? s_q[i1] : 0.0;
+    double div0 = 0.0, div1 = 0.0;
     if (n > 0) {
-      int first = 0;  // np.argmax: lowest index on ties
-      for (int i = 1; i < n; ++i)
-        if (s_q[i] > s_q[first]) first = i;
+      // np.argmax: lowest index on ties
+      const bool one = live1 && (!live0 || q1 > q0);
+      const int first = warp_argbest(one ? q1 : q0, one ? i1 : i0, live0 || live1);
       if (lane == 0) s_sel[0] = first;
       n_sel = 1;
-      remaining &= ~(1ull << first);
+      if (first == i0) live0 = false;
+      if (first == i1) live1 = false;
+      if (i0 < n) div0 = s_cc[i0 * MMR_MAX_POOL + first];
+      if (i1 < n) div1 = s_cc[i1 * MMR_MAX_POOL + first];
     }
-    __syncwarp();
     const double one_minus = __dsub_rn(1.0, lambda);
-    while (remaining && n_sel < target) {
-      double best_score = -1e9;
-      int best = -1;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h;
-        if (i < n && ((remaining >> i) & 1ull)) {
-          double div = s_cc[i * MMR_MAX_POOL + s_sel[0]];
-          for (int j = 1; j < n_sel; ++j) {
-            const double v = s_cc[i * MMR_MAX_POOL + s_sel[j]];
-            if (v > div) div = v;
-          }
-          const double sc = __dsub_rn(__dmul_rn(lambda, s_q[i]), __dmul_rn(one_minus, div));
-          if (sc > best_score) {  // h = 0 first: the lower index keeps a tie
-            best_score = sc;
-            best = i;
-          }
-        }
-      }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, off);
-        const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
-        if (ob >= 0 && (best < 0 || os > best_score || (os == best_score && ob < best))) {
-          best_score = os;
-          best = ob;
-        }
-      }
+    const double lq0 = __dmul_rn(lambda, q0), lq1 = __dmul_rn(lambda, q1);
+    while (n_sel < target) {
+      const double sc0 = __dsub_rn(lq0, __dmul_rn(one_minus, div0)), sc1 = __dsub_rn(lq1, __dmul_rn(one_minus, div1));
+      const bool ok0 = live0 && sc0 > -1e9, ok1 = live1 && sc1 > -1e9;   // the reference starts its search at -1e9
+      const bool one = ok1 && (!ok0 || sc1 > sc0);                        // the lower index keeps a tie
+      const int best = warp_argbest(one ? sc1 : sc0, one ? i1 : i0, ok0 || ok1);
       if (best < 0) break;
       if (lane == 0) s_sel[n_sel] = best;
       ++n_sel;
-      remaining &= ~(1ull << best);
-      __syncwarp();
+      if (best == i0) live0 = false;
+      if (best == i1) live1 = false;
+      if (live0) {
+        const double v = s_cc[i0 * MMR_MAX_POOL + best];
+        if (v > div0) div0 = v;
+      }
+      if (live1) {
+        const double v = s_cc[i1 * MMR_MAX_POOL + best];
+        if (v > div1) div1 = v;
+      }
     }
+    __syncwarp();
     for (int i = lane; i < k; i += 32) {
       if (i < n_sel) {
         out_ids[(size_t)qi * k + i] = cand_ids[(size_t)qi * pool + s_sel[i]];
@@ -618,9 +698,14 @@ extern "C" int cmr_mmr_select(const uint16_t* cand_rows, const double* cand_sims
   CMR_CHECK_ARG(k > 0 && k <= pool, "k %d out of range (1..pool)", k);
   CMR_CHECK_ARG(dim > 0 && dim % 8 == 0, "dim must be a multiple of 8");
   CMR_CHECK_ARG(cand_rows && cand_sims && cand_ids && cand_counts && out_ids && out_sims && out_counts, "null pointer argument");
-  mmr_select_kernel<<<n_queries, MMR_THREADS, 0, (cudaStream_t)stream>>>(
+  // the pool's rows are staged in shared memory when they fit beside the 33 KB of static tables
+  const size_t row_bytes = (size_t)pool * dim * 2;
+  const int stage = row_bytes <= 160 * 1024;
+  if (stage && row_bytes > 12 * 1024)   // per device, and cheap: set on every call rather than remembered
+    CMR_CUDA(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  mmr_select_kernel<<<n_queries, MMR_THREADS, stage ? row_bytes : 0, (cudaStream_t)stream>>>(
       cand_rows, cand_sims, (const long long*)cand_ids, cand_counts, pool, dim, k, lambda,
-      (long long*)out_ids, out_sims, out_counts);
+      (long long*)out_ids, out_sims, out_counts, stage);
   CMR_CUDA(cudaGetLastError());
   return CMR_OK;
 }
