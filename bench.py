@@ -485,11 +485,13 @@ def main():
     # step already live in HBM and are copied device-to-device into the graph's input buffers.
     clocks = ClockSampler(local)
     q_res = q_f32.contiguous()
-    gv = GraphedSearch(eng, p, a.batch, max_terms=16)
-    stream = gv.stream
+    # Two graph objects with their own streams and buffer sets alternate (PipelinedSearch), so the small-grid
+    # tail of step s (candidate merge, shard exchange, MMR, fusion) runs beside the scans of step s+1.
+    pv = PipelinedSearch(eng, p, a.batch, max_terms=16)
+    main_stream = torch.cuda.current_stream()
 
     def resident_step(s):
-        gv.launch_resident(q_res[s * a.batch:(s + 1) * a.batch], *dev_terms[s])
+        pv.launch_resident(q_res[s * a.batch:(s + 1) * a.batch], *dev_terms[s])
     dense_ms, lex_ms = [], []
     for s in range(a.warmup):
         resident_step(s)
@@ -497,21 +499,22 @@ def main():
     barrier()
     clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flag_acc = torch.zeros((), dtype=torch.int64, device=dev)
-    ev0.record(stream)
+    ev0.record(main_stream)           # every launch_resident orders its stream after the current (main) stream
     for s in range(a.warmup, n_steps):
         resident_step(s)
-    ev1.record(stream)
+    pv.wait(main_stream)
+    ev1.record(main_stream)
     barrier()
     total_ms = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = total_ms / a.steps
     value = a.batch * a.steps / (total_ms * 1e-3)
     # results of the LAST timed step (device-resident replay): digest + oracle parity + certificate flags
+    gv = pv.last
+    pipelined = pv.independent
     last_out = [t.cpu().numpy() for t in gv.out]
     last_flags = int(gv.flags.sum().item())
-    timeout_word = 0 if gv.timeout is None else int(gv.timeout.item())
+    timeout_word = max(0 if g.timeout is None else int(g.timeout.item()) for g in pv.slots)
     digest = hashlib.sha256(b"".join(np.ascontiguousarray(t).tobytes() for t in last_out[:4])).hexdigest()
-    del flag_acc
     stream = torch.cuda.current_stream()
 
     # ---- per-stage device time.  Single shard: the same steps again with timing events at the
@@ -618,7 +621,7 @@ def main():
 
     # ---- e2e: host buffers in, host results out, every step ---------------------
     q_host = q_f32.cpu().numpy()
-    gs = PipelinedSearch(eng, p, a.batch, max_terms=16)
+    gs = pv     # the same two graph objects, now fed from pinned host buffers
     for s in range(a.warmup):
         gs.submit(q_host[s * a.batch:(s + 1) * a.batch], terms[s * a.batch:(s + 1) * a.batch])
     gs.drain()
@@ -638,8 +641,9 @@ def main():
            "d2h_bytes_per_step": gs.d2h_bytes, "ms_per_step": e2e_s / a.steps * 1e3,
            "exact_reruns": sum(g.reruns for g in gs.slots), "same_digest_as_value_path": e2e_digest == digest,
            "path": "PipelinedSearch: pinned host queries -> H2D -> CUDA-graph replay of the kernel sequence -> D2H "
-                   "results + certificate flags, every step; two graph slots so the host stages step s+1 while the device "
-                   "runs step s; a batch with an uncertified query is re-run on the exhaustive scan before it is handed out"}
+                   "results + certificate flags, every step; two graph objects on two streams, so the host stages step "
+                   "s+1 while the device runs step s and the tail of step s overlaps the scans of step s+1; a batch with "
+                   "an uncertified query is re-run on the exhaustive scan before it is handed out"}
     # sanity on the last batch: the planted row is the dense top-1 unless MMR/RRF reorder it out of the top-10
     ids_last = last[0]
     planted_last = planted[(n_steps - 1) * a.batch:n_steps * a.batch].numpy()
@@ -730,7 +734,7 @@ def main():
     # ---- the drop-in call (rank 0 of a single-GPU run: it is a one-process API) -----------------
     dropin = None
     if world == 1 and a.dropin_rows > 0:
-        del gs, g1, gv
+        del gs, g1, gv, pv
         torch.cuda.empty_cache()
         try:
             dropin = dropin_block(a, dev, min(a.dropin_rows, a.rows))
@@ -758,6 +762,9 @@ def main():
                        "index_build_s": build_s, "bm25_path": "head" if head_path else "exact",
                        "overlap": ("BM25 kernels on a side stream beside the dense scan inside the step's CUDA graph"
                                    if overlap_on else "off (CMRAG_OVERLAP=0): the retrievers run one after the other"),
+                       "steps_in_flight": ("2: consecutive steps run from two CUDA-graph objects on two streams with "
+                                           "their own buffers (PipelinedSearch); each step still does all of its work"
+                                           if pipelined else "1"),
                        "stage_times": "roofline.avg_launch_ms / bm25.avg_ms_per_step: each retriever alone, in a serial step"},
            "roofline": roofline, "e2e": e2e, "latency": latency, "gpu_launches": launches_per_step * a.steps,
            "clocks": clock_info, "planted_top1_in_top10": hit, "batch_sweep": batch_sweep, "c2": c2, "dropin": dropin,
@@ -777,7 +784,7 @@ def main():
     if world > 1:
         # drop the CUDA graphs (they hold the exchange kernels), drain, then tear the group down in order
         try:
-            del gs, g1, gv
+            del gs, g1, gv, pv
         except NameError:
             pass
         torch.cuda.synchronize()

@@ -76,37 +76,38 @@ class HybridEngine:
         self.last_dense_flags = None
         self.last_exchange_timeout = None
         self.bm25_first = os.environ.get("CMRAG_BM25_ORDER", "first") != "after"
-        self._side = None
+        self._side = {}
 
-    def _fork_lexical(self, q_terms, q_ptr, k, lex_mask):
+    def _fork_lexical(self, q_terms, q_ptr, k, lex_mask, slot=0):
         """BM25 top-k on the side stream, forked from the current stream at the point of this
         call; returns (launch, join): launch() enqueues the kernels on the side stream and
         returns their result, join() makes the current stream wait for them.  Works eagerly and
         under CUDA-graph capture (the fork/join become graph edges)."""
         cur = torch.cuda.current_stream(self.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        side = self._side
+        side = self._side.get(slot)
+        if side is None:
+            side = self._side[slot] = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
 
         def launch():
             with torch.cuda.stream(side):
-                return self.lexical_topk(q_terms, q_ptr, k, lex_mask)
+                return self.lexical_topk(q_terms, q_ptr, k, lex_mask, slot)
         return launch, (lambda: cur.wait_stream(side))
 
-    def _dense_and_lexical(self, q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, k_bm25, lex_mask, dense_algo="auto"):
+    def _dense_and_lexical(self, q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, k_bm25, lex_mask, dense_algo="auto",
+                           slot=0):
         """The two retrievers of a step; BM25 on the side stream when overlap applies."""
         if not hybrid:
-            return self.dense_pool(q_bf16, pool, dense_mask, dense_algo), None, None
+            return self.dense_pool(q_bf16, pool, dense_mask, dense_algo, slot), None, None
         if not (self.overlap and q_bf16.shape[0] > 8):
-            return (self.dense_pool(q_bf16, pool, dense_mask, dense_algo), None,
-                    lambda: self.lexical_topk(q_terms, q_ptr, k_bm25, lex_mask))
-        launch, join = self._fork_lexical(q_terms, q_ptr, k_bm25, lex_mask)
+            return (self.dense_pool(q_bf16, pool, dense_mask, dense_algo, slot), None,
+                    lambda: self.lexical_topk(q_terms, q_ptr, k_bm25, lex_mask, slot))
+        launch, join = self._fork_lexical(q_terms, q_ptr, k_bm25, lex_mask, slot)
         if self.bm25_first:
             bm = launch()
-            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo)
+            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo, slot)
         else:
-            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo)
+            dense = self.dense_pool(q_bf16, pool, dense_mask, dense_algo, slot)
             bm = launch()
         return dense, join, lambda: bm
 
@@ -114,10 +115,13 @@ class HybridEngine:
     def _cert_eps(self, dim: int) -> float:
         return ops.dense_cert_eps(dim, 1.0, self.max_row_norm)
 
-    def dense_pool(self, q_bf16: torch.Tensor, k: int, row_mask: Optional[torch.Tensor] = None, algo: str = "auto"):
+    def dense_pool(self, q_bf16: torch.Tensor, k: int, row_mask: Optional[torch.Tensor] = None, algo: str = "auto",
+                   slot: int = 0):
+        """``slot``: which set of scratch / result buffers to use -- calls with different slots may be
+        in flight at the same time on different streams (PipelinedSearch)."""
         n, d = self.emb.shape
         b = q_bf16.shape[0]
-        key = (n, d, b, k)
+        key = (n, d, b, k, slot)
         ws = self._dense_ws.get(key)
         if ws is None:
             ws = self._dense_ws[key] = ops.DenseWorkspace(n, d, b, k, self.device)
@@ -125,7 +129,7 @@ class HybridEngine:
             # the widest over-selection one pass certifies (top-120, KP = 128), cut back to k: serves
             # queries whose top k sits inside a cluster of exact duplicates (tools/dup_heavy.py)
             kw = max(k, ops.WIDE_K)
-            wkey = (n, d, b, kw)
+            wkey = (n, d, b, kw, slot)
             wws = self._dense_ws.get(wkey)
             if wws is None:
                 wws = self._dense_ws[wkey] = ops.DenseWorkspace(n, d, b, kw, self.device)
@@ -140,9 +144,9 @@ class HybridEngine:
         return out
 
     def lexical_topk(self, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int,
-                     row_mask: Optional[torch.Tensor] = None):
+                     row_mask: Optional[torch.Tensor] = None, slot: int = 0):
         b = q_ptr.numel() - 1
-        key = (b, k)
+        key = (b, k, slot)
         buf = self._bm_buf.get(key)
         if buf is None:
             import ctypes as C
@@ -169,7 +173,7 @@ class HybridEngine:
     def search(self, q_bf16: torch.Tensor, q_terms: Optional[torch.Tensor], q_ptr: Optional[torch.Tensor],
                p: SearchParams, *, dense_mask: Optional[torch.Tensor] = None,
                lex_mask: Optional[torch.Tensor] = None, stage_events: Optional[list] = None,
-               dense_algo: str = "auto"):
+               dense_algo: str = "auto", slot: int = 0):
         """Returns device tensors (ids i64 [B,top_k], fused f64, vector_distance f64
         (NaN = None), bm25_score f64 (NaN = None), counts i32 [B]); nothing is
         synchronised.  ``self.last_dense_flags`` (int32 [B], device) is non-zero for queries
@@ -190,10 +194,11 @@ class HybridEngine:
         pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
         pool = min(pool, 64) if p.use_mmr else pool
         if self.comm is not None:
-            return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo)
+            return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo,
+                                        slot)
         mark()
         (scores, ids, counts, flags), join, lexical = self._dense_and_lexical(
-            q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, p.k_bm25, lex_mask, dense_algo)
+            q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr, p.k_bm25, lex_mask, dense_algo, slot)
         self.last_dense_flags = flags
         mark()
         if p.use_mmr:
@@ -215,13 +220,14 @@ class HybridEngine:
         return out
 
 
-    def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo="auto"):
+    def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo="auto",
+                        slot=0):
         """Row-sharded step with ONE collective: local dense pool + local BM25 list ->
         cmr_shard_pack -> all-gather -> cmr_shard_merge -> MMR -> fuse."""
         comm, self.comm = self.comm, None       # the stage helpers must not exchange on their own
         try:
             dense, join, lexical = self._dense_and_lexical(q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr,
-                                                           p.k_bm25, lex_mask, dense_algo)
+                                                           p.k_bm25, lex_mask, dense_algo, slot)
             bm_local = None
             if hybrid:
                 if join is not None:
@@ -233,7 +239,7 @@ class HybridEngine:
         dim = self.emb.shape[1] if p.use_mmr else 0
         kb = p.k_bm25 if hybrid else 0
         b = q_bf16.shape[0]
-        peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim), self.emb, self.row_offset)
+        peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim), self.emb, self.row_offset, slot)
         if peer is not None:
             # stores into every rank's receive buffer over NVLink + flags: no collective launch
             # with every shard's matrix in shared memory (sharding.shared_rows) no rows travel: the
@@ -265,8 +271,9 @@ class GraphedSearch:
     This is the end-to-end call with HOST buffers that bench.py's ``e2e`` times."""
 
     def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64,
-                 graph_collectives: bool = True, stream: Optional[torch.cuda.Stream] = None):
+                 graph_collectives: bool = True, stream: Optional[torch.cuda.Stream] = None, slot: int = 0):
         self.engine, self.p, self.b = engine, p, n_queries
+        self.slot = slot   # the engine's buffer set this object runs on (see PipelinedSearch)
         self.graph_collectives = graph_collectives
         dev = engine.device
         d = engine.emb.shape[1]
@@ -291,7 +298,7 @@ class GraphedSearch:
     def _run(self):
         q_bf16 = ops.f32_to_bf16(self.q_f32)
         return self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
-                                  self.q_ptr if self.hybrid else None, self.p)
+                                  self.q_ptr if self.hybrid else None, self.p, slot=self.slot)
 
     def _capture(self):
         with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
@@ -305,7 +312,7 @@ class GraphedSearch:
                 with torch.cuda.graph(g, stream=self.stream):
                     self.out = self._run()
                 self.graph = g
-                self._peer_generation = getattr(self.engine.comm, "peer_generation", 0)
+                self._peer_ref = self._current_peer()
             ids, fused, vd, bm, cnt = self.out
             # dense certificate flags (+ the peer exchange's timeout word) travel with the results
             self.flags = self.engine.last_dense_flags
@@ -341,8 +348,12 @@ class GraphedSearch:
             self.h_terms[: int(ptr[-1])].copy_(flat[: int(ptr[-1])])
             self.h_ptr.copy_(ptr)
 
+    def _current_peer(self):
+        peers = getattr(self.engine.comm, "peers", None)
+        return None if not peers else peers.get(self.slot)
+
     def _check_graph(self):
-        if self.graph is not None and getattr(self.engine.comm, "peer_generation", 0) != getattr(self, "_peer_generation", 0):
+        if self.graph is not None and self._current_peer() is not getattr(self, "_peer_ref", None):
             raise RuntimeError("the peer-exchange buffers were re-allocated after this graph was captured; "
                                "build a new GraphedSearch")
 
@@ -384,7 +395,7 @@ class GraphedSearch:
             with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
                 q_bf16 = ops.f32_to_bf16(self.q_f32)
                 out = self.engine.search(q_bf16, self.q_terms if self.hybrid else None,
-                                         self.q_ptr if self.hybrid else None, self.p, dense_algo=algo)
+                                         self.q_ptr if self.hybrid else None, self.p, dense_algo=algo, slot=self.slot)
                 self._copy_out(out)
                 self.h_flags.copy_(self.engine.last_dense_flags, non_blocking=True)
                 self.stream.synchronize()
@@ -440,21 +451,37 @@ class GraphedSearch:
 
 
 class PipelinedSearch:
-    """Throughput form of the host-buffer call: two GraphedSearch objects on one stream.
-    While the device works on batch i the host stages batch i+1 into the other object's
-    pinned buffers and enqueues it, so host staging never leaves the device idle.
+    """Throughput form of the search call: two GraphedSearch objects, each with its own stream and
+    its own set of engine buffers (slot 0 / 1), used alternately.  While the device works on
+    batch i the host stages batch i+1 into the other object's pinned buffers and enqueues it, and
+    on the device the latency-bound tail of a step (candidate merge, shard exchange, MMR, fusion --
+    small grids, and on several GPUs the wait for the slowest rank) runs beside the scans of the
+    next step instead of leaving the SMs idle.
 
         ps = PipelinedSearch(engine, params, batch)
         for q, terms in batches:
             prev = ps.submit(q, terms)        # results of the batch submitted before (or None)
         last = ps.drain()
-    """
+
+    ``launch_resident`` is the same rotation for inputs that already live in HBM.  With an NCCL
+    (not peer-memory) shard exchange both objects share one stream and one buffer set: collectives
+    of two steps must not be in flight at once."""
 
     def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64):
-        stream = torch.cuda.Stream(device=engine.device)
-        self.slots = [GraphedSearch(engine, p, n_queries, max_terms, stream=stream) for _ in range(2)]
+        comm = engine.comm
+        self.independent = (comm is None or bool(getattr(comm, "peer_memory", False))) and \
+            os.environ.get("CMRAG_PIPELINE", "1") != "0"
+        if self.independent:
+            self.slots = [GraphedSearch(engine, p, n_queries, max_terms, slot=i) for i in range(2)]
+            if comm is not None and not comm.peer_memory:
+                # the peer exchange turned out to be unavailable while capturing: fall back to one stream
+                self.independent = False
+        if not self.independent:
+            stream = torch.cuda.Stream(device=engine.device)
+            self.slots = [GraphedSearch(engine, p, n_queries, max_terms, stream=stream) for _ in range(2)]
         self.turn = 0
         self.pending: Optional[GraphedSearch] = None
+        self.last: Optional[GraphedSearch] = None
 
     @property
     def h2d_bytes(self) -> int:
@@ -469,9 +496,24 @@ class PipelinedSearch:
         self.turn ^= 1
         g.set_queries(q_f32, term_lists)   # g's previous results were handed out two submits ago
         g.launch()
-        prev, self.pending = self.pending, g
+        prev, self.pending, self.last = self.pending, g, g
         return None if prev is None else tuple(a.copy() for a in prev.result())
 
     def drain(self):
         prev, self.pending = self.pending, None
         return None if prev is None else tuple(a.copy() for a in prev.result())
+
+    def launch_resident(self, q_f32: torch.Tensor, q_terms: Optional[torch.Tensor] = None,
+                        q_ptr: Optional[torch.Tensor] = None):
+        """Device-resident rotation: returns the output tensors of this launch (valid until the
+        same slot is launched again, i.e. for one more call)."""
+        g = self.slots[self.turn]
+        self.turn ^= 1
+        self.last = g
+        return g.launch_resident(q_f32, q_terms, q_ptr)
+
+    def wait(self, stream: Optional[torch.cuda.Stream] = None):
+        """Order ``stream`` (default: the current one) after everything launched so far."""
+        cur = stream if stream is not None else torch.cuda.current_stream(self.slots[0].engine.device)
+        for g in self.slots:
+            cur.wait_stream(g.stream)

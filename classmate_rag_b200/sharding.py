@@ -133,33 +133,39 @@ class ShardComm:
         if peer_memory is None:
             peer_memory = os.environ.get("CMRAG_P2P", "1") != "0" and dist.get_backend(group) == "nccl"
         self.peer_memory = bool(peer_memory)
-        self.peer: Optional[PeerExchange] = None
+        self.peers: dict = {}      # buffer-set slot -> PeerExchange (two steps may be in flight: PipelinedSearch)
         self.peer_error: Optional[str] = None
         self.peer_generation = 0
         self.min_slot_bytes = 16 << 20
 
+    @property
+    def peer(self) -> Optional[PeerExchange]:
+        return self.peers.get(0) if self.peers else None
+
     def peer_exchange(self, device, slot_bytes: int, rows: Optional[torch.Tensor] = None,
-                      row_offset: int = 0) -> Optional[PeerExchange]:
+                      row_offset: int = 0, slot: int = 0) -> Optional[PeerExchange]:
         """The PeerExchange big enough for ``slot_bytes`` per rank (collective on first use /
         growth: every rank calls it with the same size), or None when unavailable.  ``rows``:
         this rank's matrix; if every rank's is a shared_rows() allocation the exchange pulls the
         pool rows from their owners instead of shipping them."""
         if not self.peer_memory:
             return None
-        if self.peer is None or self.peer.slot < slot_bytes:
+        cur = self.peers.get(slot)
+        if cur is None or cur.slot < slot_bytes:
             try:
                 # generous first allocation: a later, larger message would need new buffers, and
                 # CUDA graphs captured before hold the old addresses (see GraphedSearch.launch)
-                self.peer = PeerExchange(self.group, device, max(int(slot_bytes), self.min_slot_bytes))
+                cur = self.peers[slot] = PeerExchange(self.group, device, max(int(slot_bytes), self.min_slot_bytes))
                 self.peer_generation += 1
                 if os.environ.get("CMRAG_PULL_ROWS", "1") != "0":
-                    self.peer.attach_rows(rows, row_offset)
+                    cur.attach_rows(rows, row_offset)
             except Exception as exc:  # no symmetric memory on this build / topology
-                self.peer_memory, self.peer, self.peer_error = False, None, repr(exc)
+                self.peer_memory, self.peer_error = False, repr(exc)
+                self.peers.clear()
                 import warnings
                 warnings.warn(f"peer-memory shard exchange unavailable ({exc!r}): using the NCCL all-gather "
                               "(set CMRAG_P2P=0 to silence)", RuntimeWarning, stacklevel=2)
-        return self.peer
+        return self.peers.get(slot)
 
     def _merge(self, scores, ids, counts):
         if self._merge_fn is not None:

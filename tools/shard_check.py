@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from classmate_rag_b200 import lexical, ops, sharding, synth  # noqa: E402
-from classmate_rag_b200.engine import GraphedSearch, HybridEngine, SearchParams  # noqa: E402
+from classmate_rag_b200.engine import GraphedSearch, HybridEngine, PipelinedSearch, SearchParams  # noqa: E402
 
 
 def main():
@@ -59,6 +59,26 @@ def main():
             out = gs(qh, terms)
         for a, b in zip(out, want):
             assert a.tobytes() == b.cpu().numpy().tobytes(), name + " graph"
+        # two steps in flight (two graph objects, two streams, two exchange buffer sets)
+        ps = PipelinedSearch(eng, p, nq, max_terms=16)
+        assert ps.independent == peer, name
+        outs = []
+        for it in range(5):
+            r = ps.submit(qh, terms)
+            if r is not None:
+                outs.append(r)
+        outs.append(ps.drain())
+        assert len(outs) == 5
+        for o in outs:
+            for a, b in zip(o, want):
+                assert a.tobytes() == b.cpu().numpy().tobytes(), name + " pipelined"
+        for it in range(4):
+            dev_out = ps.launch_resident(q, qt, qp)
+        ps.wait()
+        torch.cuda.synchronize()
+        for a, b in zip(dev_out, want):
+            assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes(), name + " pipelined resident"
+        del ps
         # the other message shapes: no lexical list (non-hybrid), no rows (MMR off)
         for hyb, mmr in ((False, True), (True, False), (False, False)):
             p2 = SearchParams(top_k=10, hybrid=hyb, use_mmr=mmr)
