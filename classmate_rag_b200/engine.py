@@ -279,15 +279,20 @@ class GraphedSearch:
         d = engine.emb.shape[1]
         self.hybrid = p.hybrid and engine.lex is not None
         self.max_terms = max_terms
-        # static device inputs
-        self.q_f32 = torch.zeros((n_queries, d), dtype=torch.float32, device=dev)
+        # static device inputs and their pinned host staging: [queries f32 | term ids i32 | offsets i32] in ONE
+        # buffer on each side, so a launch is one host-to-device copy
+        n_q, n_t, n_p = n_queries * d, (max(1, n_queries * max_terms) + 3) // 4 * 4, n_queries + 1
+        assert n_q % 4 == 0   # dim is a multiple of 8: every part starts 16-byte aligned
+        self.d_in = torch.zeros((n_q + n_t + n_p,), dtype=torch.int32, device=dev)
+        self.h_in = torch.zeros((n_q + n_t + n_p,), dtype=torch.int32).pin_memory()
+
+        def carve(buf):
+            return (buf[:n_q].view(torch.float32).view(n_queries, d), buf[n_q:n_q + n_t], buf[n_q + n_t:])
+        self.q_f32, self.q_terms, self.q_ptr = carve(self.d_in)
+        self.h_q, self.h_terms, self.h_ptr = carve(self.h_in)
         self.q_f32[:, 0] = 1.0   # capture warm-ups run on this buffer: a unit vector, not the all-ties zero query
-        self.q_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32, device=dev)
-        self.q_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32, device=dev)
-        # pinned host staging
-        self.h_q = torch.zeros((n_queries, d), dtype=torch.float32).pin_memory()
-        self.h_terms = torch.full((max(1, n_queries * max_terms),), -1, dtype=torch.int32).pin_memory()
-        self.h_ptr = torch.zeros((n_queries + 1,), dtype=torch.int32).pin_memory()
+        self.q_terms.fill_(-1)
+        self.h_terms.fill_(-1)
         # several GraphedSearch objects may share one stream (they share the engine's scratch
         # buffers, so their device work must be serialised anyway): see PipelinedSearch
         self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
@@ -320,11 +325,22 @@ class GraphedSearch:
             self.h_flags = torch.zeros(self.flags.shape, dtype=self.flags.dtype).pin_memory()
             self.h_timeout = torch.zeros((1,), dtype=torch.int32).pin_memory()
             self.reruns = 0
-            self.h_ids = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
-            self.h_fused = torch.empty(fused.shape, dtype=fused.dtype).pin_memory()
-            self.h_vd = torch.empty(vd.shape, dtype=vd.dtype).pin_memory()
-            self.h_bm = torch.empty(bm.shape, dtype=bm.dtype).pin_memory()
-            self.h_cnt = torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory()
+            # hybrid_fuse hands back its five results as views of one allocation: one device-to-host copy
+            self.d_res = ops.fused_result_buffer(self.out)
+            if self.d_res is not None:
+                self.h_res = torch.empty(self.d_res.shape, dtype=torch.uint8).pin_memory()
+                n8 = ids.numel() * 8
+                self.h_ids = self.h_res[:n8].view(ids.dtype).view(ids.shape)
+                self.h_fused = self.h_res[n8:2 * n8].view(fused.dtype).view(fused.shape)
+                self.h_vd = self.h_res[2 * n8:3 * n8].view(vd.dtype).view(vd.shape)
+                self.h_bm = self.h_res[3 * n8:4 * n8].view(bm.dtype).view(bm.shape)
+                self.h_cnt = self.h_res[4 * n8:].view(cnt.dtype)
+            else:
+                self.h_ids = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
+                self.h_fused = torch.empty(fused.shape, dtype=fused.dtype).pin_memory()
+                self.h_vd = torch.empty(vd.shape, dtype=vd.dtype).pin_memory()
+                self.h_bm = torch.empty(bm.shape, dtype=bm.dtype).pin_memory()
+                self.h_cnt = torch.empty(cnt.shape, dtype=cnt.dtype).pin_memory()
 
     @property
     def h2d_bytes(self) -> int:
@@ -361,26 +377,25 @@ class GraphedSearch:
         """H2D copies + graph replay + D2H copies on the engine's stream (asynchronous)."""
         self._check_graph()
         with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
-            self.q_f32.copy_(self.h_q, non_blocking=True)
             if self.hybrid:
-                self.q_terms.copy_(self.h_terms, non_blocking=True)
-                self.q_ptr.copy_(self.h_ptr, non_blocking=True)
+                self.d_in.copy_(self.h_in, non_blocking=True)
+            else:
+                self.q_f32.copy_(self.h_q, non_blocking=True)
             if self.graph is not None:
                 self.graph.replay()
             else:
                 self.out = self._run()
-            ids, fused, vd, bm, cnt = self.out
-            self.h_ids.copy_(ids, non_blocking=True)
-            self.h_fused.copy_(fused, non_blocking=True)
-            self.h_vd.copy_(vd, non_blocking=True)
-            self.h_bm.copy_(bm, non_blocking=True)
-            self.h_cnt.copy_(cnt, non_blocking=True)
+            self._copy_out(self.out)
             self.h_flags.copy_(self.flags, non_blocking=True)
             if self.timeout is not None:
                 self.h_timeout.copy_(self.timeout, non_blocking=True)
             self.done.record(self.stream)
 
     def _copy_out(self, out):
+        res = ops.fused_result_buffer(out) if self.d_res is not None else None
+        if res is not None and res.shape == self.h_res.shape:
+            self.h_res.copy_(res, non_blocking=True)
+            return
         for h, t in zip((self.h_ids, self.h_fused, self.h_vd, self.h_bm, self.h_cnt), out):
             h.copy_(t, non_blocking=True)
 

@@ -10,6 +10,7 @@ torch is used for sorting and scans (plumbing); scoring is in libcmrag.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -317,9 +318,8 @@ def build_lexical_index(doc_ptr: torch.Tensor, tokens: torch.Tensor, n_terms: in
 def pack_queries(queries: Sequence[Sequence[int]]):
     """[[term ids]] -> (q_terms int32, q_ptr int32 [B+1]) host tensors."""
     ptr = np.zeros(len(queries) + 1, dtype=np.int32)
-    for i, q in enumerate(queries):
-        ptr[i + 1] = ptr[i] + len(q)
-    flat = np.fromiter((t for q in queries for t in q), dtype=np.int32, count=int(ptr[-1]))
+    np.cumsum(np.fromiter(map(len, queries), dtype=np.int64, count=len(queries)), out=ptr[1:])
+    flat = np.fromiter(itertools.chain.from_iterable(queries), dtype=np.int32, count=int(ptr[-1]))
     if flat.size == 0:
         flat = np.zeros(1, dtype=np.int32)  # keep a valid device pointer
     return torch.from_numpy(flat), torch.from_numpy(ptr)

@@ -218,17 +218,35 @@ def hybrid_fuse(vec, bm, *, top_k: int, rrf_k: int = 60, w_vec: float = 1.0, w_b
         bp = (b_ids.data_ptr(), b_sc.data_ptr(), b_cnt.data_ptr())
     else:
         kb, bp = 0, (None, None, None)
-    out_ids = torch.empty((b, top_k), dtype=torch.int64, device=dev)
-    out_fused = torch.empty((b, top_k), dtype=torch.float64, device=dev)
-    out_vd = torch.empty((b, top_k), dtype=torch.float64, device=dev)
-    out_bm = torch.empty((b, top_k), dtype=torch.float64, device=dev)
-    out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    # the five results are views of ONE allocation ([ids | fused | vector_distance | bm25 | counts]), so a caller
+    # that wants them on the host can fetch them with a single copy (fused_result_buffer)
+    n8 = b * top_k * 8
+    buf = torch.empty((4 * n8 + b * 4,), dtype=torch.uint8, device=dev)
+    out_ids = buf[:n8].view(torch.int64).view(b, top_k)
+    out_fused = buf[n8:2 * n8].view(torch.float64).view(b, top_k)
+    out_vd = buf[2 * n8:3 * n8].view(torch.float64).view(b, top_k)
+    out_bm = buf[3 * n8:4 * n8].view(torch.float64).view(b, top_k)
+    out_cnt = buf[4 * n8:].view(torch.int32)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cmr_hybrid_fuse(v_ids.data_ptr(), v_sims.data_ptr(), v_cnt.data_ptr(), kv, *bp, kb, b,
                                                float(w_vec), float(w_bm), int(rrf_k), int(top_k),
                                                out_ids.data_ptr(), out_fused.data_ptr(), out_vd.data_ptr(),
                                                out_bm.data_ptr(), out_cnt.data_ptr(), _stream()))
     return out_ids, out_fused, out_vd, out_bm, out_cnt
+
+
+def fused_result_buffer(out) -> Optional[torch.Tensor]:
+    """The single uint8 allocation behind hybrid_fuse's five results (None if ``out`` is not such a tuple)."""
+    ids, fused, vd, bm, cnt = out
+    base = ids._base
+    if base is None:
+        return None
+    while base._base is not None:
+        base = base._base
+    b, k = ids.shape
+    ok = (base.dtype == torch.uint8 and base.numel() == 4 * b * k * 8 + b * 4 and ids.data_ptr() == base.data_ptr()
+          and cnt.data_ptr() == base.data_ptr() + 4 * b * k * 8)
+    return base if ok else None
 
 
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor, counts: torch.Tensor):
