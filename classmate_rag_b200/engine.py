@@ -189,10 +189,7 @@ class HybridEngine:
                 stage_events.append(e)
         if q_bf16.dim() == 1:
             q_bf16 = q_bf16[None]
-        hybrid = p.hybrid and self.lex is not None and q_terms is not None
-        k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
-        pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
-        pool = min(pool, 64) if p.use_mmr else pool
+        hybrid, k_vec, pool = self._shape(p, q_terms)
         if self.comm is not None:
             return self._search_sharded(q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo,
                                         slot)
@@ -220,6 +217,54 @@ class HybridEngine:
         return out
 
 
+    # -- the same step in two halves (PipelinedSearch runs them on different streams) ----------
+    def _shape(self, p: SearchParams, q_terms):
+        hybrid = p.hybrid and self.lex is not None and q_terms is not None
+        k_vec = p.k_vector if hybrid else max(p.top_k, p.k_vector)
+        pool = max(k_vec, p.mmr_max_pool) if p.use_mmr else k_vec
+        pool = min(pool, 64) if p.use_mmr else pool
+        return hybrid, k_vec, pool
+
+    def search_heavy(self, q_bf16: torch.Tensor, q_terms: Optional[torch.Tensor], q_ptr: Optional[torch.Tensor],
+                     p: SearchParams, *, dense_mask: Optional[torch.Tensor] = None,
+                     lex_mask: Optional[torch.Tensor] = None, dense_algo: str = "auto", slot: int = 0):
+        """First half of search(): the two scans over this shard (dense pool + BM25 list, BM25 on its
+        side stream), nothing exchanged.  Returns the state search_tail() continues from; its tensors
+        live in the slot's buffers until the slot's next search_heavy()."""
+        if q_bf16.dim() == 1:
+            q_bf16 = q_bf16[None]
+        hybrid, k_vec, pool = self._shape(p, q_terms)
+        comm, self.comm = self.comm, None       # local lists only: the tail does the one exchange
+        try:
+            dense, join, lexical = self._dense_and_lexical(q_bf16, pool, dense_mask, hybrid, q_terms, q_ptr,
+                                                           p.k_bm25, lex_mask, dense_algo, slot)
+            bm_local = None
+            if hybrid:
+                if join is not None:
+                    join()
+                b_sc, b_ids, b_cnt, _ = lexical()
+                bm_local = (b_sc, b_ids, b_cnt)
+        finally:
+            self.comm = comm
+        return {"dense": dense, "bm": bm_local, "hybrid": hybrid, "k_vec": k_vec, "pool": pool,
+                "b": q_bf16.shape[0], "slot": slot}
+
+    def search_tail(self, state, p: SearchParams):
+        """Second half of search(): (exchange + merge,) MMR, fusion.  Same results as search()."""
+        dense, bm_local, hybrid, k_vec, pool = state["dense"], state["bm"], state["hybrid"], state["k_vec"], state["pool"]
+        if self.comm is not None:
+            return self._sharded_tail(dense, bm_local, p, hybrid, k_vec, pool, state["b"], state["slot"])
+        scores, ids, counts, flags = dense
+        self.last_dense_flags = flags
+        if p.use_mmr:
+            rows = self.pool_rows(ids)
+            v_ids, v_sims, v_cnt = ops.mmr_select(rows, scores, ids, counts, min(k_vec, pool), p.mmr_lambda)
+        else:
+            v_ids, v_sims, v_cnt = ids, scores, counts
+        bm = (bm_local[1], bm_local[0], bm_local[2]) if hybrid else None
+        return ops.hybrid_fuse((v_ids, v_sims, v_cnt), bm, top_k=p.top_k, rrf_k=p.rrf_k,
+                               w_vec=p.weight_vector if hybrid else 1.0, w_bm=p.weight_bm25)
+
     def _search_sharded(self, q_bf16, q_terms, q_ptr, p, hybrid, k_vec, pool, dense_mask, lex_mask, dense_algo="auto",
                         slot=0):
         """Row-sharded step with ONE collective: local dense pool + local BM25 list ->
@@ -236,9 +281,13 @@ class HybridEngine:
                 bm_local = (b_sc, b_ids, b_cnt)
         finally:
             self.comm = comm
+        return self._sharded_tail(dense, bm_local, p, hybrid, k_vec, pool, q_bf16.shape[0], slot)
+
+    def _sharded_tail(self, dense, bm_local, p, hybrid, k_vec, pool, b, slot):
+        """Exchange + merge + MMR + fuse of a row-sharded step (everything after the two local scans)."""
+        comm = self.comm
         dim = self.emb.shape[1] if p.use_mmr else 0
         kb = p.k_bm25 if hybrid else 0
-        b = q_bf16.shape[0]
         peer = comm.peer_exchange(self.device, b * ops.shard_msg_bytes(pool, kb, dim), self.emb, self.row_offset, slot)
         if peer is not None:
             # stores into every rank's receive buffer over NVLink + flags: no collective launch
@@ -271,9 +320,15 @@ class GraphedSearch:
     This is the end-to-end call with HOST buffers that bench.py's ``e2e`` times."""
 
     def __init__(self, engine: HybridEngine, p: SearchParams, n_queries: int, max_terms: int = 64,
-                 graph_collectives: bool = True, stream: Optional[torch.cuda.Stream] = None, slot: int = 0):
+                 graph_collectives: bool = True, stream: Optional[torch.cuda.Stream] = None, slot: int = 0,
+                 heavy_stream: Optional[torch.cuda.Stream] = None):
         self.engine, self.p, self.b = engine, p, n_queries
         self.slot = slot   # the engine's buffer set this object runs on (see PipelinedSearch)
+        # split form (PipelinedSearch): the two scans are one graph replayed on ``heavy_stream``, everything
+        # after them (exchange, merge, MMR, fusion, result copies) a second graph on this object's own stream
+        self.heavy_stream = heavy_stream
+        self.graph_h = None
+        self.heavy_done = torch.cuda.Event()
         self.graph_collectives = graph_collectives
         dev = engine.device
         d = engine.emb.shape[1]
@@ -310,7 +365,18 @@ class GraphedSearch:
             for _ in range(2):  # warm-up: one-time attribute / occupancy calls, allocations
                 self.out = self._run()
             self.stream.synchronize()
-            if self.engine.comm is None or self.graph_collectives:
+            if self.heavy_stream is not None:
+                q_terms, q_ptr = (self.q_terms, self.q_ptr) if self.hybrid else (None, None)
+                gh = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gh, stream=self.stream):
+                    self._state = self.engine.search_heavy(ops.f32_to_bf16(self.q_f32), q_terms, q_ptr, self.p,
+                                                           slot=self.slot)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream, pool=gh.pool()):
+                    self.out = self.engine.search_tail(self._state, self.p)
+                self.graph_h, self.graph = gh, g
+                self._peer_ref = self._current_peer()
+            elif self.engine.comm is None or self.graph_collectives:
                 # with a communicator the graph holds the step's single NCCL all-gather too
                 # (every rank captures and replays the same sequence)
                 g = torch.cuda.CUDAGraph()
@@ -376,20 +442,42 @@ class GraphedSearch:
     def launch(self):
         """H2D copies + graph replay + D2H copies on the engine's stream (asynchronous)."""
         self._check_graph()
-        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self._input_stream()):
             if self.hybrid:
                 self.d_in.copy_(self.h_in, non_blocking=True)
             else:
                 self.q_f32.copy_(self.h_q, non_blocking=True)
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self.out = self._run()
+            self._replay_heavy()
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            self._replay_rest()
             self._copy_out(self.out)
             self.h_flags.copy_(self.flags, non_blocking=True)
             if self.timeout is not None:
                 self.h_timeout.copy_(self.timeout, non_blocking=True)
             self.done.record(self.stream)
+
+    def _input_stream(self) -> torch.cuda.Stream:
+        """The stream the inputs are written on: the heavy stream in the split form.  There the slot's
+        previous tail must have finished first (it reads the lists the scans are about to overwrite)."""
+        if self.graph_h is None:
+            return self.stream
+        self.heavy_stream.wait_event(self.done)
+        return self.heavy_stream
+
+    def _replay_heavy(self):
+        """(current stream = _input_stream())  Split form: the scans, then the hand-over event."""
+        if self.graph_h is not None:
+            self.graph_h.replay()
+            self.heavy_done.record(self.heavy_stream)
+
+    def _replay_rest(self):
+        """(current stream = self.stream)  The whole step, or in the split form everything after the scans."""
+        if self.graph_h is not None:
+            self.stream.wait_event(self.heavy_done)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.out = self._run()
 
     def _copy_out(self, out):
         res = ops.fused_result_buffer(out) if self.d_res is not None else None
@@ -427,12 +515,13 @@ class GraphedSearch:
         # the inputs were produced on the caller's stream and may be temporaries: order this
         # stream after it and keep their memory from being reused while the copies are pending
         cur = torch.cuda.current_stream(self.engine.device)
-        if cur != self.stream:
-            self.stream.wait_stream(cur)
+        ins = self._input_stream()
+        if cur != ins:
+            ins.wait_stream(cur)
             for t in (q_f32, q_terms, q_ptr):
                 if t is not None:
-                    t.record_stream(self.stream)
-        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+                    t.record_stream(ins)
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(ins):
             if q_f32.data_ptr() != self.q_f32.data_ptr():   # an encoder may have written the buffer itself
                 self.q_f32.copy_(q_f32, non_blocking=True)
             if self.hybrid:
@@ -441,10 +530,9 @@ class GraphedSearch:
                     raise ValueError("too many query tokens for this graph (raise max_terms)")
                 self.q_terms[:n].copy_(q_terms, non_blocking=True)
                 self.q_ptr.copy_(q_ptr, non_blocking=True)
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self.out = self._run()
+            self._replay_heavy()
+        with torch.cuda.device(self.engine.device), torch.cuda.stream(self.stream):
+            self._replay_rest()
             self.done.record(self.stream)
         return self.out
 
@@ -486,8 +574,15 @@ class PipelinedSearch:
         comm = engine.comm
         self.independent = (comm is None or bool(getattr(comm, "peer_memory", False))) and \
             os.environ.get("CMRAG_PIPELINE", "1") != "0"
+        self.heavy_stream = None
         if self.independent:
-            self.slots = [GraphedSearch(engine, p, n_queries, max_terms, slot=i) for i in range(2)]
+            # the scans of consecutive steps run in order on ONE stream (the same order on every rank of a
+            # sharded engine); each slot's tail has its own high-priority stream, so its small grids take
+            # the SMs a scan kernel frees first
+            self.heavy_stream = torch.cuda.Stream(device=engine.device)
+            self.slots = [GraphedSearch(engine, p, n_queries, max_terms, slot=i, heavy_stream=self.heavy_stream,
+                                        stream=torch.cuda.Stream(device=engine.device, priority=-1))
+                          for i in range(2)]
             if comm is not None and not comm.peer_memory:
                 # the peer exchange turned out to be unavailable while capturing: fall back to one stream
                 self.independent = False
@@ -530,5 +625,7 @@ class PipelinedSearch:
     def wait(self, stream: Optional[torch.cuda.Stream] = None):
         """Order ``stream`` (default: the current one) after everything launched so far."""
         cur = stream if stream is not None else torch.cuda.current_stream(self.slots[0].engine.device)
+        if self.heavy_stream is not None:
+            cur.wait_stream(self.heavy_stream)
         for g in self.slots:
             cur.wait_stream(g.stream)
