@@ -554,12 +554,14 @@ class GraphedSearch:
 
 
 class PipelinedSearch:
-    """Throughput form of the search call: two GraphedSearch objects, each with its own stream and
+    """Throughput form of the search call: two GraphedSearch objects in their split form, each with
     its own set of engine buffers (slot 0 / 1), used alternately.  While the device works on
-    batch i the host stages batch i+1 into the other object's pinned buffers and enqueues it, and
-    on the device the latency-bound tail of a step (candidate merge, shard exchange, MMR, fusion --
-    small grids, and on several GPUs the wait for the slowest rank) runs beside the scans of the
-    next step instead of leaving the SMs idle.
+    batch i the host stages batch i+1 into the other object's pinned buffers and enqueues it.  On
+    the device the scan graphs of consecutive batches replay in order on ONE stream (on a sharded
+    engine: the same kernel order on every rank) and the latency-bound tail of a batch (candidate
+    merge, shard exchange and the wait for the slowest rank, MMR, fusion, result copy -- small
+    grids) replays on the slot's own high-priority stream beside the scans of the next batch
+    instead of leaving the SMs idle.  Events hand over: scans -> tail, tail -> the slot's next scans.
 
         ps = PipelinedSearch(engine, params, batch)
         for q, terms in batches:

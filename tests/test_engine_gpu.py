@@ -190,9 +190,56 @@ def test_single_exchange_shard_merge_equals_unsharded(small_world, n_shards, hyb
         assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
 
 
+@pytest.mark.parametrize("hybrid,use_mmr", [(True, True), (False, True), (True, False)])
+def test_search_in_two_halves_equals_search(small_world, hybrid, use_mmr):
+    """engine.search_heavy (the scans) + engine.search_tail (merge, MMR, fusion) -- the two graphs of the
+    pipelined form -- give the bytes of engine.search, on either buffer slot."""
+    from classmate_rag_b200 import lexical, ops
+    from classmate_rag_b200.engine import SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    p = SearchParams(top_k=10, hybrid=hybrid, use_mmr=use_mmr)
+    qb = ops.f32_to_bf16(q[:6])
+    qt, qp = lexical.pack_queries(terms[:6])
+    qt, qp = qt.cuda(), qp.cuda()
+    want = [t.clone() for t in eng.search(qb, qt, qp, p)]
+    for slot in (0, 1):
+        state = eng.search_heavy(qb, qt, qp, p, slot=slot)
+        got = eng.search_tail(state, p)
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+
+
+def test_pipelined_search_resident_rotation(small_world):
+    """launch_resident alternates the two slots; each launch's outputs stay valid for one more launch."""
+    from classmate_rag_b200 import lexical
+    from classmate_rag_b200.engine import GraphedSearch, PipelinedSearch, SearchParams
+    eng, emb, lex, q, planted, terms, lex_arrays = small_world
+    p = SearchParams(top_k=10)
+    one = GraphedSearch(eng, p, n_queries=2, max_terms=16)
+    qh = q.cpu().numpy()
+    ps = PipelinedSearch(eng, p, 2, max_terms=16)
+    assert ps.independent and ps.slots[0].graph_h is not None
+    prev = None
+    for i in (0, 2, 4, 0, 2):
+        want = [x.copy() for x in one(qh[i:i + 2], terms[i:i + 2])]
+        qt, qp = lexical.pack_queries(terms[i:i + 2])
+        out = ps.launch_resident(q[i:i + 2].contiguous(), qt.cuda(), qp.cuda())
+        if prev is not None:      # the launch before this one is still intact
+            ps.wait()
+            torch.cuda.synchronize()
+            for a, b in zip(prev[0], prev[1]):
+                assert a.cpu().numpy().tobytes() == b.tobytes()
+        prev = (out, want)
+    ps.wait()
+    torch.cuda.synchronize()
+    for a, b in zip(prev[0], prev[1]):
+        assert a.cpu().numpy().tobytes() == b.tobytes()
+
+
 def test_pipelined_search_returns_each_batch_in_order(small_world):
-    """PipelinedSearch (two graph slots on one stream) hands back, one submit late, exactly what
-    the single-slot GraphedSearch returns for the same batch."""
+    """PipelinedSearch (two graph objects, scans in order on one stream, tails on their own streams) hands
+    back, one submit late, exactly what the single-slot GraphedSearch returns for the same batch."""
     from classmate_rag_b200.engine import GraphedSearch, PipelinedSearch, SearchParams
     eng, emb, lex, q, planted, terms, lex_arrays = small_world
     p = SearchParams(top_k=10)
