@@ -42,6 +42,7 @@ _SIGNATURES = {
                                   C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cmr_rrf_fuse": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "cmr_filter_mask": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "cmr_masked_df": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "cmr_neardup_edges": (C.c_int, [_vp, _i64, C.c_int, C.c_float, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp]),
     "cmr_neardup_rescore": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _f64, _vp, _vp, _vp]),
     "cmr_neardup_resolve": (C.c_int, [_vp, C.c_uint64, _i64, _vp, _vp]),

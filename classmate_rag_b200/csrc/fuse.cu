@@ -672,9 +672,87 @@ __global__ void filter_mask_kernel(const int* __restrict__ cols, long long n_row
   }
 }
 
+// N1, statistics of a filtered BM25 search (rag/retrieval/bm25.py:184-191 rebuilds BM25Okapi over the
+// filtered entries, so df / N / avgdl / idf are the SUBSET's).  One pass over the CSR: a warp takes
+// MDF_CHUNK consecutive postings, finds the term its first posting belongs to (bisection on term_ptr) and
+// walks the term boundaries inside the chunk; per (term, chunk) piece the lanes sum mask[post_doc[i]] with
+// coalesced loads and one lane adds the count to df[t] and lowers first[t] to the first passing posting.
+// Bytes: 4 per posting + the mask gathers (L2-resident: one byte per document).
+constexpr int MDF_THREADS = 256;
+constexpr int MDF_CHUNK = 4096;
+
+__global__ void __launch_bounds__(MDF_THREADS)
+masked_df_kernel(const long long* __restrict__ term_ptr, const int* __restrict__ post_doc, int n_terms,
+                 long long n_post, const uint8_t* __restrict__ mask, int* __restrict__ df, int* __restrict__ first) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * MDF_THREADS + threadIdx.x) >> 5;
+  const long long lo = warp * MDF_CHUNK;
+  if (lo >= n_post) return;
+  const long long hi = lo + MDF_CHUNK < n_post ? lo + MDF_CHUNK : n_post;
+  // largest t with term_ptr[t] <= lo (empty terms before it are skipped by the walk below)
+  int a = 0, b = n_terms;
+  while (b - a > 1) {
+    const int mid = (a + b) >> 1;
+    if (term_ptr[mid] <= lo) a = mid;
+    else b = mid;
+  }
+  int t = a;
+  long long pos = lo;
+  while (pos < hi && t < n_terms) {
+    const long long t_end = term_ptr[t + 1];
+    if (t_end <= pos) {
+      ++t;
+      continue;
+    }
+    const long long e = t_end < hi ? t_end : hi;
+    int sum = 0;
+    long long fmin = n_post;
+    long long i = pos + lane;
+    for (; i + 96 < e; i += 128) {   // 4 independent posting loads and mask gathers in flight
+      const int d0 = post_doc[i], d1 = post_doc[i + 32], d2 = post_doc[i + 64], d3 = post_doc[i + 96];
+      const int m0 = mask[d0], m1 = mask[d1], m2 = mask[d2], m3 = mask[d3];
+      sum += (m0 != 0) + (m1 != 0) + (m2 != 0) + (m3 != 0);
+      if (fmin == n_post) fmin = m0 ? i : (m1 ? i + 32 : (m2 ? i + 64 : (m3 ? i + 96 : n_post)));
+    }
+    for (; i < e; i += 32) {
+      const int m = mask[post_doc[i]];
+      sum += m != 0;
+      if (m && fmin == n_post) fmin = i;
+    }
+    sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+    if (sum > 0) {
+      const unsigned int f = __reduce_min_sync(0xFFFFFFFFu, (unsigned int)(fmin - pos));   // offsets < MDF_CHUNK
+      if (lane == 0) {
+        atomicAdd(&df[t], sum);
+        atomicMin(&first[t], (int)(pos + f));
+      }
+    }
+    pos = e;
+    if (e == t_end) ++t;
+  }
+}
+
 }  // namespace cmr
 
 using namespace cmr;
+
+extern "C" int cmr_masked_df(const int64_t* term_ptr, const int32_t* post_doc, int n_terms, int64_t n_postings,
+                             const uint8_t* row_mask, int32_t* out_df, int32_t* out_first, cmr_stream_t stream) {
+  CMR_CHECK_ARG(n_terms >= 0 && n_postings >= 0 && n_postings < (int64_t)0x7FFFFFFF, "bad index shape");
+  CMR_CHECK_ARG(n_terms == 0 || (term_ptr && out_df && out_first), "null pointer argument");
+  CMR_CHECK_ARG(n_postings == 0 || (post_doc && row_mask), "null postings / mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_terms == 0) return CMR_OK;
+  CMR_CUDA(cudaMemsetAsync(out_df, 0, sizeof(int32_t) * (size_t)n_terms, st));
+  CMR_CUDA(cudaMemsetAsync(out_first, 0x7F, sizeof(int32_t) * (size_t)n_terms, st));   // 0x7F7F7F7F: above any posting index
+  if (n_postings == 0) return CMR_OK;
+  const long long warps = (n_postings + MDF_CHUNK - 1) / MDF_CHUNK;
+  const long long blocks = (warps * 32 + MDF_THREADS - 1) / MDF_THREADS;
+  masked_df_kernel<<<(unsigned int)blocks, MDF_THREADS, 0, st>>>((const long long*)term_ptr, post_doc, n_terms, n_postings,
+                                                              row_mask, out_df, out_first);
+  CMR_CUDA(cudaGetLastError());
+  return CMR_OK;
+}
 
 extern "C" int cmr_gather_rows(const uint16_t* emb, int64_t n_rows, int dim, int64_t row_offset,
                                const int64_t* ids, int n_ids, uint16_t* out_rows, cmr_stream_t stream) {

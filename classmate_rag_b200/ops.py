@@ -309,6 +309,24 @@ def filter_mask(field_codes: torch.Tensor, clause_field: torch.Tensor, clause_co
     return out
 
 
+def masked_df(term_ptr: torch.Tensor, post_doc: torch.Tensor, row_mask: torch.Tensor):
+    """Document frequency of every term over the documents passing ``row_mask`` (uint8 [n_docs]) and the
+    index of each term's first passing posting (cmr_masked_df).  Returns (df int32 [V], first int32 [V];
+    first >= 0x7F7F7F7F where df == 0)."""
+    for name, t in (("term_ptr", term_ptr), ("post_doc", post_doc), ("row_mask", row_mask)):
+        _require_cuda(t, name)
+    if term_ptr.dtype != torch.int64 or post_doc.dtype != torch.int32 or row_mask.dtype != torch.uint8:
+        raise ValueError("term_ptr int64, post_doc int32, row_mask uint8 expected")
+    n_terms = term_ptr.numel() - 1
+    dev = post_doc.device
+    df = torch.empty((n_terms,), dtype=torch.int32, device=dev)
+    first = torch.empty((n_terms,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cmr_masked_df(term_ptr.data_ptr(), post_doc.data_ptr(), n_terms, post_doc.numel(),
+                                             row_mask.data_ptr(), df.data_ptr(), first.data_ptr(), _stream()))
+    return df, first
+
+
 def shard_msg_bytes(pool: int, kb: int, dim: int) -> int:
     n = _lib.load().cmr_shard_msg_bytes(pool, kb, dim)
     if n == 0:

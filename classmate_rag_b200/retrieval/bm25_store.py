@@ -104,13 +104,18 @@ class _FilteredView:
         keep = mask.bool()
         n_terms, n_post = lex.n_terms, lex.n_postings
         doc_len = (doc_ptr[1:] - doc_ptr[:-1])
-        # df of the subset: postings whose document passes the filter (segmented sum over the CSR)
-        hit = keep.index_select(0, lex.post_doc).to(torch.int32 if n_post < 2 ** 31 else torch.int64)
-        cs = torch.zeros(n_post + 1, dtype=hit.dtype, device=dev)
-        torch.cumsum(hit, 0, out=cs[1:])
-        before = cs[lex.term_ptr[:-1]]
-        df = (cs[lex.term_ptr[1:]] - before).to(torch.int64)
-        del hit
+        # df of the subset and every term's first passing posting: one pass over the CSR (cmr_masked_df)
+        if n_post < 2 ** 31 - 1 and lex.term_ptr.dtype == torch.int64 and lex.post_doc.dtype == torch.int32:
+            df32, first32 = ops.masked_df(lex.term_ptr, lex.post_doc, mask.to(torch.uint8))
+            df = df32.to(torch.int64)
+            cs = None
+        else:   # very large shards: segmented sum with library kernels
+            hit = keep.index_select(0, lex.post_doc).to(torch.int64)
+            cs = torch.zeros(n_post + 1, dtype=hit.dtype, device=dev)
+            torch.cumsum(hit, 0, out=cs[1:])
+            before = cs[lex.term_ptr[:-1]]
+            df = (cs[lex.term_ptr[1:]] - before).to(torch.int64)
+            del hit
         mark("masked df")
         # rank_bm25 sums idf in dict order = first appearance of each term in the subset's token stream:
         # the term's first posting whose document passes (postings are in document order), then its first
@@ -118,7 +123,10 @@ class _FilteredView:
         seen = torch.nonzero(df > 0).flatten()
         order = seen
         if seen.numel():
-            first_post = torch.searchsorted(cs, (before[seen] + 1).contiguous()) - 1   # cs[j + 1] is the first to reach before + 1
+            if cs is None:
+                first_post = first32[seen].long()
+            else:
+                first_post = torch.searchsorted(cs, (before[seen] + 1).contiguous()) - 1   # cs[j + 1] is the first to reach before + 1
             mark("  first postings")
             d_first = lex.post_doc[first_post].long()
             starts, lens = doc_ptr[d_first], doc_len[d_first]

@@ -283,6 +283,14 @@ int cmr_filter_mask(const int32_t* field_codes, int64_t n_rows, int n_fields,
                     const int32_t* clause_field, const int32_t* clause_code, int n_clauses,
                     const uint8_t* alive, uint8_t* out_mask, cmr_stream_t stream);
 
+/* N1, statistics of a filtered BM25 search.  The reference rebuilds BM25Okapi over the filtered
+ *     entries for every query (rag/retrieval/bm25.py:184-191), so document frequencies are the
+ *     subset's.  One pass over the CSR: out_df[t] = number of postings of term t whose document
+ *     passes row_mask (uint8 [n_docs], non-zero = passes), out_first[t] = index (into post_doc) of
+ *     the first such posting, >= 0x7F7F7F7F when there is none.  n_postings < 2^31 - 1. */
+int cmr_masked_df(const int64_t* term_ptr, const int32_t* post_doc, int n_terms, int64_t n_postings,
+                  const uint8_t* row_mask, int32_t* out_df, int32_t* out_first, cmr_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * K7  Merge of per-shard top-k lists after the all-gather (multi-GPU; no
  *     reference counterpart).  in_* are [n_parts, n_queries, k]; order is

@@ -200,3 +200,31 @@ def test_bm25_head_path_repeated_runs_identical():
         out = [t.cpu().numpy().tobytes() for t in ops.bm25_topk(ix, qt, qp, 10, algo="head")]
         first = first or out
         assert out == first
+
+
+@pytest.mark.parametrize("n_docs,vocab,keep_every", [(5000, 300, 3), (70000, 20000, 16), (3000, 50, 1), (3000, 50, 0)])
+def test_masked_df_matches_segmented_sum(n_docs, vocab, keep_every):
+    """cmr_masked_df (subset document frequencies + first passing posting of every term, one pass over
+    the CSR) against a cumulative-sum restatement; covers empty terms, an all-pass and an empty mask."""
+    from classmate_rag_b200 import lexical, ops, synth
+    doc_ptr, tokens = synth.lexical_corpus(n_docs, vocab, 24, "cuda")
+    lex = lexical.build_lexical_index(doc_ptr, tokens, vocab)
+    g = torch.Generator(device="cpu").manual_seed(n_docs + keep_every)
+    if keep_every == 0:
+        mask = torch.zeros(n_docs, dtype=torch.uint8)
+    elif keep_every == 1:
+        mask = torch.ones(n_docs, dtype=torch.uint8)
+    else:
+        mask = (torch.randint(0, keep_every, (n_docs,), generator=g) == 0).to(torch.uint8)
+    df, first = ops.masked_df(lex.term_ptr, lex.post_doc, mask.cuda())
+    torch.cuda.synchronize()
+    tp = lex.term_ptr.cpu().numpy()
+    hit = mask.numpy()[lex.post_doc.cpu().numpy()].astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(hit)])
+    want_df = cs[tp[1:]] - cs[tp[:-1]]
+    assert np.array_equal(df.cpu().numpy().astype(np.int64), want_df)
+    got_first = first.cpu().numpy()
+    for t in np.nonzero(want_df > 0)[0][:2000]:
+        seg = hit[tp[t]:tp[t + 1]]
+        assert got_first[t] == tp[t] + int(np.argmax(seg))
+    assert np.all(got_first[want_df == 0] >= 0x7F7F7F7F)
