@@ -112,3 +112,16 @@ def test_snapshot_round_trip(tmp_path):
         assert np.array_equal(back.idf_host, ix.idf_host) and np.array_equal(back.shard_df_host, ix.shard_df_host)
         assert back.struct().n_dense == ix.struct().n_dense and back.struct().n_codes == ix.struct().n_codes
         assert back.posting_bytes([0, 1, 5]) == ix.posting_bytes([0, 1, 5])
+
+
+def test_pack_queries_shapes_and_edge_cases():
+    """pack_queries: CSR of the term lists (duplicates and -1 kept, empty queries allowed, an all-empty
+    batch still hands back a valid one-element term array)."""
+    from classmate_rag_b200 import lexical
+    flat, ptr = lexical.pack_queries([[5, 5, -1], [], [7], (1, 2)])
+    assert flat.dtype == torch.int32 and ptr.dtype == torch.int32
+    assert flat.tolist() == [5, 5, -1, 7, 1, 2] and ptr.tolist() == [0, 3, 3, 4, 6]
+    flat, ptr = lexical.pack_queries([[], []])
+    assert ptr.tolist() == [0, 0, 0] and flat.numel() == 1
+    flat, ptr = lexical.pack_queries([np.array([3, 4], dtype=np.int64)])
+    assert flat.tolist() == [3, 4] and ptr.tolist() == [0, 2]
