@@ -756,12 +756,13 @@ def main():
         except Exception as exc:
             dropin = {"error": repr(exc)}
 
-    # kernels per step (resident loop): f32 -> bf16 of the queries; dense = sample pass, bound, main pass,
-    # finalize (tcgen05 path) or scan, finalize; gather, mmr; BM25 head path = prep + per block of 32 queries
-    # (bucket, sample, bound, main, finalize) + the exact kernels' two launches (their CTAs leave at once unless a
-    # query was flagged), or tile + finalize; fuse; sharded: + pack, merge
-    bm_launches = (1 + 5 * n_blocks + 2) if head_path else 2
-    launches_per_step = 1 + (4 if a.batch > 8 else 2) + 2 + bm_launches + 1 + (2 if world > 1 else 0)
+    # kernels per step (resident loop; matches the ncu launch lists in profiles/): f32 -> bf16 of the queries;
+    # dense = sample pass, bound, main pass, finalize (tcgen05 path) or scan, finalize; gather (single shard), mmr;
+    # BM25 head path = prep + per GROUP of up to 4 blocks of 32 queries (bucket, sample, bound, main, finalize)
+    # + the exact kernels' two launches (their CTAs leave at once unless a query was flagged), or tile + finalize;
+    # fuse; sharded: pack + merge instead of gather
+    bm_launches = (1 + 5 * ((n_blocks + 3) // 4) + 2) if head_path else 2
+    launches_per_step = 1 + (4 if a.batch > 8 else 2) + (2 if world == 1 else 1) + bm_launches + 1 + (2 if world > 1 else 0)
     exchange = None
     if world > 1:
         exchange = {"transport": "p2p" if comm.peer is not None else "nccl", "peer_error": comm.peer_error,
